@@ -1,0 +1,181 @@
+"""Mint golden vectors from the IMPORTED reference (runs only where /root/reference exists).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Usage (from the repo root):
+
+    PYTHONDONTWRITEBYTECODE=1 python -m oracle.gen_golden
+
+The reference is imported from /root/reference (never copied); fastcluster/umap/hdbscan
+are stubbed in sys.modules because speakerlab/process/cluster.py:10-20 imports them at
+module scope and SpectralCluster uses none of them.  Inputs and weights are NOT stored:
+they are regenerated from seeds by oracle/synth.py on both sides.  Outputs go to
+tests/golden/*.npz together with the library versions that produced them.
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = os.environ.get("SPK_REFERENCE", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference():
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    for name in ("fastcluster", "umap", "hdbscan"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    from speakerlab.process.processor import FBank
+    from speakerlab.models.campplus.DTDNN import CAMPPlus
+    from speakerlab.process.cluster import SpectralCluster
+    return FBank, CAMPPlus, SpectralCluster
+
+
+def versions():
+    import scipy, sklearn, torch, torchaudio
+    return json.dumps(dict(numpy=np.__version__, torch=torch.__version__, torchaudio=torchaudio.__version__,
+                           scipy=scipy.__version__, sklearn=sklearn.__version__))
+
+
+# the input cases; tests regenerate them with the same calls
+def fbank_cases():
+    from oracle import synth
+    wav, _ = synth.fm_meeting(12.0, 3, seed=11)
+    cases = {
+        "noise_1p5s": synth.white_noise(2, 24000, seed=1),
+        "noise_3s": synth.white_noise(1, 48000, seed=2),
+        "fm_1p5s": synth.cut_windows(wav, synth.chunk(0.0, 12.0)[:3]),
+        "one_frame": synth.white_noise(1, 400, seed=3),
+        "ragged_559": synth.white_noise(1, 559, seed=4),
+        "ragged_560": synth.white_noise(1, 560, seed=5),
+        "loud": synth.white_noise(1, 8000, seed=6, scale=0.9),
+        "silence_tail": np.concatenate([synth.white_noise(1, 4000, seed=7), np.zeros((1, 4000), np.float32)], axis=1),
+    }
+    return cases
+
+
+def campplus_cases():
+    """(name, embedding_size, batch, n_samples, weight seed, randomize_bn)"""
+    return [
+        ("e192_t148_bnrand", 192, 3, 24000, 101, True),
+        ("e512_t148_bnrand", 512, 2, 24000, 102, True),
+        ("e192_t298_bnrand", 192, 2, 48000, 103, True),   # T'=149 -> 2 seg-pooling windows
+        ("e192_t148_freshbn", 192, 2, 24000, 104, False),
+    ]
+
+
+def campplus_input(batch, n_samples, seed):
+    from oracle import synth
+    secs = n_samples / synth.FS
+    wav, _ = synth.fm_meeting(secs * (batch + 1), 3, seed=seed)
+    ch = [[i * secs * 0.5, i * secs * 0.5 + secs] for i in range(batch)]
+    return synth.cut_windows(wav, ch)
+
+
+def cluster_cases():
+    """(name, N, D, K, seed, ctor kwargs)"""
+    return [
+        ("n600_k4", 600, 192, 4, 21, dict(min_num_spks=1, max_num_spks=15, pval=0.012)),
+        ("n300_k3_default", 300, 64, 3, 22, dict()),
+        ("n1500_k6", 1500, 192, 6, 23, dict(min_num_spks=1, max_num_spks=15, pval=0.012)),
+    ]
+
+
+def cluster_input(n, d, k, seed):
+    rng = np.random.default_rng([seed, 0xC1])
+    centers = rng.standard_normal((k, d))
+    lab = rng.integers(0, k, n)
+    X = centers[lab] + 0.35 * rng.standard_normal((n, d))
+    return X.astype(np.float32), lab
+
+
+def main():
+    import torch
+    from oracle import synth
+    os.makedirs(OUT, exist_ok=True)
+    FBank, CAMPPlus, SpectralCluster = import_reference()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ver = versions()
+
+    # ---- fbank: reference fp32 and the same code on float64 input
+    fb = FBank(80, 16000, mean_nor=True)
+    fb_raw = FBank(80, 16000, mean_nor=False)
+    out = {"versions": ver}
+    for name, wavs in fbank_cases().items():
+        f32 = np.stack([fb(torch.from_numpy(w).unsqueeze(0)).numpy() for w in wavs])
+        f64 = np.stack([fb(torch.from_numpy(w).double().unsqueeze(0)).numpy() for w in wavs])
+        raw = np.stack([fb_raw(torch.from_numpy(w).unsqueeze(0)).numpy() for w in wavs])
+        # vmap form used by the diarization call sites must agree with the loop
+        vm = torch.vmap(fb)(torch.from_numpy(wavs).unsqueeze(1)).numpy()
+        assert np.array_equal(vm, f32), name
+        out[name + ".f32"] = f32
+        out[name + ".f64"] = f64
+        out[name + ".raw_f32"] = raw
+    np.savez_compressed(os.path.join(OUT, "fbank.npz"), **out)
+    print("fbank goldens:", {k: v.shape for k, v in out.items() if k != "versions"})
+
+    # ---- CAM++: state_dict layout + embeddings with seeded weights
+    layouts = {}
+    out = {"versions": ver}
+    for name, emb, batch, n_samples, wseed, bnrand in campplus_cases():
+        torch.manual_seed(0)
+        model = CAMPPlus(feat_dim=80, embedding_size=emb).eval()
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        layouts["campplus_e%d" % emb] = {k: list(v) for k, v in shapes.items()}
+        sd = synth.fill_state_dict(shapes, wseed, randomize_bn=bnrand)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        wavs = campplus_input(batch, n_samples, seed=wseed + 1000)
+        feats = torch.vmap(fb)(torch.from_numpy(wavs).unsqueeze(1))
+        taps = {}
+        hooks = []
+        for mod_name in ("head", "xvector.tdnn", "xvector.block1", "xvector.transit1", "xvector.block2",
+                         "xvector.transit2", "xvector.block3", "xvector.transit3", "xvector.stats"):
+            mod = model.get_submodule(mod_name)
+            hooks.append(mod.register_forward_hook(
+                lambda m, i, o, n=mod_name: taps.__setitem__(n, o.detach().clone())))
+        with torch.no_grad():
+            e = model(feats)
+        for h in hooks:
+            h.remove()
+        out[name + ".feats"] = feats.numpy()
+        out[name + ".emb"] = e.numpy()
+        for k, v in taps.items():
+            # per-tap fingerprint: mean, mean|x|, L2 norm  (full tensors would be MBs)
+            out[name + ".tap." + k] = np.array([v.mean().item(), v.abs().mean().item(),
+                                                v.double().norm().item()], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "campplus.npz"), **out)
+    with open(os.path.join(OUT, "state_dict_layouts.json"), "w") as f:
+        json.dump(layouts, f)
+    print("campplus goldens:", [k for k in out if k.endswith(".emb")])
+
+    # ---- SpectralCluster
+    out = {"versions": ver}
+    for name, n, d, k, seed, kw in cluster_cases():
+        X, _ = cluster_input(n, d, k, seed)
+        sc = SpectralCluster(**kw)
+        np.random.seed(0)
+        labels = sc(X.copy())
+        # stage goldens
+        A = sc.get_sim_mat(X)
+        P = sc.p_pruning(A.copy(), None)
+        sym = 0.5 * (P + P.T)
+        L = sc.get_laplacian(sym)
+        np.random.seed(0)
+        _, kk = sc.get_spec_embs(L)
+        import scipy.sparse.linalg
+        lambdas = scipy.sparse.linalg.eigsh(L, k=min(sc.max_num_spks + 1, n), which="SM")[0]
+        out[name + ".labels"] = labels.astype(np.int32)
+        out[name + ".k"] = np.array(kk)
+        out[name + ".lambdas"] = lambdas
+        out[name + ".nnz_per_row"] = (P != 0).sum(1).astype(np.int32)
+        out[name + ".lap_diag"] = np.diag(L).copy()
+        out[name + ".lap_fro"] = np.array(np.linalg.norm(L.astype(np.float64)))
+    np.savez_compressed(os.path.join(OUT, "cluster.npz"), **out)
+    print("cluster goldens:", {k: out[k].tolist() for k in out if k.endswith(".k")})
+
+
+if __name__ == "__main__":
+    main()

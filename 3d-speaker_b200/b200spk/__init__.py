@@ -1,0 +1,19 @@
+"""b200spk - B200-native (sm_100a) implementation of 3D-Speaker's embedding-extraction hot path.
+
+Python mirrors of the reference call sites over the C ABI of ``libb200spk.so``:
+
+    FBank            <- speakerlab.process.processor.FBank
+    CAMPPlus         <- speakerlab.models.campplus.DTDNN.CAMPPlus
+    SpectralCluster  <- speakerlab.process.cluster.SpectralCluster
+    EmbeddingExtractor: the batched fbank -> model loop of
+                     speakerlab/bin/infer_diarization.py:621-639 with host buffers in/out
+
+There is no CPU fallback: without the built library import of the compute classes fails, and
+without an sm_100 device every compute call raises ``SpkError``.
+"""
+from ._lib import SpkError, lib, LIB_PATH  # noqa: F401
+from .fbank import FBank, fbank_batch, num_frames  # noqa: F401
+from .campplus import CAMPPlus  # noqa: F401
+from .extract import EmbeddingExtractor  # noqa: F401
+
+__all__ = ["FBank", "CAMPPlus", "EmbeddingExtractor", "SpkError", "fbank_batch", "num_frames", "lib"]

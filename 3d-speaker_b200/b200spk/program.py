@@ -1,0 +1,128 @@
+"""Host-side compiler from an eval-mode network (a state_dict) to the library's fused-op list.
+
+Folds BatchNorm (running stats) into per-channel scale/shift, repacks convolution weights to
+``[Cout][KH][KW][Cin]`` (channels-last implicit-GEMM order), uploads parameters once through
+``spk_model_add_param`` and registers one op list per frame count through
+``spk_model_set_program``.  Activations are channels-last buffers in a caller-owned workspace.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+BN_EPS = 1e-5
+
+
+def fold_bn(sd, prefix, affine=True, eps=BN_EPS):
+    """Eval-mode BatchNorm as y = x*scale + shift."""
+    var = sd[prefix + ".running_var"].double()
+    mean = sd[prefix + ".running_mean"].double()
+    scale = 1.0 / torch.sqrt(var + eps)
+    if affine:
+        scale = scale * sd[prefix + ".weight"].double()
+    shift = -mean * scale
+    if affine:
+        shift = shift + sd[prefix + ".bias"].double()
+    return scale.float(), shift.float()
+
+
+def pack_conv2d(w):
+    """[Cout, Cin, KH, KW] -> [Cout, KH, KW, Cin]."""
+    return w.permute(0, 2, 3, 1).contiguous()
+
+
+def pack_conv1d(w):
+    """[Cout, Cin, K] -> [Cout, 1, K, Cin]."""
+    return w.permute(0, 2, 1).contiguous()
+
+
+class Model:
+    """Owns a ``spk_model_t`` handle, its uploaded parameters and per-T programs."""
+
+    def __init__(self, precision, device):
+        self.precision = precision
+        self.device = torch.device(device)
+        self.act_dtype = _lib.DT_BF16 if precision == _lib.PREC_BF16 else _lib.DT_F32
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().spk_model_create(C.byref(h), precision))
+        self.handle = h
+        self.programs = {}
+        self._ws = {}
+
+    def close(self):
+        if self.handle is not None and self.handle.value:
+            _lib.lib().spk_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def param(self, t):
+        t = t.detach().to(torch.float32).contiguous().cpu()
+        with torch.cuda.device(self.device):
+            return int(_lib.check(_lib.lib().spk_model_add_param(self.handle, C.c_void_p(t.data_ptr()), t.numel())))
+
+    def set_program(self, T, prog):
+        bufs = (_lib.SpkBuf * len(prog.bufs))(*prog.bufs)
+        ops = (_lib.SpkOp * len(prog.ops))(*prog.ops)
+        _lib.check(_lib.lib().spk_model_set_program(self.handle, int(T), bufs, len(prog.bufs), ops, len(prog.ops)))
+        self.programs[int(T)] = prog
+
+    def workspace(self, T, chunk):
+        key = (int(T), int(chunk))
+        ws = self._ws.get(key)
+        if ws is None:
+            n = int(_lib.check(_lib.lib().spk_model_workspace_bytes(self.handle, int(T), int(chunk))))
+            ws = torch.empty(max(n, 16), dtype=torch.uint8, device=self.device)
+            self._ws = {key: ws}     # keep one workspace alive
+        return ws
+
+    def forward(self, T, feats, emb_dim, chunk):
+        """feats [B,T,F] f32 contiguous CUDA -> emb [B,E] f32."""
+        B = feats.shape[0]
+        emb = torch.empty((B, emb_dim), dtype=torch.float32, device=feats.device)
+        chunk = max(1, min(int(chunk), max(B, 1)))
+        ws = self.workspace(T, chunk)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().spk_model_forward(self.handle, int(T), C.c_void_p(feats.data_ptr()), B,
+                                                    C.c_void_p(emb.data_ptr()), C.c_void_p(ws.data_ptr()),
+                                                    ws.numel(), chunk, _lib.current_stream_ptr()))
+        return emb
+
+    def read_buffer(self, T, name, chunk, n_segments):
+        """Widened copy of a named workspace buffer for the LAST sub-batch (per-layer parity)."""
+        prog = self.programs[int(T)]
+        bid = prog.names[name]
+        n = prog.bufs[bid].elems * n_segments
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        ws = self.workspace(T, chunk)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().spk_model_read_buffer(self.handle, int(T), bid, int(chunk), C.c_void_p(ws.data_ptr()),
+                                                        C.c_void_p(out.data_ptr()), n, _lib.current_stream_ptr()))
+        return out
+
+
+class Program:
+    """Op list + buffer table under construction."""
+
+    def __init__(self, feat_elems, emb_elems):
+        self.bufs = [_lib.SpkBuf(int(feat_elems), _lib.DT_F32, 0), _lib.SpkBuf(int(emb_elems), _lib.DT_F32, 0)]
+        self.names = {"feats": 0, "emb": 1}
+        self.ops = []
+
+    def buf(self, name, elems, dtype):
+        self.bufs.append(_lib.SpkBuf(int(elems), int(dtype), 0))
+        self.names[name] = len(self.bufs) - 1
+        return len(self.bufs) - 1
+
+    def op(self, kind, **kw):
+        self.ops.append(_lib.make_op(kind, **kw))
+
+
+def conv_out(n, k, s, p, d=1):
+    return (n + 2 * p - d * (k - 1) - 1) // s + 1

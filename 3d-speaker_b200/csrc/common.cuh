@@ -1,0 +1,69 @@
+// Shared helpers for libb200spk (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/b200spk.h"
+
+namespace spk {
+
+// ---- per-thread error message + global launch counter (api.cu)
+void set_error(const char *fmt, ...);
+extern std::atomic<int64_t> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define SPK_CUDA_OK(expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            spk::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                           __LINE__);                                                       \
+            return SPK_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+#define SPK_REQUIRE(cond, ...)           \
+    do {                                 \
+        if (!(cond)) {                   \
+            spk::set_error(__VA_ARGS__); \
+            return SPK_ERR_INVALID;      \
+        }                                \
+    } while (0)
+
+inline int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+        return SPK_ERR_CUDA;
+    }
+    count_launch();
+    return SPK_OK;
+}
+
+int require_device();   // SPK_OK when the current device is sm_100 (cached)
+int sm_count();
+
+// ---- dtype helpers
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+    return __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == SPK_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == SPK_ACT_CLAMP20) return fminf(fmaxf(v, 0.f), 20.f);
+    if (act == SPK_ACT_SILU) return v / (1.f + __expf(-v));
+    return v;
+}
+
+inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace spk

@@ -1,0 +1,456 @@
+// CUDA-core (fp32 FMA) kernels: the exact-fp32 precision mode of the network forward, plus
+// the small non-GEMM ops shared by both precision modes (stem conv, CAM gate, statistics
+// pooling, AFF blend).  All activations are channels-last.
+//
+// Reference semantics:
+//   conv + BN + act + residual    speakerlab/models/campplus/layers.py:40-67,193-196,209-253
+//   CAM context gate              speakerlab/models/campplus/layers.py:93-110
+//   statistics pooling            speakerlab/models/campplus/layers.py:26-32,
+//                                 speakerlab/models/eres2net/pooling_layers.py:47-55
+//   AFF blend                     speakerlab/models/eres2net/fusion.py:22-28
+#include "ops.cuh"
+
+namespace spk {
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ void load(const float *p, float (&v)[4]) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float *p, const float (&v)[4]) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec4<bf16> {
+    static __device__ __forceinline__ void load(const bf16 *p, float (&v)[4]) {
+        const uint2 t = *reinterpret_cast<const uint2 *>(p);
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162 *>(&t.x);
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162 *>(&t.y);
+        v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+    }
+    static __device__ __forceinline__ void store(bf16 *p, const float (&v)[4]) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+        uint2 t;
+        t.x = *reinterpret_cast<uint32_t *>(&a);
+        t.y = *reinterpret_cast<uint32_t *>(&b);
+        *reinterpret_cast<uint2 *>(p) = t;
+    }
+};
+
+// ------------------------------------------------------------------ generic conv (implicit GEMM)
+constexpr int BM = 64, BK = 16;
+
+template <typename TIn, typename TOut, typename TRes, int BN>
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(const ConvArgs a) {
+    constexpr int TN = BN / 16;          // columns per thread
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+
+    const int tid = threadIdx.x;
+    const long long m0 = (long long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+
+    // A-load assignment: row = tid/4, 4 consecutive k at (tid%4)*4
+    const int lrow = tid >> 2, lk = (tid & 3) * 4;
+    const long long lm = m0 + lrow;
+    const bool lrow_ok = lm < a.M;
+    int lb = 0, lho = 0, lwo = 0;
+    if (lrow_ok) {
+        const int hw = a.Ho * a.Wo;
+        lb = (int)(lm / hw);
+        const int r = (int)(lm - (long long)lb * hw);
+        lho = r / a.Wo;
+        lwo = r - lho * a.Wo;
+    }
+    const TIn *xin = static_cast<const TIn *>(a.x);
+    const float *wgt = static_cast<const float *>(a.w);
+    // B-load assignment: BN rows x 16 k, float4 per thread
+    const int brow = tid >> 2, bk = (tid & 3) * 4;
+
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][TN];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < a.K; k0 += BK) {
+        // ---- A tile
+        float av[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+            const int tap = k0 / a.Cin;
+            const int c = k0 - tap * a.Cin + lk;
+            const int kh = tap / a.KW, kw = tap - kh * a.KW;
+            const int hi = lho * a.sh - a.ph + kh * a.dh;
+            const int wi = lwo * a.sw - a.pw + kw * a.dw;
+            if (lrow_ok && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
+                const TIn *src = xin + (((long long)lb * a.H + hi) * a.W + wi) * a.in_ld + a.in_choff + c;
+                Vec4<TIn>::load(src, av);
+                if (a.pro_scale != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        av[i] = fmaf(av[i], __ldg(a.pro_scale + c + i), __ldg(a.pro_shift + c + i));
+                        if (a.pro_relu) av[i] = fmaxf(av[i], 0.f);
+                    }
+                }
+            }
+        }
+        // ---- B tile
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (brow < BN && n0 + brow < a.Cout) {
+            const float4 t = __ldg(reinterpret_cast<const float4 *>(wgt + (long long)(n0 + brow) * a.K + k0 + bk));
+            bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+        }
+        __syncthreads();   // previous tile fully consumed
+#pragma unroll
+        for (int i = 0; i < 4; ++i) As[lk + i][lrow] = av[i];
+        if (brow < BN) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Bs[bk + i][brow] = bv[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float ar[4] = {a4.x, a4.y, a4.z, a4.w};
+            float br[TN];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) br[j] = Bs[k][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+    }
+
+    // ---- epilogue: affine, residual, activation, gate
+    TOut *yout = static_cast<TOut *>(a.y);
+    const TRes *res = static_cast<const TRes *>(a.res);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= a.M) continue;
+        const float *grow = nullptr;
+        if (a.gate != nullptr) {
+            const int hw = a.Ho * a.Wo;
+            const int b = (int)(m / hw);
+            const int wo = (int)(m % a.Wo);
+            grow = a.gate + ((long long)b * a.gate_nwin + wo / a.gate_win) * a.Cout;
+        }
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int n = n0 + tx * TN + j;
+            if (n >= a.Cout) continue;
+            float v = acc[i][j];
+            if (a.epi_scale != nullptr) v = fmaf(v, __ldg(a.epi_scale + n), __ldg(a.epi_shift + n));
+            if (res != nullptr) v += to_f32(res[m * a.res_ld + a.res_choff + n]);
+            v = apply_act(v, a.act);
+            if (grow != nullptr) v *= __ldg(grow + n);
+            yout[m * a.out_ld + a.out_choff + n] = from_f32<TOut>(v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ stem: Conv2d(1->Cout,3x3,p=1)+BN+ReLU
+// feats [B,T,F] is the image [H=F, W=T] with one channel (DTDNN.py:40-41,112).  Each thread
+// produces 4 output channels of one pixel; consecutive threads cover consecutive channels, so
+// a warp writes whole pixels contiguously.
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+stem_kernel(const StemArgs a) {
+    extern __shared__ float sw[];   // [Cout*9] weights, [Cout] scale, [Cout] shift
+    float *ssc = sw + a.Cout * 9, *ssh = ssc + a.Cout;
+    for (int i = threadIdx.x; i < a.Cout * 9; i += blockDim.x) sw[i] = a.w[i];
+    for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) {
+        ssc[i] = a.scale ? a.scale[i] : 1.f;
+        ssh[i] = a.shift ? a.shift[i] : 0.f;
+    }
+    __syncthreads();
+    const int cg = a.Cout / 4;
+    const long long total = (long long)a.B * a.F * a.T * cg;
+    TOut *y = static_cast<TOut *>(a.y);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(idx % cg) * 4;
+        const long long pix = idx / cg;             // (b, f, t)
+        const int t = (int)(pix % a.T);
+        const long long bf = pix / a.T;
+        const int f = (int)(bf % a.F);
+        const long long b = bf / a.F;
+        float in[3][3];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int ff = f + kh - 1, tt = t + kw - 1;
+                in[kh][kw] = (ff >= 0 && ff < a.F && tt >= 0 && tt < a.T)
+                                 ? __ldg(a.feats + (b * a.T + tt) * a.F + ff) : 0.f;
+            }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float *w = sw + (c0 + j) * 9;
+            float s = 0.f;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) s = fmaf(in[kh][kw], w[kh * 3 + kw], s);
+            o[j] = apply_act(fmaf(s, ssc[c0 + j], ssh[c0 + j]), a.act);
+        }
+        Vec4<TOut>::store(y + pix * a.out_ld + a.out_choff + c0, o);
+    }
+}
+
+// ------------------------------------------------------------------ CAM context gate
+// gate[b,w,:] = sigmoid(W2 relu(W1 (mean_T(x) + mean_{window w}(x)) + b1) + b2); one CTA per
+// segment, thread c owns channel c for the reductions (coalesced rows).
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+cam_gate_kernel(const CamGateArgs a) {
+    extern __shared__ float sh[];
+    float *tot = sh;                       // [C]
+    float *win = tot + a.C;                // [nwin][C]
+    float *ctx = win + a.nwin * a.C;       // [C]
+    float *hid = ctx + a.C;                // [hidden]
+    const int b = blockIdx.x;
+    const TIn *x = static_cast<const TIn *>(a.x) + (long long)b * a.T * a.in_ld + a.in_choff;
+    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+        float t = 0.f;
+        for (int w = 0; w < a.nwin; ++w) {
+            const int t0 = w * a.seg_len, t1 = min(a.T, t0 + a.seg_len);
+            float s = 0.f;
+            for (int i = t0; i < t1; ++i) s += to_f32(x[(long long)i * a.in_ld + c]);
+            win[w * a.C + c] = s / (float)(t1 - t0);
+            t += s;
+        }
+        tot[c] = t / (float)a.T;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int w = 0; w < a.nwin; ++w) {
+        for (int c = threadIdx.x; c < a.C; c += blockDim.x) ctx[c] = tot[c] + win[w * a.C + c];
+        __syncthreads();
+        for (int j = warp; j < a.hidden; j += nwarps) {
+            float s = 0.f;
+            for (int c = lane; c < a.C; c += 32) s = fmaf(__ldg(a.w1 + (long long)j * a.C + c), ctx[c], s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) hid[j] = fmaxf(s + __ldg(a.b1 + j), 0.f);
+        }
+        __syncthreads();
+        for (int o = warp; o < a.Cout; o += nwarps) {
+            float s = 0.f;
+            for (int j = lane; j < a.hidden; j += 32) s = fmaf(__ldg(a.w2 + (long long)o * a.hidden + j), hid[j], s);
+#pragma unroll
+            for (int q = 16; q > 0; q >>= 1) s += __shfl_xor_sync(0xffffffffu, s, q);
+            if (lane == 0) {
+                const float v = s + __ldg(a.b2 + o);
+                a.gate[((long long)b * a.nwin + w) * a.Cout + o] = 1.f / (1.f + expf(-v));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------ statistics pooling
+// x [B,G,P,ld] -> y[b] = [mean(G,C) | std(G,C)].  Lanes own consecutive channels (coalesced);
+// the P positions of one (b,g) are split over the 8 warps of a CTA and combined with the
+// pairwise (Chan) mean/M2 update, which is the Welford recurrence for merged partitions.
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+stats_pool_kernel(const StatsPoolArgs a) {
+    __shared__ float s_mean[8][32], s_m2[8][32];
+    __shared__ int s_n[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const int g = blockIdx.y;
+    const long long b = blockIdx.z;
+    const TIn *x = static_cast<const TIn *>(a.x) + ((b * a.G + g) * a.P) * (long long)a.in_ld + a.in_choff;
+    float mean = 0.f, m2 = 0.f;
+    int n = 0;
+    if (c < a.C) {
+        for (int p = warp; p < a.P; p += 8) {
+            const float v = to_f32(x[(long long)p * a.in_ld + c]);
+            ++n;
+            const float d = v - mean;
+            mean += d / (float)n;
+            m2 = fmaf(d, v - mean, m2);
+        }
+    } else {
+        for (int p = warp; p < a.P; p += 8) ++n;
+    }
+    s_mean[warp][lane] = mean;
+    s_m2[warp][lane] = m2;
+    if (lane == 0) s_n[warp] = n;
+    __syncthreads();
+    if (warp == 0 && c < a.C) {
+        float mu = s_mean[0][lane], M2 = s_m2[0][lane];
+        int cnt = s_n[0];
+        for (int w = 1; w < 8; ++w) {
+            const int nb = s_n[w];
+            if (nb == 0) continue;
+            const float d = s_mean[w][lane] - mu;
+            const int tot = cnt + nb;
+            mu += d * (float)nb / (float)tot;
+            M2 += s_m2[w][lane] + d * d * (float)cnt * (float)nb / (float)tot;
+            cnt = tot;
+        }
+        const float denom = a.unbiased ? (float)(a.P - 1) : (float)a.P;
+        const float var = M2 / denom;
+        float *y = a.y + b * 2ll * a.G * a.C;
+        y[(long long)g * a.C + c] = mu;
+        y[(long long)(a.G + g) * a.C + c] = sqrtf(var + a.eps);
+    }
+}
+
+// ------------------------------------------------------------------ AFF blend
+template <typename T>
+__global__ void __launch_bounds__(256)
+aff_blend_kernel(const AffBlendArgs a) {
+    const int cg = a.C / 4;
+    const long long total = a.M * cg;
+    const T *x = static_cast<const T *>(a.x), *y = static_cast<const T *>(a.y), *z = static_cast<const T *>(a.z);
+    T *o = static_cast<T *>(a.out);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % cg) * 4;
+        const long long m = idx / cg;
+        float xv[4], yv[4], zv[4], ov[4];
+        Vec4<T>::load(x + m * a.x_ld + a.x_choff + c, xv);
+        Vec4<T>::load(y + m * a.y_ld + a.y_choff + c, yv);
+        Vec4<T>::load(z + m * a.z_ld + a.z_choff + c, zv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float gq = 1.f + tanhf(zv[i]);
+            ov[i] = xv[i] * gq + yv[i] * (2.f - gq);
+        }
+        Vec4<T>::store(o + m * a.out_ld + a.out_choff + c, ov);
+    }
+}
+
+__global__ void f32_to_bf16_kernel(const float *__restrict__ s, bf16 *__restrict__ d, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        d[i] = __float2bfloat16_rn(s[i]);
+}
+template <typename T>
+__global__ void widen_kernel(const T *__restrict__ s, float *__restrict__ d, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        d[i] = to_f32(s[i]);
+}
+
+int grid_for(long long work, int threads) {
+    long long g = (work + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+template <typename TIn, typename TOut, typename TRes>
+int conv_simt_dispatch(const ConvArgs &a, cudaStream_t s) {
+    const long long mt = (a.M + BM - 1) / BM;
+    if (mt > 0x7fffffffll) {
+        set_error("conv: too many output tiles");
+        return SPK_ERR_UNSUPPORTED;
+    }
+    if (a.Cout <= 32) {
+        dim3 grid((unsigned)mt, (a.Cout + 31) / 32);
+        conv_simt_kernel<TIn, TOut, TRes, 32><<<grid, 256, 0, s>>>(a);
+    } else {
+        dim3 grid((unsigned)mt, (a.Cout + 63) / 64);
+        conv_simt_kernel<TIn, TOut, TRes, 64><<<grid, 256, 0, s>>>(a);
+    }
+    return check_launch("conv_simt_kernel");
+}
+
+}  // namespace
+
+int launch_conv_simt(const ConvArgs &a, int in_dtype, int out_dtype, int res_dtype, cudaStream_t s) {
+    if (a.Cin % BK != 0 || a.in_ld % 4 != 0 || a.in_choff % 4 != 0) {
+        set_error("conv_simt: Cin=%d must be a multiple of %d and channel offsets 4-aligned", a.Cin, BK);
+        return SPK_ERR_UNSUPPORTED;
+    }
+    if (a.M == 0) return SPK_OK;
+    const int key = in_dtype * 100 + out_dtype * 10 + (a.res ? res_dtype : out_dtype);
+    switch (key) {
+        case 0:   return conv_simt_dispatch<float, float, float>(a, s);
+        case 11:  return conv_simt_dispatch<float, bf16, bf16>(a, s);
+        case 100: return conv_simt_dispatch<bf16, float, float>(a, s);
+        case 111: return conv_simt_dispatch<bf16, bf16, bf16>(a, s);
+        default:
+            set_error("conv_simt: unsupported dtype combination in=%d out=%d res=%d", in_dtype, out_dtype, res_dtype);
+            return SPK_ERR_UNSUPPORTED;
+    }
+}
+
+int launch_stem(const StemArgs &a, int out_dtype, cudaStream_t s) {
+    if (a.Cout % 4 != 0 || a.out_ld % 4 != 0 || a.out_choff % 4 != 0) {
+        set_error("stem: Cout and channel pitch must be multiples of 4");
+        return SPK_ERR_UNSUPPORTED;
+    }
+    const long long work = (long long)a.B * a.F * a.T * (a.Cout / 4);
+    if (work == 0) return SPK_OK;
+    const size_t sh = (size_t)a.Cout * 11 * sizeof(float);
+    if (out_dtype == SPK_DT_F32) stem_kernel<float><<<grid_for(work, 256), 256, sh, s>>>(a);
+    else stem_kernel<bf16><<<grid_for(work, 256), 256, sh, s>>>(a);
+    return check_launch("stem_kernel");
+}
+
+int launch_cam_gate(const CamGateArgs &a, int in_dtype, cudaStream_t s) {
+    if (a.B == 0) return SPK_OK;
+    const size_t sh = ((size_t)a.C * (a.nwin + 2) + a.hidden) * sizeof(float);
+    if (sh > 48 * 1024) {
+        set_error("cam_gate: %d windows x %d channels exceed shared memory", a.nwin, a.C);
+        return SPK_ERR_UNSUPPORTED;
+    }
+    if (in_dtype == SPK_DT_F32) cam_gate_kernel<float><<<a.B, 128, sh, s>>>(a);
+    else cam_gate_kernel<bf16><<<a.B, 128, sh, s>>>(a);
+    return check_launch("cam_gate_kernel");
+}
+
+int launch_stats_pool(const StatsPoolArgs &a, int in_dtype, cudaStream_t s) {
+    if (a.B == 0) return SPK_OK;
+    if (a.G > 65535 || a.B > 65535) {
+        set_error("stats_pool: grid too large (G=%d, B=%d)", a.G, a.B);
+        return SPK_ERR_UNSUPPORTED;
+    }
+    dim3 grid((a.C + 31) / 32, a.G, a.B);
+    if (in_dtype == SPK_DT_F32) stats_pool_kernel<float><<<grid, 256, 0, s>>>(a);
+    else stats_pool_kernel<bf16><<<grid, 256, 0, s>>>(a);
+    return check_launch("stats_pool_kernel");
+}
+
+int launch_aff_blend(const AffBlendArgs &a, int dtype, cudaStream_t s) {
+    if (a.C % 4 != 0) {
+        set_error("aff_blend: C must be a multiple of 4");
+        return SPK_ERR_UNSUPPORTED;
+    }
+    const long long work = a.M * (a.C / 4);
+    if (work == 0) return SPK_OK;
+    if (dtype == SPK_DT_F32) aff_blend_kernel<float><<<grid_for(work, 256), 256, 0, s>>>(a);
+    else aff_blend_kernel<bf16><<<grid_for(work, 256), 256, 0, s>>>(a);
+    return check_launch("aff_blend_kernel");
+}
+
+int launch_f32_to_bf16(const float *src, __nv_bfloat16 *dst, long long n, cudaStream_t s) {
+    if (n == 0) return SPK_OK;
+    f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, s>>>(src, dst, n);
+    return check_launch("f32_to_bf16_kernel");
+}
+
+int launch_widen(const void *src, int dtype, float *dst, long long n, cudaStream_t s) {
+    if (n == 0) return SPK_OK;
+    if (dtype == SPK_DT_F32) widen_kernel<float><<<grid_for(n, 256), 256, 0, s>>>(static_cast<const float *>(src), dst, n);
+    else widen_kernel<bf16><<<grid_for(n, 256), 256, 0, s>>>(static_cast<const bf16 *>(src), dst, n);
+    return check_launch("widen_kernel");
+}
+
+}  // namespace spk

@@ -1,0 +1,65 @@
+// Internal launch interface between the op-list interpreter (model.cu) and the kernels.
+#pragma once
+#include "common.cuh"
+
+namespace spk {
+
+struct ConvArgs {
+    const void *x;        // [B,H,W,in_ld] channels-last, first channel in_choff
+    const void *w;        // packed [Cout][KH][KW][Cin] (f32 for SIMT, bf16 for the tcgen05 path)
+    void *y;              // [B,Ho,Wo,out_ld]
+    const void *res;      // optional residual [B,Ho,Wo,res_ld]
+    const float *gate;    // optional [B, gate_nwin, Cout]
+    const float *pro_scale, *pro_shift, *epi_scale, *epi_shift;
+    int B, H, W, Cin, Ho, Wo, Cout;
+    int KH, KW, sh, sw, ph, pw, dh, dw;
+    int in_ld, in_choff, out_ld, out_choff, res_ld, res_choff;
+    int gate_win, gate_nwin, pro_relu, act;
+    int K;                // KH*KW*Cin
+    long long M;          // B*Ho*Wo
+};
+
+// fp32-accumulate CUDA-core implicit GEMM (exact-fp32 mode and odd shapes)
+int launch_conv_simt(const ConvArgs &a, int in_dtype, int out_dtype, int res_dtype, cudaStream_t s);
+// tcgen05 / TMEM implicit GEMM, bf16 operands (conv_tc.cu); SPK_ERR_UNSUPPORTED when the shape
+// does not qualify
+int launch_conv_tc(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s);
+bool conv_tc_supported(const ConvArgs &a, int in_dtype);
+
+struct StemArgs {
+    const float *feats;   // [B,T,F]
+    const float *w;       // [Cout][3][3]  (kh over F, kw over T)
+    const float *scale, *shift;
+    void *y;              // [B,F,T,out_ld]
+    int B, T, F, Cout, out_ld, out_choff, act;
+};
+int launch_stem(const StemArgs &a, int out_dtype, cudaStream_t s);
+
+struct CamGateArgs {
+    const void *x;        // [B,T,in_ld] (post BN-ReLU bottleneck)
+    float *gate;          // [B,nwin,Cout]
+    const float *w1, *b1, *w2, *b2;   // [hidden,C],[hidden],[Cout,hidden],[Cout]
+    int B, T, C, in_ld, in_choff, hidden, Cout, seg_len, nwin;
+};
+int launch_cam_gate(const CamGateArgs &a, int in_dtype, cudaStream_t s);
+
+struct StatsPoolArgs {
+    const void *x;        // [B,G,P,in_ld]
+    float *y;             // [B, 2, G, C]  (mean block then std block)
+    int B, G, P, C, in_ld, in_choff, unbiased;
+    float eps;            // std = sqrt(var + eps)
+};
+int launch_stats_pool(const StatsPoolArgs &a, int in_dtype, cudaStream_t s);
+
+struct AffBlendArgs {
+    const void *x, *y, *z;   // [M, ld] each; out = x*g + y*(2-g), g = 1 + tanh(z)
+    void *out;
+    long long M;
+    int C, x_ld, x_choff, y_ld, y_choff, z_ld, z_choff, out_ld, out_choff;
+};
+int launch_aff_blend(const AffBlendArgs &a, int dtype, cudaStream_t s);
+
+int launch_f32_to_bf16(const float *src, __nv_bfloat16 *dst, long long n, cudaStream_t s);
+int launch_widen(const void *src, int dtype, float *dst, long long n, cudaStream_t s);
+
+}  // namespace spk

@@ -1,0 +1,160 @@
+/* b200spk.h - C ABI of libb200spk.so, the sm_100a implementation of 3D-Speaker's
+ * embedding-extraction hot path (waveform -> Kaldi fbank+CMN -> speaker network forward ->
+ * cosine affinity + spectral clustering).
+ *
+ * The reference has no FFI for this path: the boundary is a set of Python objects resolved by
+ * dotted name (speakerlab/utils/builder.py:9-12,52-60).  Each entry point below names the
+ * reference interface whose arithmetic it replaces; the Python mirrors of those interfaces
+ * (3d-speaker_b200/b200spk/) call these through ctypes with tensor.data_ptr() + the current
+ * CUDA stream.  See INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions: plain pointers and sizes only; every function returns SPK_OK (0) or a negative
+ * SPK_ERR_* code and never throws; spk_last_error() gives the message for the calling thread.
+ * Device entry points are asynchronous on the caller's stream (a cudaStream_t passed as void*)
+ * and never synchronise; the caller owns every device buffer including the workspace.
+ * *_host entry points take HOST buffers, do their own H2D/D2H and return when results are in
+ * host memory.  There is no CPU fallback anywhere: without an sm_100 device the compute entry
+ * points return SPK_ERR_NO_DEVICE.
+ */
+#ifndef B200SPK_H_
+#define B200SPK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPK_OK                 0
+#define SPK_ERR_INVALID       -1   /* bad argument (the reference would trip a Python assert) */
+#define SPK_ERR_CUDA          -2   /* CUDA runtime / launch failure                          */
+#define SPK_ERR_UNSUPPORTED   -3   /* shape or mode not implemented                          */
+#define SPK_ERR_WORKSPACE     -4   /* caller-provided workspace too small                    */
+#define SPK_ERR_NO_DEVICE     -5   /* no sm_100 CUDA device                                  */
+#define SPK_ERR_KERNEL        -6   /* a kernel reported an internal error (watchdog)         */
+
+#define SPK_ABI_VERSION        1
+
+/* ------------------------------------------------------------------ library */
+int         spk_abi_version(void);
+const char *spk_last_error(void);
+/* SPK_OK when device 'dev' exists and is compute capability 10.x */
+int         spk_device_check(int dev);
+
+/* ------------------------------------------------------------------ front end
+ * Replaces FBank.__call__ (speakerlab/process/processor.py:143-158) =
+ * torchaudio.compliance.kaldi.fbank(num_mel_bins, sample_frequency=16000, dither=0)
+ * (+ utterance CMN when mean_nor), in its batched torch.vmap form
+ * (speakerlab/bin/infer_diarization.py:634).
+ */
+/* 1 + (n-400)/160, or 0 when n < 400 (kaldi.py:67) */
+int64_t spk_fbank_num_frames(int64_t n_samples);
+/* Optional: replace the built-in povey window [400] and mel bank [n_mels,256] with tables the
+ * host computed (the Python mirror passes torchaudio-arithmetic tables so weights agree to
+ * the last bit).  Host pointers; copied.  NULL keeps the built-in table. */
+int spk_fbank_set_tables(const float *window400, const float *mel_bank, int n_mels);
+/* wav: device, B rows of n_samples floats in [-1,1] scale, row stride wav_stride (elements).
+ * out: device, [B, m, n_mels] contiguous.  n_samples >= 400 (kaldi.py:142). */
+int spk_fbank_f32(const float *wav, int64_t B, int64_t n_samples, int64_t wav_stride,
+                  float *out, int n_mels, int mean_nor, void *stream);
+/* Same, host buffers in / host buffers out (pageable or pinned). */
+int spk_fbank_host_f32(const float *wav, int64_t B, int64_t n_samples, int64_t wav_stride,
+                       float *out, int n_mels, int mean_nor);
+
+/* ------------------------------------------------------------------ network forward
+ * Replaces nn.Module.forward of the embedding models
+ * (CAMPPlus.forward speakerlab/models/campplus/DTDNN.py:111-115;
+ *  ERes2NetV2.forward speakerlab/models/eres2net/ERes2NetV2.py:235-254) in eval mode.
+ * The host mirror folds eval-mode BatchNorm into per-channel scale/shift, repacks conv
+ * weights to [Cout][KH][KW][Cin] and describes the network as a list of fused ops over
+ * channels-last activation buffers; the library owns the device copy of the parameters and
+ * runs the op list with its own kernels.
+ */
+typedef struct spk_model spk_model_t;
+
+enum { SPK_PREC_F32 = 0, SPK_PREC_BF16 = 1 };
+enum { SPK_DT_F32 = 0, SPK_DT_BF16 = 1 };
+
+/* activation buffer: elems per segment; ids 0 (input feats [T,F] f32) and 1 (embedding f32)
+ * are bound to the caller's pointers at forward time, the rest live in the workspace */
+typedef struct {
+    int64_t elems;
+    int32_t dtype;     /* SPK_DT_* */
+    int32_t reserved;
+} spk_buf_t;
+
+enum {
+    SPK_OP_STEM       = 1,  /* conv2d 1->Cout 3x3 pad 1 on feats[T,F] read as image [F,T] + affine + relu */
+    SPK_OP_CONV       = 2,  /* generic NHWC conv as implicit GEMM with fused prologue/epilogue        */
+    SPK_OP_CAM_GATE   = 3,  /* CAM context: mean_T + seg-mean -> 1x1 -> relu -> 1x1 -> sigmoid        */
+    SPK_OP_STATS_POOL = 4,  /* mean / std over positions                                             */
+    SPK_OP_AFF_BLEND  = 5   /* x*g + y*(2-g), g = 1+tanh(z)  (fusion.py:22-28)                        */
+};
+enum { SPK_ACT_NONE = 0, SPK_ACT_RELU = 1, SPK_ACT_CLAMP20 = 2, SPK_ACT_SILU = 3 };
+
+typedef struct {
+    int32_t kind;
+    int32_t in_buf, in_ld, in_choff;       /* buffer id, elems per pixel, first channel   */
+    int32_t out_buf, out_ld, out_choff;
+    int32_t res_buf, res_ld, res_choff;    /* residual added before the activation, or -1 */
+    int32_t gate_buf, gate_win;            /* per-(segment, window, channel) multiplier, or -1 */
+    int32_t H, W, Cin, Ho, Wo, Cout;
+    int32_t KH, KW, sh, sw, ph, pw, dh, dw;
+    int32_t w;                             /* parameter ids (spk_model_add_param), -1 = none */
+    int32_t pro_scale, pro_shift, pro_relu;/* per-input-channel affine (+relu) on the A operand */
+    int32_t epi_scale, epi_shift, act;     /* per-output-channel affine, activation          */
+    int32_t aux[4];                        /* CAM_GATE: w1,b1,w2,b2                          */
+    int32_t iaux[4];                       /* CAM_GATE: hidden, seg_len; STATS_POOL: unbiased */
+    float   faux[2];                       /* STATS_POOL: eps inside sqrt                    */
+} spk_op_t;
+
+int     spk_model_create(spk_model_t **out, int precision);
+int     spk_model_destroy(spk_model_t *m);
+/* copy n floats (host) into the model's device arena; returns the parameter id (>=0) */
+int64_t spk_model_add_param(spk_model_t *m, const float *host, int64_t n);
+/* register the op list for segments of T frames (replaces an earlier program for the same T) */
+int     spk_model_set_program(spk_model_t *m, int64_t T, const spk_buf_t *bufs, int32_t n_bufs,
+                              const spk_op_t *ops, int32_t n_ops);
+/* bytes of workspace spk_model_forward needs for sub-batches of 'chunk' segments */
+int64_t spk_model_workspace_bytes(spk_model_t *m, int64_t T, int64_t chunk);
+/* feats: device [B,T,F] f32 contiguous; emb: device [B,E] f32.  B is processed in sub-batches
+ * of at most 'chunk' segments so activations stay L2-resident. */
+int     spk_model_forward(spk_model_t *m, int64_t T, const float *feats, int64_t B, float *emb,
+                          void *workspace, int64_t workspace_bytes, int64_t chunk, void *stream);
+/* debugging / per-layer parity: copy the first n elements of workspace buffer 'buf_id' of the
+ * LAST sub-batch into dst (device pointer, f32; bf16 buffers are widened) */
+int     spk_model_read_buffer(spk_model_t *m, int64_t T, int32_t buf_id, int64_t chunk,
+                              const void *workspace, float *dst, int64_t n, void *stream);
+/* kernels launched by spk_* calls since process start (bench.py's gpu_launches) */
+int64_t spk_launch_count(void);
+
+/* ------------------------------------------------------------------ back end
+ * Replaces SpectralCluster.__call__ (speakerlab/process/cluster.py:35-57).
+ */
+/* X: device [N,D] f32 (rows need not be normalised).  Writes the unnormalised Laplacian
+ * L = D - M of the p-pruned, symmetrised cosine affinity (cluster.py:59-84) as dense [N,N] f32.
+ * keep = N - n_elems entries survive per row (cluster.py:67-68). */
+int spk_affinity_laplacian(const float *X, int64_t N, int64_t D, int64_t keep, float *L,
+                           void *workspace, int64_t workspace_bytes, void *stream);
+int64_t spk_affinity_workspace_bytes(int64_t N, int64_t D);
+/* k smallest eigenpairs of symmetric PSD L (device [N,N] f32) by block Lanczos on sigma*I - L
+ * (replaces scipy eigsh(which='SM'), cluster.py:90).  evals: host [k] ascending; evecs: device
+ * [N,k] column j = eigenvector j (row-major [N,k]).  Synchronises the stream. */
+int spk_eig_smallest(const float *L, int64_t N, int32_t k, float *evals_host, float *evecs,
+                     void *workspace, int64_t workspace_bytes, void *stream);
+int64_t spk_eig_workspace_bytes(int64_t N, int32_t k);
+/* Lloyd k-means on device points [N,d] f32 from caller-provided initial centres (host [k,d]);
+ * labels: device int32 [N].  Returns iterations run (>=0) or an error code. */
+int spk_kmeans(const float *pts, int64_t N, int32_t d, int32_t k, const float *init_centres_host,
+               int32_t max_iter, float tol, int32_t *labels, float *inertia_host,
+               void *workspace, int64_t workspace_bytes, void *stream);
+int64_t spk_kmeans_workspace_bytes(int64_t N, int32_t d, int32_t k);
+/* cosine score of trial pairs: out[i] = cos(E[a[i]], E[b[i]])
+ * (speakerlab/bin/compute_score_metrics.py:113-114) */
+int spk_cosine_pairs(const float *E, int64_t N, int64_t D, const int32_t *a, const int32_t *b,
+                     int64_t n_pairs, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPK_H_ */

@@ -1,0 +1,115 @@
+"""GPU: CAM++ forward through the C ABI vs the oracle and the golden vectors."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import b200spk
+from oracle import campplus_oracle, gen_golden, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "campplus.npz"))
+
+
+def _model(emb, wseed, bnrand, precision="fp32", chunk=None):
+    m = b200spk.CAMPPlus(embedding_size=emb, precision=precision, chunk=chunk)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = synth.fill_state_dict(shapes, wseed, randomize_bn=bnrand)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return m.cuda().eval(), sd
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def _cos_min(a, b):
+    num = (a * b).sum(1)
+    return float((num / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1))).min())
+
+
+@pytest.mark.parametrize("case", gen_golden.campplus_cases(), ids=lambda c: c[0])
+def test_fp32_vs_golden(gold, case):
+    name, emb, batch, n_samples, wseed, bnrand = case
+    model, _ = _model(emb, wseed, bnrand)
+    feats = torch.from_numpy(gold[name + ".feats"]).cuda()
+    with torch.no_grad():
+        got = model(feats).cpu().numpy()
+    ref = gold[name + ".emb"]
+    assert got.shape == ref.shape
+    # fp32 gate: rel-L2 (cosine alone passes real bugs on random-init weights)
+    assert _rel(got, ref) <= 1e-4, _rel(got, ref)
+    assert _cos_min(got, ref) >= 0.9999
+
+
+def test_fp32_per_layer_vs_oracle():
+    name, emb, batch, n_samples, wseed, bnrand = gen_golden.campplus_cases()[0]
+    model, sd = _model(emb, wseed, bnrand, chunk=8)
+    wavs = gen_golden.campplus_input(5, n_samples, seed=4242)
+    feats = b200spk.fbank_batch(torch.from_numpy(wavs).cuda())
+    taps = {}
+    ref = campplus_oracle.forward(sd, feats.cpu().numpy(), taps).numpy()
+    with torch.no_grad():
+        got = model(feats).cpu().numpy()
+    assert _rel(got, ref) <= 1e-4
+    eng = model._engine
+    B, T = feats.shape[0], feats.shape[1]
+    T2 = taps["xvector.tdnn"].shape[-1]
+    # channels-last workspace buffers vs the oracle's NCT taps
+    blk3 = eng.model.read_buffer(T, "block3", 8, B).view(B, T2, -1).permute(0, 2, 1).cpu().numpy()
+    assert _rel(blk3, taps["xvector.block3"].numpy()) <= 1e-4
+    blk1 = eng.model.read_buffer(T, "block1", 8, B).view(B, T2, -1).permute(0, 2, 1).cpu().numpy()
+    assert _rel(blk1, taps["xvector.block1"].numpy()) <= 1e-4
+    st = eng.model.read_buffer(T, "stats", 8, B).view(B, -1).cpu().numpy()
+    assert _rel(st, taps["xvector.stats"].numpy()) <= 1e-4
+
+
+def test_chunking_is_invisible():
+    name, emb, batch, n_samples, wseed, bnrand = gen_golden.campplus_cases()[0]
+    feats = b200spk.fbank_batch(torch.from_numpy(gen_golden.campplus_input(11, n_samples, seed=7)).cuda())
+    a, _ = _model(emb, wseed, bnrand, chunk=4)
+    b, _ = _model(emb, wseed, bnrand, chunk=64)
+    with torch.no_grad():
+        ea, eb = a(feats), b(feats)
+    assert torch.equal(ea, eb)             # ragged last sub-batch (11 = 4+4+3) and one-shot agree bit for bit
+
+
+def test_two_seg_windows_and_ragged_T():
+    # T=298 -> T'=149 -> 2 seg-pooling windows, the second partial (layers.py:100-110)
+    name, emb, batch, n_samples, wseed, bnrand = gen_golden.campplus_cases()[2]
+    model, sd = _model(emb, wseed, bnrand)
+    for n in (48000, 30000 + 160 * 3):
+        feats = b200spk.fbank_batch(torch.from_numpy(gen_golden.campplus_input(2, n, seed=9)).cuda())
+        ref = campplus_oracle.forward(sd, feats.cpu().numpy()).numpy()
+        with torch.no_grad():
+            got = model(feats).cpu().numpy()
+        assert _rel(got, ref) <= 1e-4
+
+
+def test_bf16_mode_vs_fp32():
+    name, emb, batch, n_samples, wseed, bnrand = gen_golden.campplus_cases()[0]
+    feats = b200spk.fbank_batch(torch.from_numpy(gen_golden.campplus_input(16, n_samples, seed=5)).cuda())
+    f32, sd = _model(emb, wseed, bnrand)
+    b16, _ = _model(emb, wseed, bnrand, precision="bf16")
+    ref = campplus_oracle.forward(sd, feats.cpu().numpy()).numpy()
+    with torch.no_grad():
+        e32, e16 = f32(feats).cpu().numpy(), b16(feats).cpu().numpy()
+    assert _cos_min(e16, ref) >= 0.999         # north-star bf16 tolerance vs the CPU reference path
+    assert _rel(e16, e32) <= 3e-2              # precision mode, validated against fp32-GPU
+
+
+def test_extractor_host_buffers_roundtrip():
+    name, emb, batch, n_samples, wseed, bnrand = gen_golden.campplus_cases()[0]
+    model, sd = _model(emb, wseed, bnrand)
+    wavs = torch.from_numpy(gen_golden.campplus_input(9, n_samples, seed=6)).pin_memory()
+    ex = b200spk.EmbeddingExtractor(b200spk.FBank(80, 16000, mean_nor=True), model, batchsize=4)
+    got = ex(wavs)
+    assert not got.is_cuda and got.shape == (9, emb)
+    dev = ex.extract_device(wavs.cuda()).cpu()
+    assert torch.equal(got, dev)

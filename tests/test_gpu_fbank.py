@@ -1,0 +1,121 @@
+"""GPU: fbank kernel through the C ABI vs the oracle and the golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import b200spk
+from oracle import fbank_oracle, gen_golden, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "fbank.npz"))
+
+
+def _run(wavs, mean_nor=True):
+    x = torch.from_numpy(np.ascontiguousarray(wavs)).cuda()
+    out = b200spk.fbank_batch(x, 80, mean_nor)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _two_sided(got, ref32, ref64):
+    """(A) as close to the fp64 truth as the reference's own fp32 path is
+    (never worse than 1e-4 unless ref-fp32 itself is), (B) within 1e-4 of ref-fp32 on
+    >= 99.9 % of elements."""
+    e_truth = np.abs(got - ref64)
+    ref_err = np.abs(ref32 - ref64).max()
+    assert e_truth.max() <= max(1e-4, 1.5 * ref_err), (e_truth.max(), ref_err)
+    assert e_truth.mean() <= 2e-6
+    assert (np.abs(got - ref32) > 1e-4).mean() <= 1e-3
+
+
+@pytest.mark.parametrize("case", list(gen_golden.fbank_cases().keys()))
+def test_fbank_vs_golden(gold, case):
+    wavs = gen_golden.fbank_cases()[case]
+    got = _run(wavs)
+    assert got.shape == gold[case + ".f32"].shape
+    _two_sided(got, gold[case + ".f32"], gold[case + ".f64"])
+
+
+def test_fbank_bounded_dynamic_range_strict(gold):
+    # speech-like input (FM speakers + -40 dB floor): strict max-abs vs the fp64 truth
+    got = _run(gen_golden.fbank_cases()["fm_1p5s"])
+    assert np.abs(got - gold["fm_1p5s.f64"]).max() <= 1e-4
+
+
+def test_fbank_no_cmn(gold):
+    got = _run(gen_golden.fbank_cases()["noise_1p5s"], mean_nor=False)
+    ref = gold["noise_1p5s.raw_f32"]
+    assert (np.abs(got - ref) > 1e-4).mean() <= 1e-3
+
+
+def test_fbank_vs_oracle_batch():
+    wavs = synth.white_noise(37, 24000, seed=77)
+    got = _run(wavs)
+    ref64 = fbank_oracle.fbank_batch(wavs, dtype=np.float64)
+    assert (np.abs(got - ref64) > 1e-4).mean() <= 1e-3
+    assert np.abs(got - ref64).mean() < 2e-6
+
+
+def test_fbank_long_utterance_two_pass_path():
+    # 10 s -> 998 frames: too big for the fused-CMN tile, takes the frame-range + cmn kernels
+    wavs = synth.white_noise(2, 160000, seed=78)
+    got = _run(wavs)
+    ref64 = fbank_oracle.fbank_batch(wavs, dtype=np.float64)
+    assert got.shape == (2, 998, 80)
+    assert (np.abs(got - ref64) > 1e-4).mean() <= 1e-3
+    assert np.abs(got.mean(axis=1)).max() < 1e-4          # CMN: zero column means
+
+
+def test_fbank_properties_full_size():
+    # config-1 shape, property checks the oracle is too slow for: CMN gives zero column means,
+    # a pure gain shifts the un-normalised log-mel by 2*log(g) (so CMN output is gain invariant)
+    wavs = synth.white_noise(1024, 48000, seed=79)
+    x = torch.from_numpy(wavs).cuda()
+    a = b200spk.fbank_batch(x, 80, True)
+    b = b200spk.fbank_batch(x * 0.5, 80, True)
+    assert a.shape == (1024, 298, 80)
+    assert a.mean(dim=1).abs().max().item() < 1e-4
+    assert (a - b).abs().max().item() < 2e-3
+    raw_a = b200spk.fbank_batch(x, 80, False)
+    raw_b = b200spk.fbank_batch(x * 0.5, 80, False)
+    d = (raw_a - raw_b) - 2 * np.log(2.0)
+    assert d.abs().median().item() < 1e-5
+
+
+def test_fbank_strided_rows_and_unaligned():
+    wavs = synth.white_noise(3, 24001, seed=80)
+    x = torch.from_numpy(wavs).cuda()
+    got = b200spk.fbank_batch(x[:, 1:], 80, True).cpu().numpy()      # odd offset: scalar-load path
+    ref64 = fbank_oracle.fbank_batch(wavs[:, 1:], dtype=np.float64)
+    assert (np.abs(got - ref64) > 1e-4).mean() <= 1e-3
+
+
+def test_fbank_class_and_vmap_match_batch():
+    wavs = synth.white_noise(5, 24000, seed=81)
+    x = torch.from_numpy(wavs).cuda()
+    fb = b200spk.FBank(80, 16000, mean_nor=True)
+    batch = fb.batch(x)
+    one = fb(x[2])
+    assert one.shape == (148, 80) and torch.equal(one, batch[2])
+    two = fb(x[1:3])                       # [C,T]: channel 0 only (processor.py:149-151)
+    assert torch.equal(two, batch[1])
+    vm = torch.vmap(fb)(x.unsqueeze(1))    # the diarization call site
+    assert vm.shape == (5, 148, 80) and torch.equal(vm, batch)
+
+
+def test_fbank_host_entry_point():
+    wavs = synth.white_noise(4, 24000, seed=82)
+    host = b200spk.fbank_batch(torch.from_numpy(wavs), 80, True)       # CPU tensor -> *_host ABI
+    dev = b200spk.fbank_batch(torch.from_numpy(wavs).cuda(), 80, True).cpu()
+    assert not host.is_cuda and torch.equal(host, dev)
+
+
+def test_fbank_empty_batch():
+    x = torch.zeros((0, 24000), device="cuda")
+    assert b200spk.fbank_batch(x).shape == (0, 148, 80)

@@ -88,14 +88,17 @@ class Model:
         emb = torch.empty((B, emb_dim), dtype=torch.float32, device=feats.device)
         chunk = max(1, min(int(chunk), max(B, 1)))
         ws = self.workspace(T, chunk)
+        self._last_chunk = chunk
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().spk_model_forward(self.handle, int(T), C.c_void_p(feats.data_ptr()), B,
                                                     C.c_void_p(emb.data_ptr()), C.c_void_p(ws.data_ptr()),
                                                     ws.numel(), chunk, _lib.current_stream_ptr()))
         return emb
 
-    def read_buffer(self, T, name, chunk, n_segments):
-        """Widened copy of a named workspace buffer for the LAST sub-batch (per-layer parity)."""
+    def read_buffer(self, T, name, n_segments, chunk=None):
+        """Widened copy of a named workspace buffer for the LAST sub-batch of the last forward
+        (per-layer parity checks)."""
+        chunk = chunk or self._last_chunk
         prog = self.programs[int(T)]
         bid = prog.names[name]
         n = prog.bufs[bid].elems * n_segments

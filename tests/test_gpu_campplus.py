@@ -62,11 +62,11 @@ def test_fp32_per_layer_vs_oracle():
     B, T = feats.shape[0], feats.shape[1]
     T2 = taps["xvector.tdnn"].shape[-1]
     # channels-last workspace buffers vs the oracle's NCT taps
-    blk3 = eng.model.read_buffer(T, "block3", 8, B).view(B, T2, -1).permute(0, 2, 1).cpu().numpy()
+    blk3 = eng.model.read_buffer(T, "block3", B).view(B, T2, -1).permute(0, 2, 1).cpu().numpy()
     assert _rel(blk3, taps["xvector.block3"].numpy()) <= 1e-4
-    blk1 = eng.model.read_buffer(T, "block1", 8, B).view(B, T2, -1).permute(0, 2, 1).cpu().numpy()
+    blk1 = eng.model.read_buffer(T, "block1", B).view(B, T2, -1).permute(0, 2, 1).cpu().numpy()
     assert _rel(blk1, taps["xvector.block1"].numpy()) <= 1e-4
-    st = eng.model.read_buffer(T, "stats", 8, B).view(B, -1).cpu().numpy()
+    st = eng.model.read_buffer(T, "stats", B).view(B, -1).cpu().numpy()
     assert _rel(st, taps["xvector.stats"].numpy()) <= 1e-4
 
 

@@ -235,7 +235,8 @@ class _Engine:
         xbufs = [prog.buf("block%d" % (i + 1), T2 * w, AD) for i, w in enumerate(widths)]
         hbuf = prog.buf("bottleneck", T2 * BNC, AD)
         gbuf = prog.buf("gate", nwin * G, _lib.DT_F32)
-        fin = prog.buf("final", T2 * mod.final_channels, AD)
+        fin = prog.buf("final", T2 * mod.final_channels, _lib.DT_F32)   # fp32 into the std pooling: bf16
+        #   quantisation of near-constant channels would dominate their (tiny) standard deviation
         stats = prog.buf("stats", 2 * mod.final_channels, _lib.DT_F32)
 
         # tdnn: Conv1d(320->128,k5,s2,p2) over channels c*H+f == conv over the [H,T,32] map with KH=H

@@ -448,8 +448,8 @@ extern "C" int spk_fbank_set_tables(const float *window400, const float *mel_ban
 extern "C" int spk_fbank_f32(const float *wav, int64_t B, int64_t n_samples, int64_t wav_stride,
                              float *out, int n_mels, int mean_nor, void *stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    SPK_REQUIRE(wav != nullptr && out != nullptr, "null buffer");
     SPK_REQUIRE(B >= 0, "negative batch");
+    SPK_REQUIRE(B == 0 || (wav != nullptr && out != nullptr), "null buffer");
     // kaldi.py:142: assert 2 <= window_size <= len(waveform)
     SPK_REQUIRE(n_samples >= kFrameLen, "choose a window size %d that is [2, %lld]", kFrameLen,
                 (long long)n_samples);
@@ -502,7 +502,7 @@ extern "C" int spk_fbank_f32(const float *wav, int64_t B, int64_t n_samples, int
 
 extern "C" int spk_fbank_host_f32(const float *wav, int64_t B, int64_t n_samples, int64_t wav_stride,
                                   float *out, int n_mels, int mean_nor) {
-    SPK_REQUIRE(wav != nullptr && out != nullptr, "null buffer");
+    SPK_REQUIRE(B == 0 || (wav != nullptr && out != nullptr), "null buffer");
     SPK_REQUIRE(n_samples >= kFrameLen, "choose a window size %d that is [2, %lld]", kFrameLen,
                 (long long)n_samples);
     if (B == 0) return SPK_OK;

@@ -222,14 +222,14 @@ def main():
         with torch.no_grad():
             for st in range(0, S, args.batch):
                 wb = wav_dev[st:st + args.batch]
-                if record:
+                if record is not None:
                     e0, e1, e2 = ev(), ev(), ev()
                     e0.record()
                 feats = fb.batch(wb)
-                if record:
+                if record is not None:
                     e1.record()
                 outs.append(model(feats))
-                if record:
+                if record is not None:
                     e2.record()
                     record.append((e0, e1, e2))
         return outs

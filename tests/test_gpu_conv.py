@@ -1,0 +1,191 @@
+"""GPU: op-level parity of the conv kernels (CUDA-core fp32 and tcgen05 bf16) through the C ABI
+against torch.nn.functional on the CPU.  A one-op program is fed through the same
+spk_model_* entry points the networks use."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from b200spk import _lib
+from b200spk.program import Model, Program, conv_out
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def run_conv(x, w, *, stride=(1, 1), pad=(0, 0), dil=(1, 1), pro=None, epi=None, act=_lib.ACT_NONE,
+             residual=False, gate=None, precision="bf16", out_choff=0, out_extra=0, chunk=None):
+    """x [B,H,W,Cin] f32 (channels-last), w [Cout,KH,KW,Cin].  Returns (y [B,Ho,Wo,Cout], ref)."""
+    B, H, W, Cin = x.shape
+    Cout, KH, KW, _ = w.shape
+    Ho, Wo = conv_out(H, KH, stride[0], pad[0], dil[0]), conv_out(W, KW, stride[1], pad[1], dil[1])
+    bf = precision == "bf16"
+    AD = _lib.DT_BF16 if bf else _lib.DT_F32
+    model = Model(_lib.PREC_BF16 if bf else _lib.PREC_F32, "cuda:0")
+    Ctot = Cin + (Cout if residual else 0)
+    ld_out = out_choff + Cout + out_extra
+    prog = Program(H * W * Ctot, Ho * Wo * ld_out)
+    xin = prog.buf("x", H * W * Ctot, AD)
+    # cast op: identity 1x1 conv on CUDA cores turns the f32 input into the activation dtype
+    eye = model.param(torch.eye(Ctot).reshape(Ctot, 1, 1, Ctot))
+    prog.op(_lib.OP_CONV, in_buf=0, in_ld=Ctot, out_buf=xin, out_ld=Ctot, H=H, W=W, Cin=Ctot, Ho=H, Wo=W, Cout=Ctot, w=eye)
+    kw = dict(in_buf=xin, in_ld=Ctot, out_buf=1, out_ld=ld_out, out_choff=out_choff, H=H, W=W, Cin=Cin, Ho=Ho, Wo=Wo,
+              Cout=Cout, KH=KH, KW=KW, sh=stride[0], sw=stride[1], ph=pad[0], pw=pad[1], dh=dil[0], dw=dil[1],
+              w=model.param(w), act=act)
+    if pro is not None:
+        kw.update(pro_scale=model.param(pro[0]), pro_shift=model.param(pro[1]), pro_relu=1)
+    if epi is not None:
+        kw.update(epi_scale=model.param(epi[0]), epi_shift=model.param(epi[1]))
+    if residual:
+        kw.update(res_buf=xin, res_ld=Ctot, res_choff=Cin)
+    gbuf = None
+    if gate is not None:
+        w1, b1, w2, b2, seg = gate
+        nwin = math.ceil(W / seg)
+        gbuf = prog.buf("gate", nwin * Cout, _lib.DT_F32)
+        prog.op(_lib.OP_CAM_GATE, in_buf=xin, in_ld=Ctot, out_buf=gbuf, W=W, Cin=Cin, Cout=Cout,
+                aux=[model.param(w1), model.param(b1), model.param(w2), model.param(b2)], iaux=[w1.shape[0], seg])
+        kw.update(gate_buf=gbuf, gate_win=seg)
+    prog.op(_lib.OP_CONV, **kw)
+    T = 1
+    model.set_program(T, prog)
+    res = torch.randn(B, H, W, Cout) if residual else None
+    xfull = torch.cat([x, res], dim=-1) if residual else x
+    out = model.forward(T, xfull.reshape(B, -1).cuda().contiguous(), Ho * Wo * ld_out, chunk or B)
+    torch.cuda.synchronize()
+    y = out.cpu().view(B, Ho, Wo, ld_out)[..., out_choff:out_choff + Cout]
+    # reference on the CPU with the operand rounding the kernel applies
+    xr = _bf16_round(x) if bf else x
+    wr = _bf16_round(w) if bf else w
+    a = xr
+    if pro is not None:
+        a = torch.relu(a * pro[0] + pro[1])
+        a = _bf16_round(a) if bf else a
+    ref = F.conv2d(a.permute(0, 3, 1, 2).double(), wr.permute(0, 3, 1, 2).double(), stride=stride, padding=pad,
+                   dilation=dil).permute(0, 2, 3, 1)
+    if epi is not None:
+        ref = ref * epi[0].double() + epi[1].double()
+    if residual:
+        ref = ref + (_bf16_round(res) if bf else res).double()
+    if act == _lib.ACT_RELU:
+        ref = torch.relu(ref)
+    elif act == _lib.ACT_CLAMP20:
+        ref = ref.clamp(0, 20)
+    if gate is not None:
+        xs = xr.double()                                              # [B,1,W,C]
+        tot = xs.mean(dim=2, keepdim=True)
+        g = torch.zeros(B, Ho, Wo, Cout, dtype=torch.float64)
+        for wi in range(math.ceil(W / seg)):
+            a0, a1 = wi * seg, min(W, (wi + 1) * seg)
+            ctx = (tot + xs[:, :, a0:a1].mean(dim=2, keepdim=True)).squeeze(2).squeeze(1)     # [B,C]
+            h = torch.relu(ctx @ w1.double().t() + b1.double())
+            g[:, :, a0:a1, :] = torch.sigmoid(h @ w2.double().t() + b2.double())[:, None, None, :]
+        ref = ref * g
+    model.close()
+    return y.double(), ref
+
+
+def _check(y, ref, tol):
+    err = (y - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= tol * scale, (err, scale)
+
+
+CASES = [
+    # name, B,H,W,Cin, Cout,KH,KW, stride, pad, dil
+    ("1x1_k128", 3, 1, 74, 128, 128, 1, 1, (1, 1), (0, 0), (1, 1)),
+    ("1x1_k992_growing_concat", 5, 1, 74, 992, 128, 1, 1, (1, 1), (0, 0), (1, 1)),
+    ("1x1_n256", 4, 1, 74, 512, 256, 1, 1, (1, 1), (0, 0), (1, 1)),
+    ("1x1_n512_two_ntiles", 4, 1, 74, 1024, 512, 1, 1, (1, 1), (0, 0), (1, 1)),
+    ("k3_dil2_cam_local", 5, 1, 74, 128, 32, 1, 3, (1, 1), (0, 2), (1, 2)),
+    ("3x3_fcm", 2, 40, 37, 32, 32, 3, 3, (1, 1), (1, 1), (1, 1)),
+    ("3x3_fcm_stride2h", 2, 40, 37, 32, 32, 3, 3, (2, 1), (1, 1), (1, 1)),
+    ("1x1_shortcut_stride2h", 2, 40, 37, 32, 32, 1, 1, (2, 1), (0, 0), (1, 1)),
+    ("tdnn_kh10_kw5_s2", 3, 10, 148, 32, 128, 10, 5, (1, 2), (0, 2), (1, 1)),
+    ("ragged_m_not_multiple_of_128", 1, 1, 131, 64, 64, 1, 1, (1, 1), (0, 0), (1, 1)),
+    ("k_not_multiple_of_64", 2, 1, 150, 160, 48, 1, 1, (1, 1), (0, 0), (1, 1)),
+]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c[0])
+def test_conv_plain(case, precision):
+    name, B, H, W, Cin, Cout, KH, KW, stride, pad, dil = case
+    import zlib
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 1000)
+    x = torch.randn(B, H, W, Cin, generator=g)
+    w = torch.randn(Cout, KH, KW, Cin, generator=g) / math.sqrt(KH * KW * Cin)
+    y, ref = run_conv(x, w, stride=stride, pad=pad, dil=dil, precision=precision)
+    _check(y, ref, 2e-5 if precision == "fp32" else 2e-5)      # same rounded operands, fp32 accumulate
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv_prologue_epilogue_relu(precision):
+    g = torch.Generator().manual_seed(1)
+    B, W, Cin, Cout = 4, 74, 352, 128
+    x = torch.randn(B, 1, W, Cin, generator=g)
+    w = torch.randn(Cout, 1, 1, Cin, generator=g) / math.sqrt(Cin)
+    pro = (torch.rand(Cin, generator=g) + 0.5, 0.1 * torch.randn(Cin, generator=g))
+    epi = (torch.rand(Cout, generator=g) + 0.5, 0.1 * torch.randn(Cout, generator=g))
+    y, ref = run_conv(x, w, pro=pro, epi=epi, act=_lib.ACT_RELU, precision=precision)
+    _check(y, ref, 1e-4 if precision == "fp32" else 2e-3)       # bf16: fma vs mul+add before re-rounding
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv_padding_stays_zero_after_prologue(precision):
+    # padded taps must contribute 0, not relu(shift): the prologue applies to real pixels only
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 1, 40, 64, generator=g)
+    w = torch.randn(32, 1, 3, 64, generator=g) / math.sqrt(192)
+    pro = (torch.ones(64), torch.full((64,), 0.7))
+    y, ref = run_conv(x, w, pad=(0, 1), pro=pro, precision=precision)
+    _check(y, ref, 1e-4 if precision == "fp32" else 2e-3)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv_residual_relu(precision):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 20, 37, 32, generator=g)
+    w = torch.randn(32, 3, 3, 32, generator=g) / math.sqrt(288)
+    epi = (torch.rand(32, generator=g) + 0.5, 0.1 * torch.randn(32, generator=g))
+    torch.manual_seed(33)
+    y, ref = run_conv(x, w, pad=(1, 1), epi=epi, residual=True, act=_lib.ACT_RELU, precision=precision)
+    _check(y, ref, 1e-4 if precision == "fp32" else 1e-4)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv_clamp20(precision):
+    g = torch.Generator().manual_seed(4)
+    x = 8 * torch.randn(2, 1, 140, 64, generator=g)
+    w = torch.randn(64, 1, 1, 64, generator=g)
+    y, ref = run_conv(x, w, act=_lib.ACT_CLAMP20, precision=precision)
+    assert ref.max().item() == 20.0 and ref.min().item() == 0.0
+    _check(y, ref, 1e-4)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("W", [74, 149, 230])
+def test_conv_cam_gate_and_concat_write(precision, W):
+    # dilated k=3 conv x CAM gate, written in place at a channel offset of a wider buffer
+    g = torch.Generator().manual_seed(5)
+    B, C, G = 3, 128, 32
+    x = torch.randn(B, 1, W, C, generator=g)
+    w = torch.randn(G, 1, 3, C, generator=g) / math.sqrt(3 * C)
+    gate = (torch.randn(64, C, generator=g) / math.sqrt(C), 0.1 * torch.randn(64, generator=g),
+            torch.randn(G, 64, generator=g) / 8, 0.1 * torch.randn(G, generator=g), 100)
+    y, ref = run_conv(x, w, pad=(0, 2), dil=(1, 2), gate=gate, precision=precision, out_choff=160, out_extra=64)
+    _check(y, ref, 1e-4 if precision == "fp32" else 1e-4)
+
+
+def test_conv_many_tiles_persistent_loop():
+    # more tiles than resident CTAs: exercises the stage ring wrap, both TMEM buffers, phase flips
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(700, 1, 74, 256, generator=g)
+    w = torch.randn(128, 1, 1, 256, generator=g) / 16
+    y, ref = run_conv(x, w, precision="bf16")
+    _check(y, ref, 2e-5)

@@ -73,19 +73,23 @@ def test_fbank_long_utterance_two_pass_path():
 
 
 def test_fbank_properties_full_size():
-    # config-1 shape, property checks the oracle is too slow for: CMN gives zero column means,
-    # a pure gain shifts the un-normalised log-mel by 2*log(g) (so CMN output is gain invariant)
+    # config-1 shape, property checks the oracle is too slow for: CMN gives zero column means;
+    # a pure gain of 2 (exact in fp32) shifts the un-normalised log-mel by 2*log(2) wherever the
+    # log floor (kaldi.py:633) is not hit.  With 0.1*randn the floor IS hit now and then in mel
+    # bin 0 (pre-emphasis attenuates 30-60 Hz by 30 dB), so floored cells are masked out.
     wavs = synth.white_noise(1024, 48000, seed=79)
     x = torch.from_numpy(wavs).cuda()
     a = b200spk.fbank_batch(x, 80, True)
-    b = b200spk.fbank_batch(x * 0.5, 80, True)
     assert a.shape == (1024, 298, 80)
     assert a.mean(dim=1).abs().max().item() < 1e-4
-    assert (a - b).abs().max().item() < 2e-3
     raw_a = b200spk.fbank_batch(x, 80, False)
-    raw_b = b200spk.fbank_batch(x * 0.5, 80, False)
-    d = (raw_a - raw_b) - 2 * np.log(2.0)
-    assert d.abs().median().item() < 1e-5
+    raw_b = b200spk.fbank_batch(x * 2.0, 80, False)
+    floor = float(np.log(1.1920929e-07))
+    assert raw_a.min().item() >= floor - 1e-6
+    mask = raw_a > floor + 1e-3
+    d = ((raw_b - raw_a) - 2 * np.log(2.0))[mask]
+    assert d.abs().max().item() < 1e-5
+    assert mask.float().mean().item() > 0.999
 
 
 def test_fbank_strided_rows_and_unaligned():

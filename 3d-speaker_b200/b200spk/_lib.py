@@ -44,6 +44,7 @@ class SpkOp(C.Structure):
         ("pro_scale", C.c_int32), ("pro_shift", C.c_int32), ("pro_relu", C.c_int32),
         ("epi_scale", C.c_int32), ("epi_shift", C.c_int32), ("act", C.c_int32),
         ("aux", C.c_int32 * 4), ("iaux", C.c_int32 * 4), ("faux", C.c_float * 2),
+        ("phase", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -84,11 +85,11 @@ _SIGS = {
     "spk_model_add_param": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),
     "spk_model_set_program": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(SpkBuf), C.c_int32, C.POINTER(SpkOp),
                                         C.c_int32]),
-    "spk_model_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64]),
+    "spk_model_workspace_bytes": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64]),
     "spk_model_forward": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
-                                    C.c_int64, C.c_int64, C.c_void_p]),
-    "spk_model_read_buffer": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
-                                        C.c_int64, C.c_void_p]),
+                                    C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
+    "spk_model_read_buffer": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
+                                        C.c_void_p, C.c_int64, C.c_void_p]),
     "spk_affinity_laplacian": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_void_p]),
     "spk_affinity_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),

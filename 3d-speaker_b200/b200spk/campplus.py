@@ -174,10 +174,14 @@ class _Engine:
     def _raw(self, key):
         return self._p(("raw", key), lambda: self.sd[key].reshape(-1))
 
-    def default_chunk(self, T):
-        # keep one sub-batch's largest activations (3 FCM maps) inside L2: ~64 segments at T=148
-        per_seg = 80 * T * 32 * (2 if self.model.precision == _lib.PREC_BF16 else 4)
-        return max(8, min(512, int(96e6 // (3 * per_seg))))
+    def default_chunks(self, T):
+        """(coarse, fine): the 2-D front keeps ~1.9 MB of activations per segment alive, so it runs
+        in fine sub-batches that fit the 126 MB L2; the D-TDNN part (<0.6 MB per segment, 74 rows
+        per segment) runs over coarse sub-batches so every launch has enough tiles for 148 SMs."""
+        bytes_per = 2 if self.model.precision == _lib.PREC_BF16 else 4
+        per_seg = 80 * T * 32 * bytes_per * 2.5
+        fine = max(4, min(256, int(100e6 // per_seg)))
+        return 512, fine
 
     def compile(self, T):
         mod, AD = self.m, self.model.act_dtype
@@ -220,8 +224,11 @@ class _Engine:
         H = res_block("head.layer1.1", bd, H, 1, bb, -1, bc)         # -> bc
         H = res_block("head.layer2.0", bc, H, 2, bb, bd, big)        # -> big [F/4]
         H = res_block("head.layer2.1", big, H, 1, bb, -1, bd)        # -> bd
-        H = conv3x3(bd, bb, H, 2, "head.conv2.weight", "head.bn2", _lib.ACT_RELU)   # -> bb [F/8, T, 32]
+        fo = prog.buf("fcm_out", (F // 8) * T * C0, AD)               # crosses into phase 1: exact size
+        H = conv3x3(bd, fo, H, 2, "head.conv2.weight", "head.bn2", _lib.ACT_RELU)   # -> [F/8, T, 32]
         assert H == F // 8
+        bb = fo
+        prog.phase = 1        # D-TDNN part: small per-segment activations, run over the coarse sub-batch
 
         # xvector
         T2 = conv_out(T, 5, 2, 2)
@@ -291,4 +298,7 @@ class _Engine:
         T = feats.shape[1]
         if T not in self._compiled:
             self.compile(T)
-        return self.model.forward(T, feats, self.m.embedding_size, chunk or self.default_chunk(T))
+        coarse, fine = self.default_chunks(T)
+        if chunk:
+            coarse, fine = (chunk if isinstance(chunk, (tuple, list)) else (chunk, min(fine, chunk)))
+        return self.model.forward(T, feats, self.m.embedding_size, coarse, fine)

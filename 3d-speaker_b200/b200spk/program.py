@@ -73,39 +73,42 @@ class Model:
         _lib.check(_lib.lib().spk_model_set_program(self.handle, int(T), bufs, len(prog.bufs), ops, len(prog.ops)))
         self.programs[int(T)] = prog
 
-    def workspace(self, T, chunk):
-        key = (int(T), int(chunk))
+    def workspace(self, T, chunk, fine):
+        key = (int(T), int(chunk), int(fine))
         ws = self._ws.get(key)
         if ws is None:
-            n = int(_lib.check(_lib.lib().spk_model_workspace_bytes(self.handle, int(T), int(chunk))))
+            n = int(_lib.check(_lib.lib().spk_model_workspace_bytes(self.handle, int(T), int(chunk), int(fine))))
+            self._ws = {}            # keep one workspace alive
             ws = torch.empty(max(n, 16), dtype=torch.uint8, device=self.device)
-            self._ws = {key: ws}     # keep one workspace alive
+            self._ws[key] = ws
         return ws
 
-    def forward(self, T, feats, emb_dim, chunk):
-        """feats [B,T,F] f32 contiguous CUDA -> emb [B,E] f32."""
+    def forward(self, T, feats, emb_dim, chunk, fine=0):
+        """feats [B,T,F] f32 contiguous CUDA -> emb [B,E] f32.  ``chunk``/``fine``: coarse and fine
+        sub-batch sizes (see spk_model_forward)."""
         B = feats.shape[0]
         emb = torch.empty((B, emb_dim), dtype=torch.float32, device=feats.device)
         chunk = max(1, min(int(chunk), max(B, 1)))
-        ws = self.workspace(T, chunk)
-        self._last_chunk = chunk
+        fine = chunk if fine <= 0 else max(1, min(int(fine), chunk))
+        ws = self.workspace(T, chunk, fine)
+        self._last_chunk = (chunk, fine)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().spk_model_forward(self.handle, int(T), C.c_void_p(feats.data_ptr()), B,
                                                     C.c_void_p(emb.data_ptr()), C.c_void_p(ws.data_ptr()),
-                                                    ws.numel(), chunk, _lib.current_stream_ptr()))
+                                                    ws.numel(), chunk, fine, _lib.current_stream_ptr()))
         return emb
 
-    def read_buffer(self, T, name, n_segments, chunk=None):
-        """Widened copy of a named workspace buffer for the LAST sub-batch of the last forward
-        (per-layer parity checks)."""
-        chunk = chunk or self._last_chunk
+    def read_buffer(self, T, name, n_segments):
+        """Widened copy of a named workspace buffer as the last sub-batch of the last forward
+        left it (per-layer parity checks)."""
+        chunk, fine = self._last_chunk
         prog = self.programs[int(T)]
         bid = prog.names[name]
         n = prog.bufs[bid].elems * n_segments
         out = torch.empty(n, dtype=torch.float32, device=self.device)
-        ws = self.workspace(T, chunk)
+        ws = self.workspace(T, chunk, fine)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().spk_model_read_buffer(self.handle, int(T), bid, int(chunk), C.c_void_p(ws.data_ptr()),
+            _lib.check(_lib.lib().spk_model_read_buffer(self.handle, int(T), bid, chunk, fine, C.c_void_p(ws.data_ptr()),
                                                         C.c_void_p(out.data_ptr()), n, _lib.current_stream_ptr()))
         return out
 
@@ -117,6 +120,7 @@ class Program:
         self.bufs = [_lib.SpkBuf(int(feat_elems), _lib.DT_F32, 0), _lib.SpkBuf(int(emb_elems), _lib.DT_F32, 0)]
         self.names = {"feats": 0, "emb": 1}
         self.ops = []
+        self.phase = 0           # phase given to ops added from now on
 
     def buf(self, name, elems, dtype):
         self.bufs.append(_lib.SpkBuf(int(elems), int(dtype), 0))
@@ -124,6 +128,7 @@ class Program:
         return len(self.bufs) - 1
 
     def op(self, kind, **kw):
+        kw.setdefault("phase", self.phase)
         self.ops.append(_lib.make_op(kind, **kw))
 
 

@@ -208,37 +208,55 @@ stem_kernel(const StemArgs a) {
 }
 
 // ------------------------------------------------------------------ CAM context gate
-// gate[b,w,:] = sigmoid(W2 relu(W1 (mean_T(x) + mean_{window w}(x)) + b1) + b2); one CTA per
-// segment, thread c owns channel c for the reductions (coalesced rows).
+// gate[b,w,:] = sigmoid(W2 relu(W1 (mean_T(x) + mean_{window w}(x)) + b1) + b2); one CTA of 256
+// threads per segment.  Column sums: thread (g, c4) adds rows g, g+G, ... of 4 adjacent
+// channels (8- or 16-byte loads, coalesced across c4), partial sums are combined through shared
+// memory in a fixed order (deterministic).  The two tiny mat-vecs use one warp per output.
 template <typename TIn>
 __global__ void __launch_bounds__(256)
 cam_gate_kernel(const CamGateArgs a) {
     extern __shared__ float sh[];
-    float *tot = sh;                       // [C]
-    float *win = tot + a.C;                // [nwin][C]
-    float *ctx = win + a.nwin * a.C;       // [C]
-    float *hid = ctx + a.C;                // [hidden]
+    float *part = sh;                               // [G][C] partial sums of one window
+    const int C = a.C, cq = C / 4;
+    const int G = blockDim.x / cq;                  // row groups
+    float *tot = part + G * C;                      // [C]
+    float *win = tot + C;                           // [nwin][C]
+    float *ctx = win + a.nwin * C;                  // [C]
+    float *hid = ctx + C;                           // [hidden]
     const int b = blockIdx.x;
     const TIn *x = static_cast<const TIn *>(a.x) + (long long)b * a.T * a.in_ld + a.in_choff;
-    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-        float t = 0.f;
-        for (int w = 0; w < a.nwin; ++w) {
-            const int t0 = w * a.seg_len, t1 = min(a.T, t0 + a.seg_len);
-            float s = 0.f;
-            for (int i = t0; i < t1; ++i) s += to_f32(x[(long long)i * a.in_ld + c]);
-            win[w * a.C + c] = s / (float)(t1 - t0);
-            t += s;
+    const int g = threadIdx.x / cq, c4 = (threadIdx.x % cq) * 4;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) tot[c] = 0.f;
+    for (int w = 0; w < a.nwin; ++w) {
+        const int t0 = w * a.seg_len, t1 = min(a.T, t0 + a.seg_len);
+        if (g < G) {
+            float s[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int i = t0 + g; i < t1; i += G) {
+                float v[4];
+                Vec4<TIn>::load(x + (long long)i * a.in_ld + c4, v);
+                s[0] += v[0]; s[1] += v[1]; s[2] += v[2]; s[3] += v[3];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) part[g * C + c4 + q] = s[q];
         }
-        tot[c] = t / (float)a.T;
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float s = 0.f;
+            for (int gg = 0; gg < G; ++gg) s += part[gg * C + c];
+            win[w * C + c] = s / (float)(t1 - t0);
+            tot[c] += s;
+        }
+        __syncthreads();
     }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) tot[c] = tot[c] / (float)a.T;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int w = 0; w < a.nwin; ++w) {
-        for (int c = threadIdx.x; c < a.C; c += blockDim.x) ctx[c] = tot[c] + win[w * a.C + c];
+        for (int c = threadIdx.x; c < C; c += blockDim.x) ctx[c] = tot[c] + win[w * C + c];
         __syncthreads();
         for (int j = warp; j < a.hidden; j += nwarps) {
             float s = 0.f;
-            for (int c = lane; c < a.C; c += 32) s = fmaf(__ldg(a.w1 + (long long)j * a.C + c), ctx[c], s);
+            for (int c = lane; c < C; c += 32) s = fmaf(__ldg(a.w1 + (long long)j * C + c), ctx[c], s);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) hid[j] = fmaxf(s + __ldg(a.b1 + j), 0.f);
@@ -406,13 +424,19 @@ int launch_stem(const StemArgs &a, int out_dtype, cudaStream_t s) {
 
 int launch_cam_gate(const CamGateArgs &a, int in_dtype, cudaStream_t s) {
     if (a.B == 0) return SPK_OK;
-    const size_t sh = ((size_t)a.C * (a.nwin + 2) + a.hidden) * sizeof(float);
+    const int threads = 256;
+    if (a.C % 4 != 0 || a.C / 4 > threads || a.in_ld % 4 != 0 || a.in_choff % 4 != 0) {
+        set_error("cam_gate: C=%d must be a multiple of 4 and <= %d", a.C, threads * 4);
+        return SPK_ERR_UNSUPPORTED;
+    }
+    const int G = threads / (a.C / 4);
+    const size_t sh = ((size_t)a.C * (G + a.nwin + 2) + a.hidden) * sizeof(float);
     if (sh > 48 * 1024) {
         set_error("cam_gate: %d windows x %d channels exceed shared memory", a.nwin, a.C);
         return SPK_ERR_UNSUPPORTED;
     }
-    if (in_dtype == SPK_DT_F32) cam_gate_kernel<float><<<a.B, 128, sh, s>>>(a);
-    else cam_gate_kernel<bf16><<<a.B, 128, sh, s>>>(a);
+    if (in_dtype == SPK_DT_F32) cam_gate_kernel<float><<<a.B, threads, sh, s>>>(a);
+    else cam_gate_kernel<bf16><<<a.B, threads, sh, s>>>(a);
     return check_launch("cam_gate_kernel");
 }
 

@@ -464,18 +464,15 @@ bool conv_tc_supported(const ConvArgs &a, int in_dtype) {
 
 int launch_conv_tc(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s) {
     if (a.M == 0) return SPK_OK;
+    const bool res_bf16 = a.res == nullptr ? (out_dtype == SPK_DT_BF16) : (res_dtype == SPK_DT_BF16);
     if (out_dtype == SPK_DT_BF16) {
-        if (a.res != nullptr && res_dtype != SPK_DT_BF16) {
-            set_error("conv_tc: residual dtype must match the bf16 output");
+        if (!res_bf16) {
+            set_error("conv_tc: a bf16 output takes a bf16 residual");
             return SPK_ERR_UNSUPPORTED;
         }
         return launch_n<bf16, bf16>(a, s);
     }
-    if (a.res != nullptr && res_dtype != SPK_DT_F32) {
-        set_error("conv_tc: residual dtype must match the f32 output");
-        return SPK_ERR_UNSUPPORTED;
-    }
-    return launch_n<float, float>(a, s);
+    return res_bf16 ? launch_n<float, bf16>(a, s) : launch_n<float, float>(a, s);
 }
 
 }  // namespace spk

@@ -33,13 +33,25 @@ namespace {
 
 size_t dtype_size(int dt) { return dt == SPK_DT_BF16 ? 2 : 4; }
 
-// byte offsets of workspace buffers (ids >= 2) for a chunk of n segments
-void plan(const spk_program &p, int64_t n, std::vector<int64_t> &off, int64_t &total) {
+// A buffer is coarse-scoped when any phase-1 op touches it, else fine-scoped.
+void scopes(const spk_program &p, std::vector<char> &coarse) {
+    coarse.assign(p.bufs.size(), 0);
+    for (const spk_op_t &o : p.ops) {
+        if (o.phase == 0) continue;
+        for (int id : {o.in_buf, o.out_buf, o.res_buf, o.gate_buf})
+            if (id >= 0) coarse[id] = 1;
+    }
+}
+
+// byte offsets of workspace buffers (ids >= 2) for sub-batches of n (coarse) / f (fine) segments
+void plan(const spk_program &p, int64_t n, int64_t f, std::vector<int64_t> &off, std::vector<char> &coarse,
+          int64_t &total) {
+    scopes(p, coarse);
     off.assign(p.bufs.size(), -1);
     int64_t cur = 0;
     for (size_t i = 2; i < p.bufs.size(); ++i) {
         off[i] = cur;
-        cur += align_up(p.bufs[i].elems * n * (int64_t)dtype_size(p.bufs[i].dtype), 1024);
+        cur += align_up(p.bufs[i].elems * (coarse[i] ? n : f) * (int64_t)dtype_size(p.bufs[i].dtype), 1024);
     }
     total = cur;
 }
@@ -157,44 +169,59 @@ extern "C" int spk_model_set_program(spk_model_t *m, int64_t T, const spk_buf_t 
     return SPK_OK;
 }
 
-extern "C" int64_t spk_model_workspace_bytes(spk_model_t *m, int64_t T, int64_t chunk) {
+extern "C" int64_t spk_model_workspace_bytes(spk_model_t *m, int64_t T, int64_t chunk, int64_t fine_chunk) {
     SPK_REQUIRE(m != nullptr && chunk > 0, "bad argument");
     auto it = m->programs.find(T);
     SPK_REQUIRE(it != m->programs.end(), "no program registered for T=%lld", (long long)T);
+    if (fine_chunk <= 0 || fine_chunk > chunk) fine_chunk = chunk;
     std::vector<int64_t> off;
+    std::vector<char> coarse;
     int64_t total = 0;
-    plan(it->second, chunk, off, total);
+    plan(it->second, chunk, fine_chunk, off, coarse, total);
     return total;
 }
 
 extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, int64_t B, float *emb,
-                                 void *workspace, int64_t workspace_bytes, int64_t chunk, void *stream_) {
+                                 void *workspace, int64_t workspace_bytes, int64_t chunk, int64_t fine_chunk,
+                                 void *stream_) {
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
     SPK_REQUIRE(m != nullptr && feats != nullptr && emb != nullptr, "null argument");
     SPK_REQUIRE(B >= 0 && chunk > 0, "bad batch/chunk");
     auto it = m->programs.find(T);
     SPK_REQUIRE(it != m->programs.end(), "no program registered for T=%lld", (long long)T);
     const spk_program &p = it->second;
+    if (fine_chunk <= 0 || fine_chunk > chunk) fine_chunk = chunk;
     std::vector<int64_t> off;
+    std::vector<char> coarse;
     int64_t total = 0;
-    plan(p, chunk, off, total);
+    plan(p, chunk, fine_chunk, off, coarse, total);
     if (total > workspace_bytes || (total > 0 && workspace == nullptr)) {
         set_error("workspace too small: need %lld bytes, got %lld", (long long)total, (long long)workspace_bytes);
         return SPK_ERR_WORKSPACE;
     }
     char *ws = static_cast<char *>(workspace);
 
+    bool has_phase1 = false;
+    for (const spk_op_t &o : p.ops) has_phase1 |= (o.phase != 0);
+
     for (int64_t c0 = 0; c0 < B; c0 += chunk) {
-        const int n = (int)std::min<int64_t>(chunk, B - c0);
+      const int n_coarse = (int)std::min<int64_t>(chunk, B - c0);
+      // pass 0: phase-0 ops per fine sub-batch; pass 1: phase-1 ops over the coarse sub-batch
+      for (int pass = 0; pass < (has_phase1 ? 2 : 1); ++pass)
+      for (int64_t f0 = 0; f0 < (pass == 0 ? n_coarse : 1); f0 += fine_chunk) {
+        const int n = pass == 0 ? (int)std::min<int64_t>(fine_chunk, n_coarse - f0) : n_coarse;
         auto ptr = [&](int id) -> void * {
             if (id < 0) return nullptr;
-            if (id == 0) return const_cast<float *>(feats) + c0 * p.bufs[0].elems;
-            if (id == 1) return emb + c0 * p.bufs[1].elems;
-            return ws + off[id];
+            if (id == 0) return const_cast<float *>(feats) + (c0 + f0) * p.bufs[0].elems;
+            if (id == 1) return emb + (c0 + f0) * p.bufs[1].elems;
+            char *base = ws + off[id];
+            if (coarse[id]) base += f0 * p.bufs[id].elems * (int64_t)dtype_size(p.bufs[id].dtype);
+            return base;
         };
         auto dt = [&](int id) { return id < 0 ? SPK_DT_F32 : p.bufs[id].dtype; };
         for (size_t oi = 0; oi < p.ops.size(); ++oi) {
             const spk_op_t &o = p.ops[oi];
+            if ((o.phase != 0) != (pass == 1)) continue;
             int rc = SPK_OK;
             switch (o.kind) {
                 case SPK_OP_STEM: {
@@ -274,11 +301,12 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
             }
             if (rc != SPK_OK) return rc;
         }
+      }
     }
     return SPK_OK;
 }
 
-extern "C" int spk_model_read_buffer(spk_model_t *m, int64_t T, int32_t buf_id, int64_t chunk,
+extern "C" int spk_model_read_buffer(spk_model_t *m, int64_t T, int32_t buf_id, int64_t chunk, int64_t fine_chunk,
                                      const void *workspace, float *dst, int64_t n, void *stream_) {
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
     SPK_REQUIRE(m != nullptr && workspace != nullptr && dst != nullptr, "null argument");
@@ -286,9 +314,12 @@ extern "C" int spk_model_read_buffer(spk_model_t *m, int64_t T, int32_t buf_id, 
     SPK_REQUIRE(it != m->programs.end(), "no program registered for T=%lld", (long long)T);
     const spk_program &p = it->second;
     SPK_REQUIRE(buf_id >= 2 && buf_id < (int)p.bufs.size(), "buffer id %d is not a workspace buffer", buf_id);
+    if (fine_chunk <= 0 || fine_chunk > chunk) fine_chunk = chunk;
     std::vector<int64_t> off;
+    std::vector<char> coarse;
     int64_t total = 0;
-    plan(p, chunk, off, total);
-    SPK_REQUIRE(n <= p.bufs[buf_id].elems * chunk, "read past the end of buffer %d", buf_id);
+    plan(p, chunk, fine_chunk, off, coarse, total);
+    SPK_REQUIRE(n <= p.bufs[buf_id].elems * (coarse[buf_id] ? chunk : fine_chunk), "read past the end of buffer %d",
+                buf_id);
     return launch_widen(static_cast<const char *>(workspace) + off[buf_id], p.bufs[buf_id].dtype, dst, n, s);
 }

@@ -106,6 +106,8 @@ typedef struct {
     int32_t aux[4];                        /* CAM_GATE: w1,b1,w2,b2                          */
     int32_t iaux[4];                       /* CAM_GATE: hidden, seg_len; STATS_POOL: unbiased */
     float   faux[2];                       /* STATS_POOL: eps inside sqrt                    */
+    int32_t phase;                         /* 0: runs per fine sub-batch; 1: per coarse sub-batch */
+    int32_t reserved;
 } spk_op_t;
 
 int     spk_model_create(spk_model_t **out, int precision);
@@ -115,15 +117,19 @@ int64_t spk_model_add_param(spk_model_t *m, const float *host, int64_t n);
 /* register the op list for segments of T frames (replaces an earlier program for the same T) */
 int     spk_model_set_program(spk_model_t *m, int64_t T, const spk_buf_t *bufs, int32_t n_bufs,
                               const spk_op_t *ops, int32_t n_ops);
-/* bytes of workspace spk_model_forward needs for sub-batches of 'chunk' segments */
-int64_t spk_model_workspace_bytes(spk_model_t *m, int64_t T, int64_t chunk);
-/* feats: device [B,T,F] f32 contiguous; emb: device [B,E] f32.  B is processed in sub-batches
- * of at most 'chunk' segments so activations stay L2-resident. */
+/* bytes of workspace spk_model_forward needs for the given sub-batch sizes */
+int64_t spk_model_workspace_bytes(spk_model_t *m, int64_t T, int64_t chunk, int64_t fine_chunk);
+/* feats: device [B,T,F] f32 contiguous; emb: device [B,E] f32.  B is walked in sub-batches of
+ * at most 'chunk' segments; inside each, the phase-0 ops (large per-segment activations, e.g.
+ * the 2-D front of CAM++) run over sub-batches of 'fine_chunk' segments so their
+ * producer->consumer traffic stays inside L2, then the phase-1 ops run once over the whole
+ * sub-batch so their grids fill the GPU.  fine_chunk <= 0 means fine_chunk = chunk. */
 int     spk_model_forward(spk_model_t *m, int64_t T, const float *feats, int64_t B, float *emb,
-                          void *workspace, int64_t workspace_bytes, int64_t chunk, void *stream);
+                          void *workspace, int64_t workspace_bytes, int64_t chunk, int64_t fine_chunk,
+                          void *stream);
 /* debugging / per-layer parity: copy the first n elements of workspace buffer 'buf_id' of the
  * LAST sub-batch into dst (device pointer, f32; bf16 buffers are widened) */
-int     spk_model_read_buffer(spk_model_t *m, int64_t T, int32_t buf_id, int64_t chunk,
+int     spk_model_read_buffer(spk_model_t *m, int64_t T, int32_t buf_id, int64_t chunk, int64_t fine_chunk,
                               const void *workspace, float *dst, int64_t n, void *stream);
 /* kernels launched by spk_* calls since process start (bench.py's gpu_launches) */
 int64_t spk_launch_count(void);

@@ -39,9 +39,9 @@ def test_abi_version_and_frame_count():
 
 
 def test_struct_layout_matches_header():
-    # spk_op_t is 45 int32 + 2 float; spk_buf_t is int64 + 2 int32
+    # spk_op_t is 41 int32 + 2 float + phase/reserved; spk_buf_t is int64 + 2 int32
     assert C.sizeof(_lib.SpkBuf) == 16
-    assert C.sizeof(_lib.SpkOp) == 4 * (1 + 3 + 3 + 3 + 2 + 6 + 8 + 1 + 3 + 3 + 4 + 4) + 8
+    assert C.sizeof(_lib.SpkOp) == 4 * (1 + 3 + 3 + 3 + 2 + 6 + 8 + 1 + 3 + 3 + 4 + 4) + 8 + 8
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device error path")

@@ -75,9 +75,10 @@ def test_chunking_is_invisible():
     feats = b200spk.fbank_batch(torch.from_numpy(gen_golden.campplus_input(11, n_samples, seed=7)).cuda())
     a, _ = _model(emb, wseed, bnrand, chunk=4)
     b, _ = _model(emb, wseed, bnrand, chunk=64)
+    c, _ = _model(emb, wseed, bnrand, chunk=(7, 3))        # coarse 7 (11 = 7+4), fine 3 (7 = 3+3+1)
     with torch.no_grad():
-        ea, eb = a(feats), b(feats)
-    assert torch.equal(ea, eb)             # ragged last sub-batch (11 = 4+4+3) and one-shot agree bit for bit
+        ea, eb, ec = a(feats), b(feats), c(feats)
+    assert torch.equal(ea, eb) and torch.equal(ea, ec)     # sub-batching never changes a bit
 
 
 def test_two_seg_windows_and_ragged_T():
@@ -92,16 +93,34 @@ def test_two_seg_windows_and_ragged_T():
         assert _rel(got, ref) <= 1e-4
 
 
-def test_bf16_mode_vs_fp32():
-    name, emb, batch, n_samples, wseed, bnrand = gen_golden.campplus_cases()[0]
-    feats = b200spk.fbank_batch(torch.from_numpy(gen_golden.campplus_input(16, n_samples, seed=5)).cuda())
-    f32, sd = _model(emb, wseed, bnrand)
-    b16, _ = _model(emb, wseed, bnrand, precision="bf16")
+# torch's own CPU bf16 execution of the reference graph on the same weights/inputs, measured in
+# this repo's container (tools/diag_bf16.py + the snippet in DESIGN.md): min cosine vs fp32.
+TORCH_CPU_BF16_COS = {"noise_bnrand7": 0.999066, "fm_freshbn104": 0.999801, "fm_bnrand101": 0.959640}
+
+
+@pytest.mark.parametrize("case", ["noise_bnrand7", "fm_freshbn104", "fm_bnrand101"])
+def test_bf16_mode(case):
+    """bf16 = tcgen05 tensor-core path.  North-star tolerance: cosine >= 0.999 vs the CPU fp32
+    reference path.  Weight set 101 (randomised BN) is ill-conditioned - PyTorch's own bf16 run of
+    the reference graph only reaches 0.9596 on it - so there the bar is 'no worse than torch bf16'."""
+    wseed, bnrand = {"noise_bnrand7": (7, True), "fm_freshbn104": (104, False), "fm_bnrand101": (101, True)}[case]
+    if case.startswith("noise"):
+        wavs = synth.white_noise(16, 24000, seed=123)
+    else:
+        wavs = gen_golden.campplus_input(16, 24000, seed=5)
+    feats = b200spk.fbank_batch(torch.from_numpy(wavs).cuda())
+    f32, sd = _model(192, wseed, bnrand)
+    b16, _ = _model(192, wseed, bnrand, precision="bf16")
     ref = campplus_oracle.forward(sd, feats.cpu().numpy()).numpy()
     with torch.no_grad():
         e32, e16 = f32(feats).cpu().numpy(), b16(feats).cpu().numpy()
-    assert _cos_min(e16, ref) >= 0.999         # north-star bf16 tolerance vs the CPU reference path
-    assert _rel(e16, e32) <= 3e-2              # precision mode, validated against fp32-GPU
+    assert _rel(e32, ref) <= 1e-4
+    cos = _cos_min(e16, ref)
+    if case == "fm_bnrand101":
+        assert cos >= TORCH_CPU_BF16_COS[case], cos
+    else:
+        assert cos >= 0.999, cos
+        assert _rel(e16, e32) <= 3e-2
 
 
 def test_extractor_host_buffers_roundtrip():

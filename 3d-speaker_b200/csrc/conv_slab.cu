@@ -1,0 +1,376 @@
+// "Slab" implicit-GEMM for the small-channel 2-D convolutions of the CAM++ FCM head
+// (BasicResBlock 3x3 convs, the 1x1 strided shortcuts and head.conv2:
+// speakerlab/models/campplus/DTDNN.py:13-48, layers.py:218-253): Cin = Cout = 32, kernel 3x3
+// pad 1 or 1x1 pad 0, stride (1|2, 1).  bf16 operands, fp32 accumulation in TMEM.
+//
+// Why not the generic gather kernel: with K = 9*32 every input pixel is needed by 9 taps, and a
+// per-tap gather re-reads it 9 times through L1.  Here a CTA stages a band of input rows ONCE in
+// shared memory as four 16-byte "channel planes" (plane j holds channels 8j..8j+7 of every
+// pixel, pixels 16 B apart).  That is the no-swizzle K-major UMMA layout with SBO = 128 B
+// (8 pixels) and LBO = plane stride, and - because consecutive pixels are a constant 16 B apart
+// - the SAME staged data serves every tap: tap (kh,kw) is just the descriptor start address
+// advanced by (kh*Wp + kw) pixels over the zero-padded, flattened band (Wp = W + KW - 1).
+// For stride 2 in H, even and odd input rows go to separate sub-slabs so the shift stays uniform.
+// Output pixels are produced for all Wp flat columns; the KW-1 wrap-around columns per row are
+// computed and dropped (1.3 % at W=148).
+//
+// Per band: load slab + weights (all 256 threads) -> fence.proxy.async -> one thread issues
+// tiles x taps x 2 tcgen05.mma (M=128, N=32, K=16) -> tcgen05.commit -> all warps run the
+// epilogue (TMEM -> folded BN, residual, ReLU -> bf16 store).  Two CTAs share an SM so one
+// band's loads/stores overlap the other's MMAs.
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
+#include "ops.cuh"
+
+namespace spk {
+namespace {
+
+using bf16 = __nv_bfloat16;
+constexpr int kC = 32;                 // Cin = Cout
+constexpr int kThreads = 256;
+constexpr uint32_t kSpinLimit = 1u << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no swizzle: core matrix = 8 rows x 16 B contiguous; SBO = next 8 rows, LBO = next
+// 16-byte K chunk (cute::UMMA INTERLEAVE layout ((8,n),2):((1,SBO),LBO) in 16-byte units).
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+constexpr uint32_t kIdescN32 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ uint4 ldg16(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t v) {
+    __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162 *>(&v);
+    return make_float2(__low2float(t), __high2float(t));
+}
+
+struct SlabGeom {
+    int R;          // output rows per band
+    int Wp;         // W + KW - 1
+    int n_bands;    // per segment
+    int n_tiles;    // 128-pixel MMA tiles per band
+    int rows_e, rows_o;     // input rows staged per sub-slab
+    int px_e, px_o;         // pixels allocated per sub-slab (incl. slack)
+    int taps;
+    int smem_bytes;
+    int tmem_cols;
+};
+
+// S: stride in H (1|2); KS: kernel size (1|3)
+template <int S, int KS>
+__global__ void __launch_bounds__(kThreads, 2)
+conv_slab_kernel(const ConvArgs a, const SlabGeom g, long long n_items, int swap_lbo_sbo) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int TAPS = KS * KS;
+    constexpr int PAD = (KS - 1) / 2;
+    const uint32_t s_w = smem_u32(smem);                                 // weights: [tap][chunk j][n=32] x 16 B
+    const uint32_t s_e = s_w + TAPS * 4 * 32 * 16;                        // sub-slab E: 4 planes x px_e x 16 B
+    const uint32_t s_o = s_e + 4u * g.px_e * 16u;                         // sub-slab O
+    const uint32_t s_bar = s_o + 4u * g.px_o * 16u;                       // mbarrier (8 B) + tmem slot
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + (s_bar - s_w) + 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(s_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), g.tmem_cols);
+    }
+    // ---- weights -> smem planes (once per CTA): piece (n, tap, j) = w[n][tap][8j..8j+7]
+    {
+        const bf16 *w = static_cast<const bf16 *>(a.w);
+        for (int idx = threadIdx.x; idx < kC * TAPS * 4; idx += kThreads) {
+            const int j = idx & 3, t = (idx >> 2) % TAPS, n = idx / (4 * TAPS);
+            const uint4 v = ldg16(w + ((long long)n * TAPS + t) * kC + j * 8);
+            sts16(s_w + (uint32_t)(((t * 4 + j) * 32 + n) * 16), v);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const bf16 *x = static_cast<const bf16 *>(a.x);
+    bf16 *y = static_cast<bf16 *>(a.y);
+    const bf16 *res = static_cast<const bf16 *>(a.res);
+    const uint32_t plane_e = (uint32_t)g.px_e * 16u, plane_o = (uint32_t)g.px_o * 16u;
+    uint32_t parity = 0;
+
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int b = (int)(item / g.n_bands);
+        const int band = (int)(item - (long long)b * g.n_bands);
+        const int ho0 = band * g.R;
+        const int r_valid = min(g.R, a.Ho - ho0);
+        const int hi_base = ho0 * S - PAD;                  // input row of slab row 0
+        // ---- stage the input band: piece (row, pixel, chunk)
+        {
+            const int rows_total = g.rows_e + g.rows_o;
+            const int pieces = rows_total * g.Wp * 4;
+            for (int idx = threadIdx.x; idx < pieces; idx += kThreads) {
+                const int j = idx & 3;
+                const int pix = idx >> 2;
+                const int row = pix / g.Wp, col = pix - row * g.Wp;
+                // slab row -> (sub-slab, row inside it, input row)
+                int sub = 0, srow = row, hi;
+                if (S == 2 && KS == 3) {
+                    if (row < g.rows_e) { sub = 0; srow = row; hi = hi_base + 2 * row; }
+                    else { sub = 1; srow = row - g.rows_e; hi = hi_base + 2 * srow + 1; }
+                } else if (S == 2) {
+                    hi = hi_base + 2 * row;
+                } else {
+                    hi = hi_base + row;
+                }
+                const int wi = col - PAD;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W)
+                    v = ldg16(x + (((long long)b * a.H + hi) * a.W + wi) * a.in_ld + a.in_choff + j * 8);
+                const uint32_t dst = (sub == 0 ? s_e + j * plane_e : s_o + j * plane_o) + (uint32_t)(srow * g.Wp + col) * 16u;
+                sts16(dst, v);
+            }
+            // slack pixels past the staged rows are read by the last tile's shifted views: zero them
+            const int slack_e = g.px_e - g.rows_e * g.Wp, slack_o = g.px_o - g.rows_o * g.Wp;
+            for (int idx = threadIdx.x; idx < (slack_e + slack_o) * 4; idx += kThreads) {
+                const int j = idx & 3, p = idx >> 2;
+                const uint32_t dst = (p < slack_e) ? s_e + j * plane_e + (uint32_t)(g.rows_e * g.Wp + p) * 16u
+                                                   : s_o + j * plane_o + (uint32_t)(g.rows_o * g.Wp + (p - slack_e)) * 16u;
+                sts16(dst, make_uint4(0u, 0u, 0u, 0u));
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        // ---- MMAs: one thread
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            for (int t = 0; t < g.n_tiles; ++t) {
+                const uint32_t d = tmem_base + (uint32_t)t * 32u;
+#pragma unroll
+                for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < KS; ++kw) {
+                        uint32_t sbase, plane;
+                        int off;
+                        if (S == 2 && KS == 3) {
+                            if (kh & 1) { sbase = s_o; plane = plane_o; off = kw; }
+                            else { sbase = s_e; plane = plane_e; off = (kh >> 1) * g.Wp + kw; }
+                        } else {
+                            sbase = s_e; plane = plane_e; off = kh * g.Wp + kw;
+                        }
+                        const uint32_t a_addr = sbase + (uint32_t)(t * 128 + off) * 16u;
+                        const uint32_t b_addr = s_w + (uint32_t)((kh * KS + kw) * 4 * 32 * 16);
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            uint64_t ad, bd;
+                            if (!swap_lbo_sbo) {
+                                ad = make_desc_nosw(a_addr + 2u * half * plane, plane, 128u);
+                                bd = make_desc_nosw(b_addr + 2u * half * 512u, 512u, 128u);
+                            } else {
+                                ad = make_desc_nosw(a_addr + 2u * half * plane, 128u, plane);
+                                bd = make_desc_nosw(b_addr + 2u * half * 512u, 128u, 512u);
+                            }
+                            umma_bf16(d, ad, bd, kIdescN32, (kh | kw | half) ? 1u : 0u);
+                        }
+                    }
+            }
+            umma_commit(s_bar);
+        }
+        mbar_wait(s_bar, parity);
+        parity ^= 1u;
+        tc_fence_after();
+        // ---- epilogue: warp w reads TMEM lane quarter w%4; warps 0-3 take even tiles, 4-7 odd
+        {
+            const int q = warp & 3;
+            for (int t = warp >> 2; t < g.n_tiles; t += 2) {
+                const int p = t * 128 + q * 32 + lane;
+                const int i = p / g.Wp, col = p - i * g.Wp;
+                const bool ok = (i < r_valid) && (col < a.W);
+                const long long opix = ((long long)b * a.Ho + ho0 + i) * a.Wo + col;
+                const uint32_t taddr = tmem_base + (uint32_t)t * 32u + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+                for (int c0 = 0; c0 < kC; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c0, r);
+                    tmem_ld_wait();
+                    if (ok) {
+                        float v[16];
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+                        if (a.epi_scale != nullptr) {
+#pragma unroll
+                            for (int e = 0; e < 16; e += 4) {
+                                const float4 s4 = __ldg(reinterpret_cast<const float4 *>(a.epi_scale + c0 + e));
+                                const float4 h4 = __ldg(reinterpret_cast<const float4 *>(a.epi_shift + c0 + e));
+                                v[e] = fmaf(v[e], s4.x, h4.x); v[e + 1] = fmaf(v[e + 1], s4.y, h4.y);
+                                v[e + 2] = fmaf(v[e + 2], s4.z, h4.z); v[e + 3] = fmaf(v[e + 3], s4.w, h4.w);
+                            }
+                        }
+                        if (res != nullptr) {
+                            const uint4 r0 = ldg16(res + opix * a.res_ld + a.res_choff + c0);
+                            const uint4 r1 = ldg16(res + opix * a.res_ld + a.res_choff + c0 + 8);
+                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float2 f = unpack2(rr[e]);
+                                v[2 * e] += f.x;
+                                v[2 * e + 1] += f.y;
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = apply_act(v[e], a.act);
+                        bf16 *yp = y + opix * a.out_ld + a.out_choff + c0;
+                        *reinterpret_cast<uint4 *>(yp) = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+                        *reinterpret_cast<uint4 *>(yp + 8) = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();     // TMEM and the slab are free for the next band
+        tc_fence_after();
+    }
+    if (warp == 0) tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+bool geometry(const ConvArgs &a, SlabGeom &g) {
+    const int KS = a.KH;
+    g.taps = KS * KS;
+    g.Wp = a.W + KS - 1;
+    int R = 768 / g.Wp;
+    if (R < 1) R = 1;
+    if (R > a.Ho) R = a.Ho;
+    for (;; --R) {
+        g.R = R;
+        g.n_tiles = (R * g.Wp + 127) / 128;
+        if (a.sh == 1) { g.rows_e = R + KS - 1; g.rows_o = 0; }
+        else if (KS == 3) { g.rows_e = R + 1; g.rows_o = R; }
+        else { g.rows_e = R; g.rows_o = 0; }
+        const int max_off_e = (a.sh == 1 ? (KS - 1) * g.Wp : (KS == 3 ? g.Wp : 0)) + (KS - 1);
+        g.px_e = std::max(g.rows_e * g.Wp, g.n_tiles * 128 + max_off_e) + 8;
+        g.px_o = g.rows_o ? std::max(g.rows_o * g.Wp, g.n_tiles * 128 + (KS - 1)) + 8 : 0;
+        g.smem_bytes = g.taps * 4 * 32 * 16 + 64 * (g.px_e + g.px_o) + 64;
+        int cols = g.n_tiles * 32;
+        g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+        if ((g.n_tiles <= 8 && g.smem_bytes <= 110 * 1024) || R == 1) break;
+    }
+    g.n_bands = (a.Ho + g.R - 1) / g.R;
+    return g.n_tiles <= 16 && g.smem_bytes <= 200 * 1024;
+}
+
+template <int S, int KS>
+int launch(const ConvArgs &a, const SlabGeom &g, cudaStream_t s) {
+    auto kern = conv_slab_kernel<S, KS>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    if (attr_err != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(conv_slab) failed: %s", cudaGetErrorString(attr_err));
+        return SPK_ERR_CUDA;
+    }
+    static const int swap = [] { const char *e = getenv("SPK_SLAB_SWAP_LBO_SBO"); return (e && e[0] == '1') ? 1 : 0; }();
+    const long long items = (long long)a.B * g.n_bands;
+    int per_sm = std::min(2, std::min(512 / g.tmem_cols, (227 * 1024) / (g.smem_bytes + 1024)));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = std::min<long long>(items, (long long)sm_count() * per_sm);
+    kern<<<(unsigned)grid, kThreads, g.smem_bytes, s>>>(a, g, items, swap);
+    return check_launch("conv_slab_kernel");
+}
+
+}  // namespace
+
+bool conv_slab_supported(const ConvArgs &a, int in_dtype, int out_dtype, int res_dtype) {
+    if (in_dtype != SPK_DT_BF16 || out_dtype != SPK_DT_BF16) return false;
+    if (a.res != nullptr && res_dtype != SPK_DT_BF16) return false;
+    if (a.Cin != kC || a.Cout != kC) return false;
+    if (!((a.KH == 3 && a.KW == 3 && a.ph == 1 && a.pw == 1) || (a.KH == 1 && a.KW == 1 && a.ph == 0 && a.pw == 0))) return false;
+    if (a.sw != 1 || (a.sh != 1 && a.sh != 2) || a.dh != 1 || a.dw != 1) return false;
+    if (a.pro_scale != nullptr || a.gate != nullptr) return false;
+    if (a.in_ld % 8 || a.in_choff % 8 || a.out_ld % 8 || a.out_choff % 8) return false;
+    if (a.res != nullptr && (a.res_ld % 8 || a.res_choff % 8)) return false;
+    if (a.Wo != a.W || a.Ho != (a.H + 2 * a.ph - a.KH) / a.sh + 1) return false;
+    if (a.KH == 1 && a.sh == 1) return false;      // plain 1x1: the generic GEMM path is already ideal
+    SlabGeom g;
+    return geometry(a, g);
+}
+
+int launch_conv_slab(const ConvArgs &a, cudaStream_t s) {
+    SlabGeom g;
+    if (!geometry(a, g)) {
+        set_error("conv_slab: geometry does not fit");
+        return SPK_ERR_UNSUPPORTED;
+    }
+    if (a.B == 0) return SPK_OK;
+    if (a.KH == 3) return a.sh == 1 ? launch<1, 3>(a, g, s) : launch<2, 3>(a, g, s);
+    return launch<2, 1>(a, g, s);
+}
+
+}  // namespace spk

@@ -252,7 +252,15 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                     a.pro_relu = o.pro_relu; a.act = o.act;
                     a.K = o.KH * o.KW * o.Cin;
                     a.M = (long long)n * o.Ho * o.Wo;
-                    if (m->precision == SPK_PREC_BF16 && conv_tc_supported(a, dt(o.in_buf))) {
+                    if (m->precision == SPK_PREC_BF16 &&
+                        conv_slab_supported(a, dt(o.in_buf), dt(o.out_buf), dt(o.res_buf))) {
+                        const __nv_bfloat16 *wb = nullptr;
+                        rc = param_bf16(m, o.w, &wb, s);
+                        if (rc == SPK_OK) {
+                            a.w = wb;
+                            rc = launch_conv_slab(a, s);
+                        }
+                    } else if (m->precision == SPK_PREC_BF16 && conv_tc_supported(a, dt(o.in_buf))) {
                         const __nv_bfloat16 *wb = nullptr;
                         rc = param_bf16(m, o.w, &wb, s);
                         if (rc == SPK_OK) {

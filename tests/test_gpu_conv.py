@@ -34,7 +34,11 @@ def run_conv(x, w, *, stride=(1, 1), pad=(0, 0), dil=(1, 1), pro=None, epi=None,
     # cast op: identity 1x1 conv on CUDA cores turns the f32 input into the activation dtype
     eye = model.param(torch.eye(Ctot).reshape(Ctot, 1, 1, Ctot))
     prog.op(_lib.OP_CONV, in_buf=0, in_ld=Ctot, out_buf=xin, out_ld=Ctot, H=H, W=W, Cin=Ctot, Ho=H, Wo=W, Cout=Ctot, w=eye)
-    kw = dict(in_buf=xin, in_ld=Ctot, out_buf=1, out_ld=ld_out, out_choff=out_choff, H=H, W=W, Cin=Cin, Ho=Ho, Wo=Wo,
+    # the conv under test writes the activation dtype (as inside a network) unless it targets a
+    # channel slice of a wider buffer; a second identity conv widens the result to the f32 output
+    staged = out_choff == 0 and out_extra == 0 and Cout % 16 == 0
+    ybuf = prog.buf("y", Ho * Wo * ld_out, AD) if staged else 1
+    kw = dict(in_buf=xin, in_ld=Ctot, out_buf=ybuf, out_ld=ld_out, out_choff=out_choff, H=H, W=W, Cin=Cin, Ho=Ho, Wo=Wo,
               Cout=Cout, KH=KH, KW=KW, sh=stride[0], sw=stride[1], ph=pad[0], pw=pad[1], dh=dil[0], dw=dil[1],
               w=model.param(w), act=act)
     if pro is not None:
@@ -52,6 +56,10 @@ def run_conv(x, w, *, stride=(1, 1), pad=(0, 0), dil=(1, 1), pro=None, epi=None,
                 aux=[model.param(w1), model.param(b1), model.param(w2), model.param(b2)], iaux=[w1.shape[0], seg])
         kw.update(gate_buf=gbuf, gate_win=seg)
     prog.op(_lib.OP_CONV, **kw)
+    if staged:
+        eye_o = model.param(torch.eye(Cout).reshape(Cout, 1, 1, Cout))
+        prog.op(_lib.OP_CONV, in_buf=ybuf, in_ld=Cout, out_buf=1, out_ld=Cout, H=Ho, W=Wo, Cin=Cout, Ho=Ho, Wo=Wo,
+                Cout=Cout, w=eye_o)
     T = 1
     model.set_program(T, prog)
     res = torch.randn(B, H, W, Cout) if residual else None
@@ -87,13 +95,20 @@ def run_conv(x, w, *, stride=(1, 1), pad=(0, 0), dil=(1, 1), pro=None, epi=None,
             g[:, :, a0:a1, :] = torch.sigmoid(h @ w2.double().t() + b2.double())[:, None, None, :]
         ref = ref * g
     model.close()
-    return y.double(), ref
+    y = y.double()
+    y.bf16_stored = bool(staged and bf)
+    if y.bf16_stored:
+        ref = _bf16_round(ref.float()).double()       # the conv stores bf16
+    return y, ref
 
 
 def _check(y, ref, tol):
-    err = (y - ref).abs().max().item()
+    # a bf16-stored result may land one bf16 ulp away from the rounded reference when the fp32
+    # accumulation order moves a value across a rounding boundary: allow one bf16 ulp (2^-7 relative) per element
+    err = (y - ref).abs()
     scale = ref.abs().max().item() + 1e-6
-    assert err <= tol * scale, (err, scale)
+    ok = err <= tol * scale + (2.0 ** -7 * ref.abs() if y.bf16_stored else 0.0)
+    assert bool(ok.all()), (err.max().item(), scale)
 
 
 CASES = [
@@ -121,7 +136,7 @@ def test_conv_plain(case, precision):
     x = torch.randn(B, H, W, Cin, generator=g)
     w = torch.randn(Cout, KH, KW, Cin, generator=g) / math.sqrt(KH * KW * Cin)
     y, ref = run_conv(x, w, stride=stride, pad=pad, dil=dil, precision=precision)
-    _check(y, ref, 2e-5 if precision == "fp32" else 2e-5)      # same rounded operands, fp32 accumulate
+    _check(y, ref, 2e-5)      # same rounded operands, fp32 accumulate
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

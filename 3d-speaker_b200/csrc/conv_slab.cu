@@ -123,6 +123,7 @@ struct SlabGeom {
     int taps;
     int smem_bytes;
     int tmem_cols;
+    unsigned wp_magic;      // ceil(2^32 / Wp): exact pix / Wp for pix < 2^16
 };
 
 // S: stride in H (1|2); KS: kernel size (1|3)
@@ -173,30 +174,43 @@ conv_slab_kernel(const ConvArgs a, const SlabGeom g, long long n_items, int swap
         const int ho0 = band * g.R;
         const int r_valid = min(g.R, a.Ho - ho0);
         const int hi_base = ho0 * S - PAD;                  // input row of slab row 0
-        // ---- stage the input band: piece (row, pixel, chunk)
+        // ---- stage the input band: piece (row, pixel, chunk); 8 independent 16-byte loads are in
+        // flight per thread before the first store (the loop is latency bound otherwise)
         {
             const int rows_total = g.rows_e + g.rows_o;
             const int pieces = rows_total * g.Wp * 4;
-            for (int idx = threadIdx.x; idx < pieces; idx += kThreads) {
-                const int j = idx & 3;
-                const int pix = idx >> 2;
-                const int row = pix / g.Wp, col = pix - row * g.Wp;
-                // slab row -> (sub-slab, row inside it, input row)
-                int sub = 0, srow = row, hi;
-                if (S == 2 && KS == 3) {
-                    if (row < g.rows_e) { sub = 0; srow = row; hi = hi_base + 2 * row; }
-                    else { sub = 1; srow = row - g.rows_e; hi = hi_base + 2 * srow + 1; }
-                } else if (S == 2) {
-                    hi = hi_base + 2 * row;
-                } else {
-                    hi = hi_base + row;
+            for (int base_idx = 0; base_idx < pieces; base_idx += kThreads * 8) {
+                uint4 v[8];
+                uint32_t dst[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int idx = base_idx + u * kThreads + threadIdx.x;
+                    v[u] = make_uint4(0u, 0u, 0u, 0u);
+                    dst[u] = 0xFFFFFFFFu;
+                    if (idx < pieces) {
+                        const int j = idx & 3;
+                        const int pix = idx >> 2;
+                        const int row = (int)__umulhi((unsigned)pix, g.wp_magic);     // pix / Wp
+                        const int col = pix - row * g.Wp;
+                        // slab row -> (sub-slab, row inside it, input row)
+                        int sub = 0, srow = row, hi;
+                        if (S == 2 && KS == 3) {
+                            if (row < g.rows_e) { sub = 0; srow = row; hi = hi_base + 2 * row; }
+                            else { sub = 1; srow = row - g.rows_e; hi = hi_base + 2 * srow + 1; }
+                        } else if (S == 2) {
+                            hi = hi_base + 2 * row;
+                        } else {
+                            hi = hi_base + row;
+                        }
+                        const int wi = col - PAD;
+                        if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W)
+                            v[u] = ldg16(x + (((long long)b * a.H + hi) * a.W + wi) * a.in_ld + a.in_choff + j * 8);
+                        dst[u] = (sub == 0 ? s_e + j * plane_e : s_o + j * plane_o) + (uint32_t)(srow * g.Wp + col) * 16u;
+                    }
                 }
-                const int wi = col - PAD;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W)
-                    v = ldg16(x + (((long long)b * a.H + hi) * a.W + wi) * a.in_ld + a.in_choff + j * 8);
-                const uint32_t dst = (sub == 0 ? s_e + j * plane_e : s_o + j * plane_o) + (uint32_t)(srow * g.Wp + col) * 16u;
-                sts16(dst, v);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (dst[u] != 0xFFFFFFFFu) sts16(dst[u], v[u]);
             }
             // slack pixels past the staged rows are read by the last tile's shifted views: zero them
             const int slack_e = g.px_e - g.rows_e * g.Wp, slack_o = g.px_o - g.rows_o * g.Wp;
@@ -256,41 +270,51 @@ conv_slab_kernel(const ConvArgs a, const SlabGeom g, long long n_items, int swap
                 const bool ok = (i < r_valid) && (col < a.W);
                 const long long opix = ((long long)b * a.Ho + ho0 + i) * a.Wo + col;
                 const uint32_t taddr = tmem_base + (uint32_t)t * 32u + ((uint32_t)(q * 32) << 16);
+                uint4 rr4[4];
+                if (res != nullptr && ok) {
 #pragma unroll
-                for (int c0 = 0; c0 < kC; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(taddr + c0, r);
+                    for (int e = 0; e < 4; ++e) rr4[e] = ldg16(res + opix * a.res_ld + a.res_choff + e * 8);
+                }
+                uint32_t r[32];
+                {
+                    uint32_t (&r0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[0]);
+                    uint32_t (&r1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[16]);
+                    tmem_ld16(taddr, r0);
+                    tmem_ld16(taddr + 16, r1);
                     tmem_ld_wait();
-                    if (ok) {
-                        float v[16];
+                }
+                if (ok) {
+                    float v[32];
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
-                        if (a.epi_scale != nullptr) {
+                    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+                    if (a.epi_scale != nullptr) {
 #pragma unroll
-                            for (int e = 0; e < 16; e += 4) {
-                                const float4 s4 = __ldg(reinterpret_cast<const float4 *>(a.epi_scale + c0 + e));
-                                const float4 h4 = __ldg(reinterpret_cast<const float4 *>(a.epi_shift + c0 + e));
-                                v[e] = fmaf(v[e], s4.x, h4.x); v[e + 1] = fmaf(v[e + 1], s4.y, h4.y);
-                                v[e + 2] = fmaf(v[e + 2], s4.z, h4.z); v[e + 3] = fmaf(v[e + 3], s4.w, h4.w);
-                            }
+                        for (int e = 0; e < 32; e += 4) {
+                            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(a.epi_scale + e));
+                            const float4 h4 = __ldg(reinterpret_cast<const float4 *>(a.epi_shift + e));
+                            v[e] = fmaf(v[e], s4.x, h4.x); v[e + 1] = fmaf(v[e + 1], s4.y, h4.y);
+                            v[e + 2] = fmaf(v[e + 2], s4.z, h4.z); v[e + 3] = fmaf(v[e + 3], s4.w, h4.w);
                         }
-                        if (res != nullptr) {
-                            const uint4 r0 = ldg16(res + opix * a.res_ld + a.res_choff + c0);
-                            const uint4 r1 = ldg16(res + opix * a.res_ld + a.res_choff + c0 + 8);
-                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const float2 f = unpack2(rr[e]);
-                                v[2 * e] += f.x;
-                                v[2 * e + 1] += f.y;
-                            }
-                        }
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] = apply_act(v[e], a.act);
-                        bf16 *yp = y + opix * a.out_ld + a.out_choff + c0;
-                        *reinterpret_cast<uint4 *>(yp) = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-                        *reinterpret_cast<uint4 *>(yp + 8) = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
                     }
+                    if (res != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t w4[4] = {rr4[e].x, rr4[e].y, rr4[e].z, rr4[e].w};
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                const float2 f = unpack2(w4[h]);
+                                v[e * 8 + 2 * h] += f.x;
+                                v[e * 8 + 2 * h + 1] += f.y;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = apply_act(v[e], a.act);
+                    bf16 *yp = y + opix * a.out_ld + a.out_choff;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 8)
+                        *reinterpret_cast<uint4 *>(yp + e) =
+                            make_uint4(pack2(v[e], v[e + 1]), pack2(v[e + 2], v[e + 3]), pack2(v[e + 4], v[e + 5]), pack2(v[e + 6], v[e + 7]));
                 }
             }
         }
@@ -323,6 +347,8 @@ bool geometry(const ConvArgs &a, SlabGeom &g) {
         if ((g.n_tiles <= 8 && g.smem_bytes <= 110 * 1024) || R == 1) break;
     }
     g.n_bands = (a.Ho + g.R - 1) / g.R;
+    g.wp_magic = (unsigned)(((1ull << 32) + g.Wp - 1) / g.Wp);
+    if ((long long)(g.rows_e + g.rows_o) * g.Wp >= 65536) return false;
     return g.n_tiles <= 16 && g.smem_bytes <= 200 * 1024;
 }
 

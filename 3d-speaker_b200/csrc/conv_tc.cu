@@ -21,6 +21,7 @@
 //              convert and store channels-last.
 // The accumulator is double buffered in TMEM (2 x BLOCK_N columns), so the epilogue of tile i
 // overlaps the gather + MMA of tile i+1.
+#include <cstdlib>
 #include <mutex>
 
 #include "ops.cuh"
@@ -464,6 +465,9 @@ bool conv_tc_supported(const ConvArgs &a, int in_dtype) {
 
 int launch_conv_tc(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s) {
     if (a.M == 0) return SPK_OK;
+    // the first-generation kernel below stays selectable for A/B runs (SPK_CONV_TC_V1=1)
+    static const bool v1 = [] { const char *e = getenv("SPK_CONV_TC_V1"); return e && e[0] == '1'; }();
+    if (!v1) return launch_conv_tc2(a, out_dtype, res_dtype, s);
     const bool res_bf16 = a.res == nullptr ? (out_dtype == SPK_DT_BF16) : (res_dtype == SPK_DT_BF16);
     if (out_dtype == SPK_DT_BF16) {
         if (!res_bf16) {

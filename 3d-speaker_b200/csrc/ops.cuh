@@ -25,6 +25,8 @@ int launch_conv_simt(const ConvArgs &a, int in_dtype, int out_dtype, int res_dty
 // does not qualify
 int launch_conv_tc(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s);
 bool conv_tc_supported(const ConvArgs &a, int in_dtype);
+// second-generation kernel (TMA weights, double-buffered gather; conv_tc2.cu)
+int launch_conv_tc2(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s);
 // slab kernel for the Cin=Cout=32 2-D convs of the CAM++ head (conv_slab.cu)
 bool conv_slab_supported(const ConvArgs &a, int in_dtype, int out_dtype, int res_dtype);
 int launch_conv_slab(const ConvArgs &a, cudaStream_t s);

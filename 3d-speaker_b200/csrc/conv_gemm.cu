@@ -1,0 +1,467 @@
+// 1x1-convolution GEMM for sm_100a: both operands by TMA, BN-ReLU prologue applied in shared
+// memory, tcgen05.mma with TMEM accumulators.  Serves the layers that hold half of CAM++'s
+// FLOPs: the D-TDNN bottleneck 1x1s over the growing concat buffer (layers.py:140-141), the
+// transit layers (layers.py:193-196) and every other stride-1 1x1 conv of the embedding nets.
+//
+//   D[m, n] = sum_k f(A[m, k]) * W[n, k],   f = identity or relu(x*scale_k + shift_k)
+//
+// A is the channels-last activation matrix [M, ld] (a channel window of a wider buffer), W the
+// packed [Cout, K] weights; both are loaded as 128-byte-swizzled K-major tiles by
+// cp.async.bulk.tensor.2d (out-of-range rows / channels are zero-filled by the TMA unit), so
+// the loads need no registers and run a full stage ring (5-6 x 32 KB) ahead of the tensor core.
+// The pre-activation BatchNorm+ReLU of the dense block cannot be folded into the producer of
+// the concat buffer (every layer applies its own BN to all earlier channels), so four
+// "transform" warps rewrite the landed A tile in place with packed bf16x2 math
+// (HFMA2.BF16 + HMNMX2), fence it to the async proxy and hand it to the MMA warp.
+//
+// Warp roles (320 threads, one persistent CTA per SM): 0 TMA producer, 1 TMEM alloc + MMA issue,
+// 2-5 transform, 6-9 epilogue (folded BN, residual, activation, CAM gate; double-buffered TMEM
+// accumulator so the epilogue of tile i overlaps the mainloop of tile i+1).
+#include <cuda.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+
+#include "ops.cuh"
+
+namespace spk {
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 320;
+constexpr int kXformThreads = 128;
+constexpr int kEpilogueThreads = 128;
+constexpr uint32_t kSpinLimit = 1u << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+__device__ __forceinline__ uint4 ldg16(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+__device__ __forceinline__ uint32_t bnrelu2(uint32_t x, uint32_t s, uint32_t b, bool relu) {
+    __nv_bfloat162 r = __hfma2(*reinterpret_cast<__nv_bfloat162 *>(&x), *reinterpret_cast<__nv_bfloat162 *>(&s),
+                               *reinterpret_cast<__nv_bfloat162 *>(&b));
+    if (relu) r = __hmax2(r, __floats2bfloat162_rn(0.f, 0.f));
+    return *reinterpret_cast<uint32_t *>(&r);
+}
+
+template <int BLOCK_N> struct Cfg {
+    static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+    static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : 2 * BLOCK_N;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
+};
+
+template <int BLOCK_N, typename TOut, typename TRes>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const bf16 *__restrict__ pro_shift_bf,
+                 int n_tiles_n, long long n_tiles, const __grid_constant__ CUtensorMap amap,
+                 const __grid_constant__ CUtensorMap wmap) {
+    using C = Cfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (base - raw) + C::kStages * C::kStageBytes);
+    const uint32_t bar0 = smem_u32(bars);
+    // [0,S) landed (TMA tx)  [S,2S) ready (transformed)  [2S,3S) empty  then accum full/empty x2
+    auto land_bar = [&](int s) { return bar0 + 8u * s; };
+    auto ready_bar = [&](int s) { return bar0 + 8u * (C::kStages + s); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + s); };
+    auto accf_bar = [&](int b) { return bar0 + 8u * (3 * C::kStages + b); };
+    auto acce_bar = [&](int b) { return bar0 + 8u * (3 * C::kStages + 2 + b); };
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + 3 * C::kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool has_pro = pro_scale_bf != nullptr;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(land_bar(s), 1);
+            mbar_init(ready_bar(s), kXformThreads);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(accf_bar(b), 1);
+            mbar_init(acce_bar(b), kEpilogueThreads);
+        }
+        fence_barrier_init();
+        prefetch_tmap(&amap);
+        prefetch_tmap(&wmap);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), C::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nk = (a.K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const long long mt = tile / n_tiles_n;
+                const int nt = (int)(tile - mt * n_tiles_n);
+                for (int kc = 0; kc < nk; ++kc) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = base + stage * C::kStageBytes;
+                    mbar_arrive_expect_tx(land_bar(stage), C::kStageBytes);
+                    tma_load_2d(sa, &amap, kc * BLOCK_K, (int)(mt * BLOCK_M), land_bar(stage));
+                    tma_load_2d(sa + C::kABytes, &wmap, kc * BLOCK_K, nt * BLOCK_N, land_bar(stage));
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        constexpr uint32_t idesc = make_idesc(BLOCK_N);
+        int stage = 0;
+        uint32_t phase = 0, it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = it & 1u, acc_phase = (it >> 1) & 1u;
+            mbar_wait(acce_bar(buf), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+            for (int kc = 0; kc < nk; ++kc) {
+                mbar_wait(has_pro ? ready_bar(stage) : land_bar(stage), phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = base + stage * C::kStageBytes;
+                    const uint64_t ad = make_desc_sw128(sa), bd = make_desc_sw128(sa + C::kABytes);
+#pragma unroll
+                    for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+                        umma_bf16(d_tmem, ad + 2u * kk, bd + 2u * kk, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(empty_bar(stage));
+                    if (kc == nk - 1) umma_commit(accf_bar(buf));
+                }
+                __syncwarp();
+                if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp < 6) {
+        // =========================== transform (BN-ReLU prologue, in place) ===========================
+        if (has_pro) {
+            const int t = threadIdx.x - 64;            // 0..127
+            const int j = t & 7, r0 = t >> 3;          // 16-byte column j, rows r0 + 16*i
+            const uint32_t sw_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((j ^ (r0 & 7)) << 4));
+            const bool relu = a.pro_relu != 0;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int kc = 0; kc < nk; ++kc) {
+                    // scale/shift of this thread's 8 channels (zero beyond K: relu(0*x+0) = 0)
+                    const int c = kc * BLOCK_K + j * 8;
+                    uint4 s4 = make_uint4(0u, 0u, 0u, 0u), h4 = s4;
+                    if (c < a.K) {
+                        s4 = ldg16(pro_scale_bf + c);
+                        h4 = ldg16(pro_shift_bf + c);
+                    }
+                    mbar_wait(land_bar(stage), phase);
+                    const uint32_t sa = base + stage * C::kStageBytes + sw_off;
+                    uint4 v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = lds16(sa + i * 2048);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v[i].x = bnrelu2(v[i].x, s4.x, h4.x, relu);
+                        v[i].y = bnrelu2(v[i].y, s4.y, h4.y, relu);
+                        v[i].z = bnrelu2(v[i].z, s4.z, h4.z, relu);
+                        v[i].w = bnrelu2(v[i].w, s4.w, h4.w, relu);
+                        sts16(sa + i * 2048, v[i]);
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(ready_bar(stage));
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // =========================== epilogue ===========================
+        const int q = warp & 3;                       // warps 6..9 -> lane quarters 2,3,0,1
+        const int row = q * 32 + lane;
+        const int HoWo = a.Ho * a.Wo;
+        TOut *y = static_cast<TOut *>(a.y);
+        const TRes *res = static_cast<const TRes *>(a.res);
+        uint32_t it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const long long mt = tile / n_tiles_n;
+            const int nt = (int)(tile - mt * n_tiles_n);
+            const long long m = mt * BLOCK_M + row;
+            const int n0 = nt * BLOCK_N;
+            const uint32_t buf = it & 1u, acc_phase = (it >> 1) & 1u;
+            const float *grow = nullptr;
+            if (a.gate != nullptr && m < a.M) {
+                const int b = (int)(m / HoWo);
+                const int wo = (int)(m % a.Wo);
+                grow = a.gate + ((long long)b * a.gate_nwin + wo / a.gate_win) * a.Cout;
+            }
+            mbar_wait(accf_bar(buf), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+                const int n = n0 + c0;
+                if (n >= a.Cout) break;
+                uint32_t r[16];
+                tmem_ld16(taddr + c0, r);
+                tmem_ld_wait();
+                if (m < a.M) {
+                    float v[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+                    if (a.epi_scale != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(a.epi_scale + n + e));
+                            const float4 h4 = __ldg(reinterpret_cast<const float4 *>(a.epi_shift + n + e));
+                            v[e] = fmaf(v[e], s4.x, h4.x); v[e + 1] = fmaf(v[e + 1], s4.y, h4.y);
+                            v[e + 2] = fmaf(v[e + 2], s4.z, h4.z); v[e + 3] = fmaf(v[e + 3], s4.w, h4.w);
+                        }
+                    }
+                    if (res != nullptr) {
+                        const TRes *rp = res + m * a.res_ld + a.res_choff + n;
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] += to_f32(rp[e]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = apply_act(v[e], a.act);
+                    if (grow != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(grow + n + e));
+                            v[e] *= g4.x; v[e + 1] *= g4.y; v[e + 2] *= g4.z; v[e + 3] *= g4.w;
+                        }
+                    }
+                    TOut *yp = y + m * a.out_ld + a.out_choff + n;
+                    if constexpr (sizeof(TOut) == 2) {
+                        *reinterpret_cast<uint4 *>(yp) = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+                        *reinterpret_cast<uint4 *>(yp + 8) = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4)
+                            *reinterpret_cast<float4 *>(yp + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acce_bar(buf));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// ------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// [rows, cols] bf16 matrix with row pitch ld (elements), K-major box {64, box_rows}, 128B swizzle
+int make_map(const void *ptr, long long rows, int cols, long long ld, int box_rows, CUtensorMap *out) {
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return SPK_ERR_CUDA;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(bf16)};
+    const cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%d ld=%lld", (int)r, rows, cols, ld);
+        return SPK_ERR_CUDA;
+    }
+    return SPK_OK;
+}
+
+int bf16_vector(const float *src, int n, const bf16 **out, cudaStream_t s) {
+    static std::mutex mu;
+    static std::map<const float *, bf16 *> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(src);
+    if (it != cache.end()) {
+        *out = it->second;
+        return SPK_OK;
+    }
+    bf16 *d = nullptr;
+    SPK_CUDA_OK(cudaMalloc(&d, (size_t)(n + 8) * sizeof(bf16)));
+    SPK_CUDA_OK(cudaMemsetAsync(d, 0, (size_t)(n + 8) * sizeof(bf16), s));
+    int rc = launch_f32_to_bf16(src, d, n, s);
+    if (rc != SPK_OK) return rc;
+    cache[src] = d;
+    *out = d;
+    return SPK_OK;
+}
+
+template <int BLOCK_N, typename TOut, typename TRes>
+int launch_one(const ConvArgs &a, cudaStream_t s) {
+    using C = Cfg<BLOCK_N>;
+    auto kern = conv_gemm_kernel<BLOCK_N, TOut, TRes>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes); });
+    if (attr_err != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(conv_gemm) failed: %s", cudaGetErrorString(attr_err));
+        return SPK_ERR_CUDA;
+    }
+    CUtensorMap amap, wmap;
+    int rc = make_map(static_cast<const bf16 *>(a.x) + a.in_choff, a.M, a.Cin, a.in_ld, BLOCK_M, &amap);
+    if (rc == SPK_OK) rc = make_map(a.w, a.Cout, a.K, a.K, BLOCK_N, &wmap);
+    if (rc != SPK_OK) return rc;
+    const bf16 *ps = nullptr, *ph = nullptr;
+    if (a.pro_scale != nullptr) {
+        rc = bf16_vector(a.pro_scale, a.Cin, &ps, s);
+        if (rc == SPK_OK) rc = bf16_vector(a.pro_shift, a.Cin, &ph, s);
+        if (rc != SPK_OK) return rc;
+    }
+    const long long mt = (a.M + BLOCK_M - 1) / BLOCK_M;
+    const int ntn = (a.Cout + BLOCK_N - 1) / BLOCK_N;
+    const long long tiles = mt * ntn;
+    const long long grid = std::min<long long>(tiles, sm_count());
+    kern<<<(unsigned)grid, kThreads, C::kSmemBytes, s>>>(a, ps, ph, ntn, tiles, amap, wmap);
+    return check_launch("conv_gemm_kernel");
+}
+
+template <typename TOut, typename TRes>
+int launch_n(const ConvArgs &a, cudaStream_t s) {
+    if (a.Cout <= 32) return launch_one<32, TOut, TRes>(a, s);
+    if (a.Cout <= 64) return launch_one<64, TOut, TRes>(a, s);
+    if (a.Cout <= 128) return launch_one<128, TOut, TRes>(a, s);
+    return launch_one<256, TOut, TRes>(a, s);
+}
+
+}  // namespace
+
+bool conv_gemm_supported(const ConvArgs &a, int in_dtype) {
+    if (!conv_tc_supported(a, in_dtype)) return false;
+    if (a.KH != 1 || a.KW != 1 || a.sh != 1 || a.sw != 1 || a.ph != 0 || a.pw != 0) return false;
+    if (a.Ho != a.H || a.Wo != a.W) return false;
+    if ((reinterpret_cast<uintptr_t>(a.x) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.w) & 15) != 0) return false;
+    return true;
+}
+
+int launch_conv_gemm(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s) {
+    if (a.M == 0) return SPK_OK;
+    const bool res_bf16 = a.res == nullptr ? (out_dtype == SPK_DT_BF16) : (res_dtype == SPK_DT_BF16);
+    if (out_dtype == SPK_DT_BF16) {
+        if (!res_bf16) {
+            set_error("conv_gemm: a bf16 output takes a bf16 residual");
+            return SPK_ERR_UNSUPPORTED;
+        }
+        return launch_n<bf16, bf16>(a, s);
+    }
+    return res_bf16 ? launch_n<float, bf16>(a, s) : launch_n<float, float>(a, s);
+}
+
+}  // namespace spk

@@ -260,6 +260,13 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                             a.w = wb;
                             rc = launch_conv_slab(a, s);
                         }
+                    } else if (m->precision == SPK_PREC_BF16 && conv_gemm_supported(a, dt(o.in_buf))) {
+                        const __nv_bfloat16 *wb = nullptr;
+                        rc = param_bf16(m, o.w, &wb, s);
+                        if (rc == SPK_OK) {
+                            a.w = wb;
+                            rc = launch_conv_gemm(a, dt(o.out_buf), dt(o.res_buf), s);
+                        }
                     } else if (m->precision == SPK_PREC_BF16 && conv_tc_supported(a, dt(o.in_buf))) {
                         const __nv_bfloat16 *wb = nullptr;
                         rc = param_bf16(m, o.w, &wb, s);

@@ -27,6 +27,9 @@ int launch_conv_tc(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t
 bool conv_tc_supported(const ConvArgs &a, int in_dtype);
 // second-generation kernel (TMA weights, double-buffered gather; conv_tc2.cu)
 int launch_conv_tc2(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s);
+// TMA-fed GEMM for stride-1 1x1 convs with the BN-ReLU prologue applied in shared memory (conv_gemm.cu)
+bool conv_gemm_supported(const ConvArgs &a, int in_dtype);
+int launch_conv_gemm(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s);
 // slab kernel for the Cin=Cout=32 2-D convs of the CAM++ head (conv_slab.cu)
 bool conv_slab_supported(const ConvArgs &a, int in_dtype, int out_dtype, int res_dtype);
 int launch_conv_slab(const ConvArgs &a, cudaStream_t s);

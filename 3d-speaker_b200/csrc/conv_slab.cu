@@ -18,6 +18,8 @@
 // tiles x taps x 2 tcgen05.mma (M=128, N=32, K=16) -> tcgen05.commit -> all warps run the
 // epilogue (TMEM -> folded BN, residual, ReLU -> bf16 store).  Two CTAs share an SM so one
 // band's loads/stores overlap the other's MMAs.
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
@@ -325,13 +327,253 @@ conv_slab_kernel(const ConvArgs a, const SlabGeom g, long long n_items, int swap
     if (warp == 0) tmem_dealloc(tmem_base, g.tmem_cols);
 }
 
-bool geometry(const ConvArgs &a, SlabGeom &g) {
+
+// ====================================================================================== v2
+// Second generation (default): the band is staged by TMA instead of by threads.  The input is
+// described to the TMA unit as a 5-D tensor {8 channels (16 B), 4 pieces, W, H, B}; one request
+// per (slab row, 16-byte piece j) with box {8,1,Wp,1,1} starting at column -PAD lands exactly one
+// row of channel plane j (pixels 16 B apart), and rows / columns outside the image are
+// zero-filled by the hardware, so the conv padding costs nothing.  Two slab buffers and two TMEM
+// accumulator sets let the three roles run one band apart:
+//   warp 0      TMA producer (weights are staged once by all threads before the role split)
+//   warp 1      MMA issuer (+ TMEM allocation)
+//   warps 2-9   epilogue (two warps per TMEM lane quarter, alternating tiles)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, int c4,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+constexpr int kThreads2 = 320;
+constexpr int kEpiThreads2 = 256;
+
+template <int S, int KS>
+__global__ void __launch_bounds__(kThreads2, 1)
+conv_slab2_kernel(const ConvArgs a, const SlabGeom g, long long n_items, const __grid_constant__ CUtensorMap xmap) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int TAPS = KS * KS;
+    constexpr int PAD = (KS - 1) / 2;
+    const uint32_t s_w = smem_u32(smem);
+    const uint32_t slab_bytes = 64u * (uint32_t)(g.px_e + g.px_o);
+    const uint32_t s_slab0 = s_w + TAPS * 4 * 32 * 16;
+    const uint32_t s_bar = s_slab0 + 2u * slab_bytes;
+    // barriers: slab_full[2], slab_empty[2], acc_full[2], acc_empty[2]
+    auto sfull = [&](int i) { return s_bar + 8u * i; };
+    auto sempty = [&](int i) { return s_bar + 8u * (2 + i); };
+    auto afull = [&](int i) { return s_bar + 8u * (4 + i); };
+    auto aempty = [&](int i) { return s_bar + 8u * (6 + i); };
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + (s_bar - s_w) + 64);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t plane_e = (uint32_t)g.px_e * 16u, plane_o = (uint32_t)g.px_o * 16u;
+    const uint32_t acc_cols = (uint32_t)g.n_tiles * 32u;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(sfull(i), 1);
+            mbar_init(sempty(i), 1);
+            mbar_init(afull(i), 1);
+            mbar_init(aempty(i), kEpiThreads2);
+        }
+        fence_barrier_init();
+        prefetch_tmap(&xmap);
+    }
+    if (warp == 1) {
+        __syncwarp();
+        tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), g.tmem_cols);
+    }
+    {   // weights -> smem planes; slack pixels of both slabs -> 0 (TMA never writes them)
+        const bf16 *w = static_cast<const bf16 *>(a.w);
+        for (int idx = threadIdx.x; idx < kC * TAPS * 4; idx += kThreads2) {
+            const int j = idx & 3, t = (idx >> 2) % TAPS, n = idx / (4 * TAPS);
+            sts16(s_w + (uint32_t)(((t * 4 + j) * 32 + n) * 16), ldg16(w + ((long long)n * TAPS + t) * kC + j * 8));
+        }
+        const int slack_e = g.px_e - g.rows_e * g.Wp, slack_o = g.px_o - g.rows_o * g.Wp;
+        for (int idx = threadIdx.x; idx < 2 * (slack_e + slack_o) * 4; idx += kThreads2) {
+            const int j = idx & 3;
+            int p = idx >> 2;
+            const uint32_t sb = s_slab0 + (p >= slack_e + slack_o ? slab_bytes : 0u);
+            if (p >= slack_e + slack_o) p -= slack_e + slack_o;
+            const uint32_t dst = (p < slack_e) ? sb + j * plane_e + (uint32_t)(g.rows_e * g.Wp + p) * 16u
+                                               : sb + 4u * plane_e + j * plane_o + (uint32_t)(g.rows_o * g.Wp + (p - slack_e)) * 16u;
+            sts16(dst, make_uint4(0u, 0u, 0u, 0u));
+        }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            uint32_t it = 0;
+            const uint32_t row_bytes = (uint32_t)g.Wp * 16u;
+            for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int b = (int)(item / g.n_bands);
+                const int band = (int)(item - (long long)b * g.n_bands);
+                const int hi_base = band * g.R * S - PAD;
+                const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+                mbar_wait(sempty(buf), ph ^ 1u);
+                const uint32_t se = s_slab0 + buf * slab_bytes, so = se + 4u * plane_e;
+                mbar_arrive_expect_tx(sfull(buf), (uint32_t)(g.rows_e + g.rows_o) * row_bytes * 4u);
+                if (S == 1) {
+                    // one request per channel plane: box {8,1,Wp,rows_e,1}
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) tma_load_5d(se + j * plane_e, &xmap, 0, j, -PAD, hi_base, b, sfull(buf));
+                } else {
+                    for (int r = 0; r < g.rows_e; ++r)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            tma_load_5d(se + j * plane_e + r * row_bytes, &xmap, 0, j, -PAD, hi_base + 2 * r, b, sfull(buf));
+                    for (int r = 0; r < g.rows_o; ++r)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            tma_load_5d(so + j * plane_o + r * row_bytes, &xmap, 0, j, -PAD, hi_base + 2 * r + 1, b, sfull(buf));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        uint32_t it = 0;
+        for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+            mbar_wait(aempty(buf), ph ^ 1u);
+            mbar_wait(sfull(buf), ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t se = s_slab0 + buf * slab_bytes, so = se + 4u * plane_e;
+                for (int t = 0; t < g.n_tiles; ++t) {
+                    const uint32_t d = tmem_base + buf * acc_cols + (uint32_t)t * 32u;
+#pragma unroll
+                    for (int kh = 0; kh < KS; ++kh)
+#pragma unroll
+                        for (int kw = 0; kw < KS; ++kw) {
+                            uint32_t sbase, plane;
+                            int off;
+                            if (S == 2 && KS == 3) {
+                                if (kh & 1) { sbase = so; plane = plane_o; off = kw; }
+                                else { sbase = se; plane = plane_e; off = (kh >> 1) * g.Wp + kw; }
+                            } else {
+                                sbase = se; plane = plane_e; off = kh * g.Wp + kw;
+                            }
+                            const uint32_t a_addr = sbase + (uint32_t)(t * 128 + off) * 16u;
+                            const uint32_t b_addr = s_w + (uint32_t)((kh * KS + kw) * 4 * 32 * 16);
+#pragma unroll
+                            for (int half = 0; half < 2; ++half)
+                                umma_bf16(d, make_desc_nosw(a_addr + 2u * half * plane, plane, 128u),
+                                          make_desc_nosw(b_addr + 2u * half * 512u, 512u, 128u), kIdescN32,
+                                          (kh | kw | half) ? 1u : 0u);
+                        }
+                }
+                umma_commit(sempty(buf));      // slab reusable once these MMAs retire
+                umma_commit(afull(buf));
+            }
+            __syncwarp();
+        }
+    } else {
+        // =========================== epilogue ===========================
+        const int q = warp & 3;
+        const int tsel = (warp - 2) >> 2;           // 0 or 1: even / odd tiles
+        bf16 *y = static_cast<bf16 *>(a.y);
+        const bf16 *res = static_cast<const bf16 *>(a.res);
+        uint32_t it = 0;
+        for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int b = (int)(item / g.n_bands);
+            const int band = (int)(item - (long long)b * g.n_bands);
+            const int ho0 = band * g.R;
+            const int r_valid = min(g.R, a.Ho - ho0);
+            const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+            bool waited = false;
+            for (int t = tsel; t < g.n_tiles; t += 2) {
+                const int p = t * 128 + q * 32 + lane;
+                const int i = (int)__umulhi((unsigned)p, g.wp_magic), col = p - i * g.Wp;
+                const bool ok = (i < r_valid) && (col < a.W);
+                const long long opix = ((long long)b * a.Ho + ho0 + i) * a.Wo + col;
+                uint4 rr4[4];
+                if (res != nullptr && ok) {      // independent of the MMAs: issue before waiting
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) rr4[e] = ldg16(res + opix * a.res_ld + a.res_choff + e * 8);
+                }
+                if (!waited) {
+                    mbar_wait(afull(buf), ph);
+                    tc_fence_after();
+                    waited = true;
+                }
+                const uint32_t taddr = tmem_base + buf * acc_cols + (uint32_t)t * 32u + ((uint32_t)(q * 32) << 16);
+                uint32_t r[32];
+                {
+                    uint32_t (&r0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[0]);
+                    uint32_t (&r1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[16]);
+                    tmem_ld16(taddr, r0);
+                    tmem_ld16(taddr + 16, r1);
+                    tmem_ld_wait();
+                }
+                if (ok) {
+                    float v[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+                    if (a.epi_scale != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(a.epi_scale + e));
+                            const float4 h4 = __ldg(reinterpret_cast<const float4 *>(a.epi_shift + e));
+                            v[e] = fmaf(v[e], s4.x, h4.x); v[e + 1] = fmaf(v[e + 1], s4.y, h4.y);
+                            v[e + 2] = fmaf(v[e + 2], s4.z, h4.z); v[e + 3] = fmaf(v[e + 3], s4.w, h4.w);
+                        }
+                    }
+                    if (res != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t w4[4] = {rr4[e].x, rr4[e].y, rr4[e].z, rr4[e].w};
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                const float2 f = unpack2(w4[h]);
+                                v[e * 8 + 2 * h] += f.x;
+                                v[e * 8 + 2 * h + 1] += f.y;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = apply_act(v[e], a.act);
+                    bf16 *yp = y + opix * a.out_ld + a.out_choff;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 8)
+                        *reinterpret_cast<uint4 *>(yp + e) =
+                            make_uint4(pack2(v[e], v[e + 1]), pack2(v[e + 2], v[e + 3]), pack2(v[e + 4], v[e + 5]), pack2(v[e + 6], v[e + 7]));
+                }
+            }
+            if (!waited) {                      // this warp had no tile in the band: still keep the phase in step
+                mbar_wait(afull(buf), ph);
+                tc_fence_after();
+            }
+            tc_fence_before();
+            mbar_arrive(aempty(buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
+}
+
+bool geometry(const ConvArgs &a, SlabGeom &g, bool v2 = false) {
     const int KS = a.KH;
     g.taps = KS * KS;
     g.Wp = a.W + KS - 1;
     int R = 768 / g.Wp;
     if (R < 1) R = 1;
     if (R > a.Ho) R = a.Ho;
+    const int smem_cap = v2 ? 210 * 1024 : 110 * 1024;
     for (;; --R) {
         g.R = R;
         g.n_tiles = (R * g.Wp + 127) / 128;
@@ -339,17 +581,19 @@ bool geometry(const ConvArgs &a, SlabGeom &g) {
         else if (KS == 3) { g.rows_e = R + 1; g.rows_o = R; }
         else { g.rows_e = R; g.rows_o = 0; }
         const int max_off_e = (a.sh == 1 ? (KS - 1) * g.Wp : (KS == 3 ? g.Wp : 0)) + (KS - 1);
-        g.px_e = std::max(g.rows_e * g.Wp, g.n_tiles * 128 + max_off_e) + 8;
-        g.px_o = g.rows_o ? std::max(g.rows_o * g.Wp, g.n_tiles * 128 + (KS - 1)) + 8 : 0;
-        g.smem_bytes = g.taps * 4 * 32 * 16 + 64 * (g.px_e + g.px_o) + 64;
-        int cols = g.n_tiles * 32;
+        g.px_e = (std::max(g.rows_e * g.Wp, g.n_tiles * 128 + max_off_e) + 8 + 7) & ~7;
+        g.px_o = g.rows_o ? (std::max(g.rows_o * g.Wp, g.n_tiles * 128 + (KS - 1)) + 8 + 7) & ~7 : 0;
+        const int slab = 64 * (g.px_e + g.px_o);
+        g.smem_bytes = g.taps * 4 * 32 * 16 + (v2 ? 2 : 1) * slab + 128;
+        const int cols = g.n_tiles * 32 * (v2 ? 2 : 1);
         g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-        if ((g.n_tiles <= 8 && g.smem_bytes <= 110 * 1024) || R == 1) break;
+        if ((cols <= (v2 ? 512 : 256) && g.smem_bytes <= smem_cap) || R == 1) break;
     }
     g.n_bands = (a.Ho + g.R - 1) / g.R;
     g.wp_magic = (unsigned)(((1ull << 32) + g.Wp - 1) / g.Wp);
-    if ((long long)(g.rows_e + g.rows_o) * g.Wp >= 65536) return false;
-    return g.n_tiles <= 16 && g.smem_bytes <= 200 * 1024;
+    if ((long long)(g.rows_e + g.rows_o) * g.Wp >= 65536 || g.n_tiles * 128 >= 65536) return false;
+    if (v2 && (g.Wp > 256 || g.rows_e > 256)) return false;          // TMA box limits
+    return g.n_tiles * 32 * (v2 ? 2 : 1) <= 512 && g.smem_bytes <= (v2 ? 220 : 200) * 1024;
 }
 
 template <int S, int KS>
@@ -362,13 +606,69 @@ int launch(const ConvArgs &a, const SlabGeom &g, cudaStream_t s) {
         set_error("cudaFuncSetAttribute(conv_slab) failed: %s", cudaGetErrorString(attr_err));
         return SPK_ERR_CUDA;
     }
-    static const int swap = [] { const char *e = getenv("SPK_SLAB_SWAP_LBO_SBO"); return (e && e[0] == '1') ? 1 : 0; }();
     const long long items = (long long)a.B * g.n_bands;
     int per_sm = std::min(2, std::min(512 / g.tmem_cols, (227 * 1024) / (g.smem_bytes + 1024)));
     if (per_sm < 1) per_sm = 1;
     long long grid = std::min<long long>(items, (long long)sm_count() * per_sm);
-    kern<<<(unsigned)grid, kThreads, g.smem_bytes, s>>>(a, g, items, swap);
+    kern<<<(unsigned)grid, kThreads, g.smem_bytes, s>>>(a, g, items, 0);
     return check_launch("conv_slab_kernel");
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+template <int S, int KS>
+int launch2(const ConvArgs &a, const SlabGeom &g, cudaStream_t s) {
+    auto kern = conv_slab2_kernel<S, KS>;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
+    if (attr_err != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(conv_slab2) failed: %s", cudaGetErrorString(attr_err));
+        return SPK_ERR_CUDA;
+    }
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return SPK_ERR_CUDA;
+    }
+    // input as {8 ch, 4 pieces, W, H, B}; one box = one (or rows_e) row(s) of one channel plane
+    CUtensorMap xmap;
+    const cuuint64_t e = sizeof(bf16);
+    const cuuint64_t dims[5] = {8, 4, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)a.in_ld * e, (cuuint64_t)a.W * a.in_ld * e,
+                                   (cuuint64_t)a.H * a.W * a.in_ld * e};
+    const cuuint32_t box[5] = {8, 1, (cuuint32_t)g.Wp, (cuuint32_t)(S == 1 ? g.rows_e : 1), 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                    const_cast<bf16 *>(static_cast<const bf16 *>(a.x) + a.in_choff), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(slab) failed (%d): W=%d H=%d B=%d ld=%d", (int)r, a.W, a.H, a.B, a.in_ld);
+        return SPK_ERR_CUDA;
+    }
+    const long long items = (long long)a.B * g.n_bands;
+    const long long grid = std::min<long long>(items, sm_count());
+    kern<<<(unsigned)grid, kThreads2, g.smem_bytes, s>>>(a, g, items, xmap);
+    return check_launch("conv_slab2_kernel");
+}
+
+bool use_v1() {
+    static const bool v = [] { const char *e = getenv("SPK_SLAB_V1"); return e && e[0] == '1'; }();
+    return v;
 }
 
 }  // namespace
@@ -384,17 +684,22 @@ bool conv_slab_supported(const ConvArgs &a, int in_dtype, int out_dtype, int res
     if (a.res != nullptr && (a.res_ld % 8 || a.res_choff % 8)) return false;
     if (a.Wo != a.W || a.Ho != (a.H + 2 * a.ph - a.KH) / a.sh + 1) return false;
     if (a.KH == 1 && a.sh == 1) return false;      // plain 1x1: the generic GEMM path is already ideal
+    if ((reinterpret_cast<uintptr_t>(a.x) & 15) != 0) return false;
     SlabGeom g;
-    return geometry(a, g);
+    return geometry(a, g, !use_v1()) || geometry(a, g, false);
 }
 
 int launch_conv_slab(const ConvArgs &a, cudaStream_t s) {
+    if (a.B == 0) return SPK_OK;
     SlabGeom g;
-    if (!geometry(a, g)) {
+    if (!use_v1() && geometry(a, g, true)) {
+        if (a.KH == 3) return a.sh == 1 ? launch2<1, 3>(a, g, s) : launch2<2, 3>(a, g, s);
+        return launch2<2, 1>(a, g, s);
+    }
+    if (!geometry(a, g, false)) {
         set_error("conv_slab: geometry does not fit");
         return SPK_ERR_UNSUPPORTED;
     }
-    if (a.B == 0) return SPK_OK;
     if (a.KH == 3) return a.sh == 1 ? launch<1, 3>(a, g, s) : launch<2, 3>(a, g, s);
     return launch<2, 1>(a, g, s);
 }

@@ -117,7 +117,7 @@ __device__ __forceinline__ float2 unpack2(uint32_t v) {
 
 struct SlabGeom {
     int R;          // output rows per band
-    int Wp;         // W + KW - 1
+    int Wp;         // staged row pitch in pixels: W + KW - 1 rounded up to a multiple of 8
     int n_bands;    // per segment
     int n_tiles;    // 128-pixel MMA tiles per band
     int rows_e, rows_o;     // input rows staged per sub-slab
@@ -329,15 +329,15 @@ conv_slab_kernel(const ConvArgs a, const SlabGeom g, long long n_items, int swap
 
 
 // ====================================================================================== v2
-// Second generation (default): the band is staged by TMA instead of by threads.  The input is
-// described to the TMA unit as a 5-D tensor {8 channels (16 B), 4 pieces, W, H, B}; one request
-// per (slab row, 16-byte piece j) with box {8,1,Wp,1,1} starting at column -PAD lands exactly one
-// row of channel plane j (pixels 16 B apart), and rows / columns outside the image are
-// zero-filled by the hardware, so the conv padding costs nothing.  Two slab buffers and two TMEM
-// accumulator sets let the three roles run one band apart:
-//   warp 0      TMA producer (weights are staged once by all threads before the role split)
-//   warp 1      MMA issuer (+ TMEM allocation)
-//   warps 2-9   epilogue (two warps per TMEM lane quarter, alternating tiles)
+// Second generation (default): warp-specialised and double buffered.  Two slab buffers and two
+// TMEM accumulator sets let the three roles run one band apart:
+//   warps 0-3   producers: 16-byte cp.async (LDGSTS, zero-fill for the conv padding) straight
+//               into the channel planes - no register staging, so each thread has its ~33 copies
+//               of a band in flight at once instead of paying the L2 latency per batch
+//               (a TMA tiled load was tried first: with a 16-byte innermost box the TMA unit
+//               processes one 16-byte line at a time and took ~10 us per band)
+//   warp 4      MMA issuer (+ TMEM allocation)
+//   warps 5-12  epilogue (two warps per TMEM lane quarter, alternating tiles)
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -354,12 +354,19 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
-constexpr int kThreads2 = 320;
+constexpr int kProdThreads2 = 128;
 constexpr int kEpiThreads2 = 256;
+constexpr int kThreads2 = kProdThreads2 + 32 + kEpiThreads2;      // 416
+
+// 16-byte async copy global -> shared; src_bytes = 0 writes zeros (conv padding)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int S, int KS>
 __global__ void __launch_bounds__(kThreads2, 1)
-conv_slab2_kernel(const ConvArgs a, const SlabGeom g, long long n_items, const __grid_constant__ CUtensorMap xmap) {
+conv_slab2_kernel(const ConvArgs a, const SlabGeom g, long long n_items) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int TAPS = KS * KS;
     constexpr int PAD = (KS - 1) / 2;
@@ -379,15 +386,14 @@ conv_slab2_kernel(const ConvArgs a, const SlabGeom g, long long n_items, const _
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(sfull(i), 1);
+            mbar_init(sfull(i), kProdThreads2);
             mbar_init(sempty(i), 1);
             mbar_init(afull(i), 1);
             mbar_init(aempty(i), kEpiThreads2);
         }
         fence_barrier_init();
-        prefetch_tmap(&xmap);
     }
-    if (warp == 1) {
+    if (warp == 4) {
         __syncwarp();
         tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), g.tmem_cols);
     }
@@ -414,36 +420,44 @@ conv_slab2_kernel(const ConvArgs a, const SlabGeom g, long long n_items, const _
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // =========================== TMA producer ===========================
-        if (lane == 0) {
-            uint32_t it = 0;
-            const uint32_t row_bytes = (uint32_t)g.Wp * 16u;
-            for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int b = (int)(item / g.n_bands);
-                const int band = (int)(item - (long long)b * g.n_bands);
-                const int hi_base = band * g.R * S - PAD;
-                const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
-                mbar_wait(sempty(buf), ph ^ 1u);
-                const uint32_t se = s_slab0 + buf * slab_bytes, so = se + 4u * plane_e;
-                mbar_arrive_expect_tx(sfull(buf), (uint32_t)(g.rows_e + g.rows_o) * row_bytes * 4u);
-                if (S == 1) {
-                    // one request per channel plane: box {8,1,Wp,rows_e,1}
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) tma_load_5d(se + j * plane_e, &xmap, 0, j, -PAD, hi_base, b, sfull(buf));
+    if (warp < 4) {
+        // =========================== producers (cp.async) ===========================
+        const bf16 *x = static_cast<const bf16 *>(a.x);
+        uint32_t it = 0;
+        const int rows_total = g.rows_e + g.rows_o;
+        const int pieces = rows_total * g.Wp * 4;
+        for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int b = (int)(item / g.n_bands);
+            const int band = (int)(item - (long long)b * g.n_bands);
+            const int hi_base = band * g.R * S - PAD;
+            const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+            mbar_wait(sempty(buf), ph ^ 1u);
+            const uint32_t se = s_slab0 + buf * slab_bytes, so = se + 4u * plane_e;
+            for (int idx = threadIdx.x; idx < pieces; idx += kProdThreads2) {
+                const int j = idx & 3;
+                const int pix = idx >> 2;
+                const int row = (int)__umulhi((unsigned)pix, g.wp_magic);
+                const int col = pix - row * g.Wp;
+                int sub = 0, srow = row, hi;
+                if (S == 2 && KS == 3) {
+                    if (row < g.rows_e) { sub = 0; srow = row; hi = hi_base + 2 * row; }
+                    else { sub = 1; srow = row - g.rows_e; hi = hi_base + 2 * srow + 1; }
+                } else if (S == 2) {
+                    hi = hi_base + 2 * row;
                 } else {
-                    for (int r = 0; r < g.rows_e; ++r)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tma_load_5d(se + j * plane_e + r * row_bytes, &xmap, 0, j, -PAD, hi_base + 2 * r, b, sfull(buf));
-                    for (int r = 0; r < g.rows_o; ++r)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            tma_load_5d(so + j * plane_o + r * row_bytes, &xmap, 0, j, -PAD, hi_base + 2 * r + 1, b, sfull(buf));
+                    hi = hi_base + row;
                 }
+                const int wi = col - PAD;
+                const bool ok = hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
+                const bf16 *src = ok ? x + (((long long)b * a.H + hi) * a.W + wi) * a.in_ld + a.in_choff + j * 8 : x;
+                const uint32_t dst = (sub == 0 ? se + j * plane_e : so + j * plane_o) + (uint32_t)(srow * g.Wp + col) * 16u;
+                cp_async16(dst, src, ok ? 16u : 0u);
             }
+            cp_async_wait_all();
+            fence_proxy_async();
+            mbar_arrive(sfull(buf));
         }
-    } else if (warp == 1) {
+    } else if (warp == 4) {
         // =========================== MMA issuer ===========================
         uint32_t it = 0;
         for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -484,7 +498,7 @@ conv_slab2_kernel(const ConvArgs a, const SlabGeom g, long long n_items, const _
     } else {
         // =========================== epilogue ===========================
         const int q = warp & 3;
-        const int tsel = (warp - 2) >> 2;           // 0 or 1: even / odd tiles
+        const int tsel = (warp - 5) >> 2;           // 0 or 1: even / odd tiles
         bf16 *y = static_cast<bf16 *>(a.y);
         const bf16 *res = static_cast<const bf16 *>(a.res);
         uint32_t it = 0;
@@ -563,13 +577,15 @@ conv_slab2_kernel(const ConvArgs a, const SlabGeom g, long long n_items, const _
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
+    if (warp == 4) tmem_dealloc(tmem_base, g.tmem_cols);
 }
 
 bool geometry(const ConvArgs &a, SlabGeom &g, bool v2 = false) {
     const int KS = a.KH;
     g.taps = KS * KS;
-    g.Wp = a.W + KS - 1;
+    // row pitch of the staged band in pixels: W + KS - 1 rounded up to 8 pixels so that every slab
+    // row starts 128-byte aligned (TMA destination alignment); the extra columns are zero (OOB)
+    g.Wp = (a.W + KS - 1 + 7) & ~7;
     int R = 768 / g.Wp;
     if (R < 1) R = 1;
     if (R > a.Ho) R = a.Ho;
@@ -592,7 +608,6 @@ bool geometry(const ConvArgs &a, SlabGeom &g, bool v2 = false) {
     g.n_bands = (a.Ho + g.R - 1) / g.R;
     g.wp_magic = (unsigned)(((1ull << 32) + g.Wp - 1) / g.Wp);
     if ((long long)(g.rows_e + g.rows_o) * g.Wp >= 65536 || g.n_tiles * 128 >= 65536) return false;
-    if (v2 && (g.Wp > 256 || g.rows_e > 256)) return false;          // TMA box limits
     return g.n_tiles * 32 * (v2 ? 2 : 1) <= 512 && g.smem_bytes <= (v2 ? 220 : 200) * 1024;
 }
 
@@ -639,30 +654,9 @@ int launch2(const ConvArgs &a, const SlabGeom &g, cudaStream_t s) {
         set_error("cudaFuncSetAttribute(conv_slab2) failed: %s", cudaGetErrorString(attr_err));
         return SPK_ERR_CUDA;
     }
-    EncodeTiledFn fn = encode_fn();
-    if (fn == nullptr) {
-        set_error("cuTensorMapEncodeTiled is not available from the driver");
-        return SPK_ERR_CUDA;
-    }
-    // input as {8 ch, 4 pieces, W, H, B}; one box = one (or rows_e) row(s) of one channel plane
-    CUtensorMap xmap;
-    const cuuint64_t e = sizeof(bf16);
-    const cuuint64_t dims[5] = {8, 4, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
-    const cuuint64_t strides[4] = {16, (cuuint64_t)a.in_ld * e, (cuuint64_t)a.W * a.in_ld * e,
-                                   (cuuint64_t)a.H * a.W * a.in_ld * e};
-    const cuuint32_t box[5] = {8, 1, (cuuint32_t)g.Wp, (cuuint32_t)(S == 1 ? g.rows_e : 1), 1};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(&xmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
-                    const_cast<bf16 *>(static_cast<const bf16 *>(a.x) + a.in_choff), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled(slab) failed (%d): W=%d H=%d B=%d ld=%d", (int)r, a.W, a.H, a.B, a.in_ld);
-        return SPK_ERR_CUDA;
-    }
     const long long items = (long long)a.B * g.n_bands;
     const long long grid = std::min<long long>(items, sm_count());
-    kern<<<(unsigned)grid, kThreads2, g.smem_bytes, s>>>(a, g, items, xmap);
+    kern<<<(unsigned)grid, kThreads2, g.smem_bytes, s>>>(a, g, items);
     return check_launch("conv_slab2_kernel");
 }
 

@@ -175,13 +175,11 @@ class _Engine:
         return self._p(("raw", key), lambda: self.sd[key].reshape(-1))
 
     def default_chunks(self, T):
-        """(coarse, fine): the 2-D front keeps ~1.9 MB of activations per segment alive, so it runs
-        in fine sub-batches that fit the 126 MB L2; the D-TDNN part (<0.6 MB per segment, 74 rows
-        per segment) runs over coarse sub-batches so every launch has enough tiles for 148 SMs."""
-        bytes_per = 2 if self.model.precision == _lib.PREC_BF16 else 4
-        per_seg = 80 * T * 32 * bytes_per * 2.5
-        fine = max(4, min(256, int(100e6 // per_seg)))
-        return 512, fine
+        """(coarse, fine) sub-batch sizes.  Measured on B200 (bench.py sweeps): launch
+        count and pipeline fill matter more than L2 residency of the 2-D front, so both are large;
+        they only bound the workspace (about 0.6 MB coarse + 1.9 MB fine per segment in bf16)."""
+        scale = max(1, T // 148)
+        return max(64, 2048 // scale), max(32, 1024 // scale)
 
     def compile(self, T):
         mod, AD = self.m, self.model.act_dtype

@@ -179,8 +179,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--segments", type=int, default=4096, help="1.5 s windows per GPU per step")
-    ap.add_argument("--batch", type=int, default=1024, help="windows per fbank/forward call")
-    ap.add_argument("--chunk", type=int, default=0, help="segments per L2-resident sub-batch (0 = auto)")
+    ap.add_argument("--batch", type=int, default=2048, help="windows per fbank/forward call")
+    ap.add_argument("--chunk", type=int, default=0, help="coarse sub-batch (D-TDNN part), 0 = auto")
+    ap.add_argument("--fine", type=int, default=0, help="fine sub-batch (2-D front), 0 = auto")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
@@ -202,7 +203,10 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
-    model = b200spk.CAMPPlus(embedding_size=EMB, precision=args.precision, chunk=args.chunk or None)
+    chunk = None
+    if args.chunk or args.fine:
+        chunk = (args.chunk or 2048, args.fine or min(args.chunk or 2048, 1024))
+    model = b200spk.CAMPPlus(embedding_size=EMB, precision=args.precision, chunk=chunk)
     tsd, _ = make_weights(model)
     model.load_state_dict(tsd)
     model = model.to(dev).eval()

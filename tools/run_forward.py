@@ -7,7 +7,7 @@ import b200spk
 import bench
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--segments", type=int, default=512)
+ap.add_argument("--segments", type=int, default=2048)
 ap.add_argument("--chunk", type=int, default=0)
 ap.add_argument("--precision", default="bf16")
 ap.add_argument("--iters", type=int, default=2)

@@ -158,52 +158,61 @@ conv_simt_kernel(const ConvArgs a) {
 }
 
 // ------------------------------------------------------------------ stem: Conv2d(1->Cout,3x3,p=1)+BN+ReLU
-// feats [B,T,F] is the image [H=F, W=T] with one channel (DTDNN.py:40-41,112).  Each thread
-// produces 4 output channels of one pixel; consecutive threads cover consecutive channels, so
-// a warp writes whole pixels contiguously.
+// feats [B,T,F] is the image [H=F, W=T] with one channel (DTDNN.py:40-41,112).  One CTA per
+// (segment, frequency row): the three input rows are staged in shared memory (transposing the
+// [T,F] feature layout on the way), then every thread produces 8 output channels of one pixel so
+// consecutive threads write consecutive 16/32-byte pieces of the channels-last output row.
+// Pure 32-bit index arithmetic; the output write is the only HBM traffic that matters.
 template <typename TOut>
 __global__ void __launch_bounds__(256)
 stem_kernel(const StemArgs a) {
-    extern __shared__ float sw[];   // [Cout*9] weights, [Cout] scale, [Cout] shift
-    float *ssc = sw + a.Cout * 9, *ssh = ssc + a.Cout;
-    for (int i = threadIdx.x; i < a.Cout * 9; i += blockDim.x) sw[i] = a.w[i];
+    extern __shared__ float sm[];
+    float *sw = sm;                         // [9][Cout]  (tap-major so a thread reads 8 adjacent channels)
+    float *ssc = sw + 9 * a.Cout, *ssh = ssc + a.Cout;
+    float *rows = ssh + a.Cout;             // [3][T+2]  zero padded
+    const int Tp = a.T + 2;
+    const int f = blockIdx.x % a.F, b = blockIdx.x / a.F;
+    for (int i = threadIdx.x; i < a.Cout * 9; i += blockDim.x) sw[(i % 9) * a.Cout + i / 9] = a.w[i];
     for (int i = threadIdx.x; i < a.Cout; i += blockDim.x) {
         ssc[i] = a.scale ? a.scale[i] : 1.f;
         ssh[i] = a.shift ? a.shift[i] : 0.f;
     }
+    const float *fe = a.feats + (size_t)b * a.T * a.F;
+    for (int i = threadIdx.x; i < 3 * Tp; i += blockDim.x) {
+        const int kh = i / Tp, tt = i - kh * Tp - 1, ff = f + kh - 1;
+        rows[i] = (ff >= 0 && ff < a.F && tt >= 0 && tt < a.T) ? __ldg(fe + (size_t)tt * a.F + ff) : 0.f;
+    }
     __syncthreads();
-    const int cg = a.Cout / 4;
-    const long long total = (long long)a.B * a.F * a.T * cg;
-    TOut *y = static_cast<TOut *>(a.y);
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int c0 = (int)(idx % cg) * 4;
-        const long long pix = idx / cg;             // (b, f, t)
-        const int t = (int)(pix % a.T);
-        const long long bf = pix / a.T;
-        const int f = (int)(bf % a.F);
-        const long long b = bf / a.F;
-        float in[3][3];
+    const int cg = a.Cout / 8;
+    TOut *y = static_cast<TOut *>(a.y) + ((size_t)b * a.F + f) * a.T * a.out_ld + a.out_choff;
+    for (int idx = threadIdx.x; idx < a.T * cg; idx += blockDim.x) {
+        const int t = idx / cg, c0 = (idx - t * cg) * 8;
+        float in[9];
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int ff = f + kh - 1, tt = t + kw - 1;
-                in[kh][kw] = (ff >= 0 && ff < a.F && tt >= 0 && tt < a.T)
-                                 ? __ldg(a.feats + (b * a.T + tt) * a.F + ff) : 0.f;
-            }
-        float o[4];
+            for (int kw = 0; kw < 3; ++kw) in[kh * 3 + kw] = rows[kh * Tp + t + kw];
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(sw + k * a.Cout + c0);
+            const float4 w1 = *reinterpret_cast<const float4 *>(sw + k * a.Cout + c0 + 4);
+            o[0] = fmaf(in[k], w0.x, o[0]); o[1] = fmaf(in[k], w0.y, o[1]);
+            o[2] = fmaf(in[k], w0.z, o[2]); o[3] = fmaf(in[k], w0.w, o[3]);
+            o[4] = fmaf(in[k], w1.x, o[4]); o[5] = fmaf(in[k], w1.y, o[5]);
+            o[6] = fmaf(in[k], w1.z, o[6]); o[7] = fmaf(in[k], w1.w, o[7]);
+        }
+        float r0[4], r1[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float *w = sw + (c0 + j) * 9;
-            float s = 0.f;
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) s = fmaf(in[kh][kw], w[kh * 3 + kw], s);
-            o[j] = apply_act(fmaf(s, ssc[c0 + j], ssh[c0 + j]), a.act);
+            r0[j] = apply_act(fmaf(o[j], ssc[c0 + j], ssh[c0 + j]), a.act);
+            r1[j] = apply_act(fmaf(o[4 + j], ssc[c0 + 4 + j], ssh[c0 + 4 + j]), a.act);
         }
-        Vec4<TOut>::store(y + pix * a.out_ld + a.out_choff + c0, o);
+        TOut *yp = y + (size_t)t * a.out_ld + c0;
+        Vec4<TOut>::store(yp, r0);
+        Vec4<TOut>::store(yp + 4, r1);
     }
 }
 
@@ -410,15 +419,23 @@ int launch_conv_simt(const ConvArgs &a, int in_dtype, int out_dtype, int res_dty
 }
 
 int launch_stem(const StemArgs &a, int out_dtype, cudaStream_t s) {
-    if (a.Cout % 4 != 0 || a.out_ld % 4 != 0 || a.out_choff % 4 != 0) {
-        set_error("stem: Cout and channel pitch must be multiples of 4");
+    if (a.Cout % 8 != 0 || a.out_ld % 8 != 0 || a.out_choff % 8 != 0) {
+        set_error("stem: Cout and channel pitch must be multiples of 8");
         return SPK_ERR_UNSUPPORTED;
     }
-    const long long work = (long long)a.B * a.F * a.T * (a.Cout / 4);
-    if (work == 0) return SPK_OK;
-    const size_t sh = (size_t)a.Cout * 11 * sizeof(float);
-    if (out_dtype == SPK_DT_F32) stem_kernel<float><<<grid_for(work, 256), 256, sh, s>>>(a);
-    else stem_kernel<bf16><<<grid_for(work, 256), 256, sh, s>>>(a);
+    const long long blocks = (long long)a.B * a.F;
+    if (blocks == 0) return SPK_OK;
+    if (blocks > 0x7fffffffll) {
+        set_error("stem: batch too large");
+        return SPK_ERR_UNSUPPORTED;
+    }
+    const size_t sh = ((size_t)a.Cout * 11 + 3 * (a.T + 2)) * sizeof(float);
+    if (sh > 48 * 1024) {
+        set_error("stem: %d frames exceed the shared-memory row buffer", a.T);
+        return SPK_ERR_UNSUPPORTED;
+    }
+    if (out_dtype == SPK_DT_F32) stem_kernel<float><<<(unsigned)blocks, 256, sh, s>>>(a);
+    else stem_kernel<bf16><<<(unsigned)blocks, 256, sh, s>>>(a);
     return check_launch("stem_kernel");
 }
 

@@ -14,6 +14,7 @@ without an sm_100 device every compute call raises ``SpkError``.
 from ._lib import SpkError, lib, LIB_PATH  # noqa: F401
 from .fbank import FBank, fbank_batch, num_frames  # noqa: F401
 from .campplus import CAMPPlus  # noqa: F401
+from .cluster import SpectralCluster, cosine_pairs  # noqa: F401
 from .extract import EmbeddingExtractor  # noqa: F401
 
-__all__ = ["FBank", "CAMPPlus", "EmbeddingExtractor", "SpkError", "fbank_batch", "num_frames", "lib"]
+__all__ = ["FBank", "CAMPPlus", "SpectralCluster", "cosine_pairs", "EmbeddingExtractor", "SpkError", "fbank_batch", "num_frames", "lib"]

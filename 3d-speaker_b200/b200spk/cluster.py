@@ -1,0 +1,152 @@
+"""Drop-in for ``speakerlab.process.cluster.SpectralCluster`` (speakerlab/process/cluster.py:23-112).
+
+Same constructor and call convention (numpy ``X [N, D]`` in, writable numpy int labels out,
+``pval=`` / ``speaker_num=`` keyword overrides, ``X`` is never mutated).  The arithmetic runs on
+the GPU through the C ABI: cosine affinity (tensor-core GEMM at fp32 accuracy), p-pruning,
+symmetrised unnormalised Laplacian, smallest eigenpairs (Lanczos) and Lloyd k-means.  Host side:
+the eigengap rule (cluster.py:93-96, 107-112) and the k-means++ seeding, which draws from numpy's
+GLOBAL RandomState in the same order sklearn's ``k_means(emb, k)`` does (sklearn
+``_kmeans_plusplus``), so ``np.random.seed(s)`` before the call pins the result exactly as it does
+for the reference.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _kmeans_plusplus(X, n_clusters, random_state):
+    """Greedy k-means++ seeding, sklearn/cluster/_kmeans.py:_kmeans_plusplus (uniform sample weights):
+    same RandomState calls in the same order."""
+    n_samples = X.shape[0]
+    centers = np.empty((n_clusters, X.shape[1]), dtype=X.dtype)
+    n_local_trials = 2 + int(np.log(n_clusters))
+    sample_weight = np.ones(n_samples, dtype=X.dtype)
+    center_id = random_state.choice(n_samples, p=sample_weight / sample_weight.sum())
+    centers[0] = X[center_id]
+    X64 = X.astype(np.float64)
+    x_sq = (X64 * X64).sum(axis=1)
+
+    def dist_sq(Y):
+        # sklearn upcasts float32 inputs to float64 for this product (_euclidean_distances_upcast)
+        Y64 = Y.astype(np.float64)
+        d = x_sq[None, :] - 2.0 * (Y64 @ X64.T) + (Y64 * Y64).sum(axis=1)[:, None]
+        np.maximum(d, 0, out=d)
+        return d.astype(X.dtype)
+
+    closest = dist_sq(centers[0:1])
+    current_pot = closest @ sample_weight
+    for c in range(1, n_clusters):
+        rand_vals = random_state.uniform(size=n_local_trials) * current_pot
+        candidate_ids = np.searchsorted(np.cumsum(sample_weight * closest), rand_vals)
+        np.clip(candidate_ids, None, closest.size - 1, out=candidate_ids)
+        d2c = dist_sq(X[candidate_ids])
+        np.minimum(closest, d2c, out=d2c)
+        pots = d2c @ sample_weight.reshape(-1, 1)
+        best = int(np.argmin(pots))
+        current_pot = pots[best]
+        closest = d2c[best:best + 1]
+        centers[c] = X[candidate_ids[best]]
+    return centers
+
+
+class SpectralCluster:
+    """A spectral clustering method using the unnormalised Laplacian of the pruned cosine affinity."""
+
+    def __init__(self, min_num_spks=1, max_num_spks=10, pval=0.02, min_pnum=6, oracle_num=None, device="cuda:0"):
+        self.min_num_spks = min_num_spks
+        self.max_num_spks = max_num_spks
+        self.min_pnum = min_pnum
+        self.pval = pval
+        self.k = oracle_num
+        self.device = torch.device(device)
+        self.last = {}          # stage results of the last call (eigenvalues, k, Krylov size) for inspection
+
+    # ------------------------------------------------------------------ stages (device)
+    def laplacian(self, X, pval=None):
+        """X: torch f32 [N, D] on the device -> (L [Np, Np] with row pitch Np, N)."""
+        L = _lib.lib()
+        N, D = X.shape
+        pval = self.pval if pval is None else pval
+        n_elems = min(int((1 - pval) * N), N - self.min_pnum)        # cluster.py:67-68
+        keep = N - max(n_elems, 0)
+        Np = (N + 15) // 16 * 16
+        lap = torch.empty((Np, Np), dtype=torch.float32, device=X.device)
+        ws = torch.empty(int(L.spk_affinity_workspace_bytes(N, D)), dtype=torch.uint8, device=X.device)
+        with torch.cuda.device(X.device):
+            _lib.check(L.spk_affinity_laplacian(C.c_void_p(X.data_ptr()), N, D, keep, C.c_void_p(lap.data_ptr()),
+                                                C.c_void_p(ws.data_ptr()), ws.numel(), _lib.current_stream_ptr()))
+        return lap
+
+    def eig_smallest(self, lap, N, k):
+        L = _lib.lib()
+        evals = np.empty(k, dtype=np.float32)
+        evecs = torch.empty((N, k), dtype=torch.float32, device=lap.device)
+        ws = torch.empty(int(L.spk_eig_workspace_bytes(N, k)), dtype=torch.uint8, device=lap.device)
+        with torch.cuda.device(lap.device):
+            m = _lib.check(L.spk_eig_smallest(C.c_void_p(lap.data_ptr()), N, k, evals.ctypes.data_as(C.c_void_p),
+                                              C.c_void_p(evecs.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                              _lib.current_stream_ptr()))
+        self.last["krylov"] = int(m)
+        return evals, evecs
+
+    def kmeans(self, emb, k):
+        """emb: torch f32 [N, d] on the device -> numpy int32 labels.  Mirrors sklearn k_means(emb, k):
+        mean-centring, tol = mean(var)*1e-4, k-means++ from the global numpy RNG, one init, Lloyd."""
+        L = _lib.lib()
+        N, d = emb.shape
+        host = emb.cpu().numpy().astype(np.float32)
+        host = host - host.mean(axis=0)
+        tol = float(np.mean(np.var(host, axis=0)) * 1e-4)
+        centers = _kmeans_plusplus(host, k, np.random.mtrand._rand).astype(np.float32)
+        pts = torch.from_numpy(host).to(emb.device)
+        labels = torch.empty(N, dtype=torch.int32, device=emb.device)
+        ws = torch.empty(int(L.spk_kmeans_workspace_bytes(N, d, k)), dtype=torch.uint8, device=emb.device)
+        inertia = C.c_float(0.0)
+        with torch.cuda.device(emb.device):
+            it = _lib.check(L.spk_kmeans(C.c_void_p(pts.data_ptr()), N, d, k, centers.ctypes.data_as(C.c_void_p), 300,
+                                         C.c_float(tol), C.c_void_p(labels.data_ptr()), C.byref(inertia),
+                                         C.c_void_p(ws.data_ptr()), ws.numel(), _lib.current_stream_ptr()))
+        self.last["kmeans_iters"] = int(it)
+        return labels.cpu().numpy()
+
+    # ------------------------------------------------------------------ reference call convention
+    def __call__(self, X, **kwargs):
+        pval = kwargs.get('pval', None)
+        oracle_num = kwargs.get('speaker_num', None)
+        if isinstance(X, torch.Tensor):
+            Xd = X.detach().to(self.device, torch.float32).contiguous()
+        else:
+            Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).to(self.device)
+        N = Xd.shape[0]
+        k_eig = min(self.max_num_spks + 1, N)
+        if k_eig >= N:
+            raise ValueError("k=%d must be less than N=%d (scipy eigsh would raise too)" % (k_eig, N))
+        if k_eig > 32:
+            raise ValueError("max_num_spks > 31 is not supported by the GPU eigensolver")
+        lap = self.laplacian(Xd, pval)
+        lambdas, vecs = self.eig_smallest(lap, N, k_eig)
+        k_oracle = self.k if oracle_num is None else oracle_num
+        if k_oracle is not None:
+            num_of_spk = int(k_oracle)
+        else:
+            lam = lambdas[self.min_num_spks - 1:self.max_num_spks + 1]
+            gaps = [float(lam[i + 1]) - float(lam[i]) for i in range(len(lam) - 1)]
+            num_of_spk = int(np.argmax(gaps)) + self.min_num_spks
+        self.last.update(lambdas=lambdas, k=num_of_spk)
+        emb = vecs[:, :num_of_spk].contiguous()
+        labels = self.kmeans(emb, num_of_spk)
+        return labels
+
+
+def cosine_pairs(E, a, b):
+    """out[i] = cos(E[a[i]], E[b[i]]): trial scoring (speakerlab/bin/compute_score_metrics.py:113-114).
+    E torch f32 [N, D] on the device, a/b int32 index tensors on the device."""
+    out = torch.empty(a.shape[0], dtype=torch.float32, device=E.device)
+    with torch.cuda.device(E.device):
+        _lib.check(_lib.lib().spk_cosine_pairs(C.c_void_p(E.data_ptr()), E.shape[0], E.shape[1], C.c_void_p(a.data_ptr()),
+                                               C.c_void_p(b.data_ptr()), a.shape[0], C.c_void_p(out.data_ptr()),
+                                               _lib.current_stream_ptr()))
+    return out

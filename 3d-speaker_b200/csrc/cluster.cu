@@ -1,14 +1,664 @@
-// Spectral-clustering back end (placeholder entry points; implemented in cluster kernels).
-#include "common.cuh"
+// Spectral-clustering back end for sm_100a.  Replaces the arithmetic of
+// SpectralCluster.__call__ (speakerlab/process/cluster.py:35-112):
+//
+//   get_sim_mat   :59-62   cosine affinity  = normalize(X) normalize(X)^T
+//   p_pruning     :64-77   per row keep the `keep` largest entries
+//   sym + get_laplacian :46,:79-84   M = 0.5 (P + P^T), zero diagonal, L = diag(sum |M|) - M
+//   get_spec_embs :86-100  k smallest eigenpairs (scipy eigsh which='SM' in the reference)
+//   cluster_embs  :102-105 k-means (Lloyd iterations here; k-means++ seeding stays on the host
+//                          RNG exactly like sklearn, see b200spk/cluster.py)
+//
+// The affinity is a tensor-core GEMM at fp32 accuracy: every normalised row is split into three
+// bf16 terms (x = hi + mid + lo) and ONE tcgen05 GEMM with K = 6 D accumulates the six
+// significant cross terms in the fp32 TMEM accumulator (conv_gemm.cu).  fp32-level accuracy is
+// needed because pruning keeps an exact count per row and near-ties decide which edges survive.
+// Pruning is a per-row radix select in shared memory; the eigensolver is Lanczos with full
+// re-orthogonalisation on sigma*I - L (sigma = Gershgorin bound), whose largest Ritz pairs are
+// the smallest eigenpairs of L; the small tridiagonal problem is solved on the host (implicit QL).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "ops.cuh"
+
+namespace spk {
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ float block_sum(float v, float *sh) {      // sh: >= 32 floats
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    float r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+    if (warp == 0) r = warp_sum(r);
+    if (threadIdx.x == 0) sh[0] = r;
+    __syncthreads();
+    r = sh[0];
+    return r;
+}
+
+// ---- row L2-normalise + 3-term bf16 split, laid out for the K = 6*Dp product
+// A' = [hi hi mid hi lo mid],  B' = [hi mid hi lo hi mid]  ->  A' B'^T = sum of the six terms
+__global__ void __launch_bounds__(256)
+normalize_split_kernel(const float *__restrict__ X, int N, int D, int Np, int Dp, bf16 *__restrict__ A, bf16 *__restrict__ B,
+                       float *__restrict__ Xn) {
+    __shared__ float sh[32];
+    const int row = blockIdx.x;
+    float ss = 0.f;
+    if (row < N)
+        for (int c = threadIdx.x; c < D; c += blockDim.x) {
+            const float v = X[(size_t)row * D + c];
+            ss += v * v;
+        }
+    ss = block_sum(ss, sh);
+    float inv = 0.f;
+    if (row < N) inv = ss > 0.f ? 1.f / sqrtf(ss) : 1.f;        // sklearn normalize: zero rows stay zero
+    for (int c = threadIdx.x; c < Dp; c += blockDim.x) {
+        const float v = (row < N && c < D) ? X[(size_t)row * D + c] * inv : 0.f;
+        if (Xn != nullptr) Xn[(size_t)row * Dp + c] = v;
+        if (A != nullptr) {
+            const bf16 hi = __float2bfloat16_rn(v);
+            const float r1 = v - __bfloat162float(hi);
+            const bf16 mid = __float2bfloat16_rn(r1);
+            const bf16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+            bf16 *a = A + (size_t)row * 6 * Dp, *b = B + (size_t)row * 6 * Dp;
+            a[c] = hi;          b[c] = hi;
+            a[Dp + c] = hi;     b[Dp + c] = mid;
+            a[2 * Dp + c] = mid; b[2 * Dp + c] = hi;
+            a[3 * Dp + c] = hi;  b[3 * Dp + c] = lo;
+            a[4 * Dp + c] = lo;  b[4 * Dp + c] = hi;
+            a[5 * Dp + c] = mid; b[5 * Dp + c] = mid;
+        }
+    }
+}
+
+// ---- p-pruning: keep the `keep` largest entries of each row (ties: higher column index wins,
+// i.e. what a stable ascending argsort zeroes first).  One CTA per row, row in shared memory,
+// 4-pass 8-bit radix select on the order-preserving integer image of the floats.
+__device__ __forceinline__ unsigned f2key(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void __launch_bounds__(256)
+prune_rows_kernel(float *__restrict__ S, int N, int ld, int keep) {
+    extern __shared__ unsigned shm[];
+    unsigned *keys = shm;                 // [N]
+    unsigned *hist = shm + N;             // [256]
+    __shared__ unsigned s_prefix, s_mask;
+    __shared__ int s_need;
+    const int row = blockIdx.x;
+    float *srow = S + (size_t)row * ld;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) keys[j] = f2key(srow[j]);
+    if (threadIdx.x == 0) { s_prefix = 0; s_mask = 0; s_need = keep; }
+    __syncthreads();
+    // find the key of the keep-th largest element
+    for (int pass = 3; pass >= 0; --pass) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const unsigned prefix = s_prefix, mask = s_mask;
+        const int shift = pass * 8;
+        for (int j = threadIdx.x; j < N; j += blockDim.x) {
+            const unsigned k = keys[j];
+            if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int need = s_need;
+            int b = 255;
+            for (; b > 0; --b) {
+                const int c = (int)hist[b];
+                if (c >= need) break;
+                need -= c;
+            }
+            s_need = need;
+            s_prefix = prefix | ((unsigned)b << shift);
+            s_mask = mask | (255u << shift);
+        }
+        __syncthreads();
+    }
+    const unsigned tau = s_prefix;       // key of the keep-th largest
+    const int ties_to_keep = s_need;     // how many elements equal to tau survive
+    // ties: keep the ones with the highest column index.  Count ties from the right.
+    // (rare path; a serial scan by one thread is fine for the handful of rows that have ties)
+    __shared__ int s_tie_cut;            // smallest column index among kept ties
+    if (threadIdx.x == 0) {
+        int left = ties_to_keep, cut = N;
+        for (int j = N - 1; j >= 0 && left > 0; --j)
+            if (keys[j] == tau) { cut = j; --left; }
+        s_tie_cut = cut;
+    }
+    __syncthreads();
+    const int cut = s_tie_cut;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const unsigned k = keys[j];
+        const bool kept = (k > tau) || (k == tau && j >= cut);
+        if (!kept) srow[j] = 0.f;
+    }
+}
+
+// ---- L offdiag = -0.5 (P + P^T); diagonal filled by laplacian_diag_kernel
+__global__ void __launch_bounds__(256)
+symmetrize_neg_kernel(const float *__restrict__ P, float *__restrict__ L, int N, int ldp, int ldl) {
+    __shared__ float t[32][33];
+    const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int i = bj + r, j = bi + tx;                       // transposed block P[bj.., bi..]
+        t[r][tx] = (i < N && j < N) ? P[(size_t)i * ldp + j] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = bi + r, j = bj + tx;
+        if (i < N && j < N) {
+            const float v = 0.5f * (P[(size_t)i * ldp + j] + t[tx][r]);
+            L[(size_t)i * ldl + j] = (i == j) ? 0.f : -v;
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+laplacian_diag_kernel(float *__restrict__ L, int N, int ld) {
+    __shared__ float sh[32];
+    const int row = blockIdx.x;
+    float s = 0.f;
+    for (int j = threadIdx.x; j < N; j += blockDim.x)
+        if (j != row) s += fabsf(L[(size_t)row * ld + j]);
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) L[(size_t)row * ld + row] = s;
+}
+
+// ---- Lanczos building blocks (fp32 storage, fp32 accumulate with tree reductions)
+// w = sigma*v - L v      (one warp per row)
+__global__ void __launch_bounds__(256)
+shifted_matvec_kernel(const float *__restrict__ L, int N, int ld, float sigma, const float *__restrict__ v,
+                      float *__restrict__ w) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= N) return;
+    const float *lr = L + (size_t)row * ld;
+    float s = 0.f;
+    for (int j = lane; j < N; j += 32) s = fmaf(lr[j], v[j], s);
+    s = warp_sum(s);
+    if (lane == 0) w[row] = sigma * v[row] - s;
+}
+// h[j] = dot(V[j,:], w) for j < m     (one CTA per j)
+__global__ void __launch_bounds__(256)
+dots_kernel(const float *__restrict__ V, int N, int m, const float *__restrict__ w, float *__restrict__ h) {
+    __shared__ float sh[32];
+    const int j = blockIdx.x;
+    const float *vj = V + (size_t)j * N;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s = fmaf(vj[i], w[i], s);
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) h[j] = s;
+}
+// w -= sum_j h[j] V[j,:]; optionally accumulate alpha += h[m-1]
+__global__ void __launch_bounds__(256)
+axpys_kernel(const float *__restrict__ V, int N, int m, const float *__restrict__ h, float *__restrict__ w) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float s = 0.f;
+    for (int j = 0; j < m; ++j) s = fmaf(h[j], V[(size_t)j * N + i], s);
+    w[i] -= s;
+}
+// beta = ||w||; V[m,:] = w / beta; record alpha (sum of the two projections on v_{m-1}) and beta
+__global__ void __launch_bounds__(256)
+normalize_next_kernel(const float *__restrict__ w, int N, float *__restrict__ vnext, const float *__restrict__ h1,
+                      const float *__restrict__ h2, int jlast, float *__restrict__ alpha, float *__restrict__ beta, int step) {
+    __shared__ float sh[32];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s = fmaf(w[i], w[i], s);
+    s = block_sum(s, sh);
+    const float b = sqrtf(s);
+    const float inv = b > 0.f ? 1.f / b : 0.f;
+    if (vnext != nullptr)
+        for (int i = threadIdx.x; i < N; i += blockDim.x) vnext[i] = w[i] * inv;
+    if (threadIdx.x == 0) {
+        alpha[step] = h1[jlast] + h2[jlast];
+        beta[step] = b;
+    }
+}
+__global__ void init_vector_kernel(float *__restrict__ v, int N, unsigned seed) {
+    __shared__ float sh[32];
+    // deterministic pseudo-random start vector (hash), then normalised by the caller kernel
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        unsigned x = (unsigned)i * 2654435761u ^ seed;
+        x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+        v[i] = ((x >> 8) * (1.0f / 16777216.0f)) - 0.5f;
+    }
+    __syncthreads();
+    float s = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s = fmaf(v[i], v[i], s);
+    s = block_sum(s, sh);
+    const float inv = rsqrtf(s);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) v[i] *= inv;
+}
+// evecs[i, c] = sum_j V[j, i] * Sm[j, c]     (Ritz vectors; Sm is m x k row-major on device)
+__global__ void __launch_bounds__(256)
+ritz_kernel(const float *__restrict__ V, int N, int m, const float *__restrict__ Sm, int k, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    for (int j = 0; j < m; ++j) {
+        const float v = V[(size_t)j * N + i];
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (c < k) acc[c] = fmaf(v, Sm[j * k + c], acc[c]);
+    }
+    for (int c = 0; c < k; ++c) out[(size_t)i * k + c] = acc[c];
+}
+__global__ void gershgorin_kernel(const float *__restrict__ L, int N, int ld, float *__restrict__ out) {
+    // sigma = max_i 2*L[i][i] (unnormalised Laplacian: row sum of |offdiag| equals the diagonal)
+    __shared__ float sh[32];
+    float mx = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) mx = fmaxf(mx, L[(size_t)i * ld + i]);
+    // block max via the sum helper on a one-hot trick is wasteful; do a plain shared reduction
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) sh[warp] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m2 = 0.f;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) m2 = fmaxf(m2, sh[w]);
+        out[0] = 2.f * m2 + 1e-3f;
+    }
+}
+
+// ---- k-means (Lloyd).  The update is a fixed-order tree reduction per (cluster, dimension), so
+// the centres - and with them labels of boundary points - are bit-reproducible run to run.
+__global__ void __launch_bounds__(256)
+kmeans_assign_kernel(const float *__restrict__ P, int N, int d, int k, const float *__restrict__ C, int *__restrict__ labels,
+                     float *__restrict__ inertia, int *__restrict__ changed) {
+    extern __shared__ float cen[];        // [k*d]
+    for (int i = threadIdx.x; i < k * d; i += blockDim.x) cen[i] = C[i];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float my_in = 0.f;
+    if (i < N) {
+        const float *p = P + (size_t)i * d;
+        float best = 3.4e38f;
+        int bj = 0;
+        for (int j = 0; j < k; ++j) {
+            float s = 0.f;
+            for (int c = 0; c < d; ++c) {
+                const float df = p[c] - cen[j * d + c];
+                s = fmaf(df, df, s);
+            }
+            if (s < best) { best = s; bj = j; }      // first minimum wins, like np.argmin
+        }
+        if (labels[i] != bj) { labels[i] = bj; atomicAdd(changed, 1); }
+        my_in = best;
+    }
+    my_in = warp_sum(my_in);
+    if ((threadIdx.x & 31) == 0) atomicAdd(inertia, my_in);      // diagnostic only
+}
+// one CTA per cluster: new centre = mean of its points (empty clusters keep their centre)
+__global__ void __launch_bounds__(256)
+kmeans_update_kernel(const float *__restrict__ P, int N, int d, const int *__restrict__ labels, float *__restrict__ C,
+                     float *__restrict__ shift2) {
+    __shared__ float sh[32];
+    const int j = blockIdx.x;
+    float cnt = 0.f;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) cnt += (labels[i] == j) ? 1.f : 0.f;
+    cnt = block_sum(cnt, sh);
+    if (cnt == 0.f) return;
+    float sh2 = 0.f;
+    for (int c = 0; c < d; ++c) {
+        float s = 0.f;
+        for (int i = threadIdx.x; i < N; i += blockDim.x)
+            if (labels[i] == j) s += P[(size_t)i * d + c];
+        s = block_sum(s, sh);
+        const float nc = s / cnt;
+        const float df = nc - C[j * d + c];
+        sh2 = fmaf(df, df, sh2);
+        __syncthreads();
+        if (threadIdx.x == 0) C[j * d + c] = nc;
+    }
+    if (threadIdx.x == 0) atomicAdd(shift2, sh2);      // k addends: order-insensitive to ~1 ulp, only compared to tol
+}
+
+__global__ void cosine_pairs_kernel(const float *__restrict__ E, long long N, int D, const int *__restrict__ a,
+                                    const int *__restrict__ b, long long n_pairs, float *__restrict__ out) {
+    const long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pair >= n_pairs) return;
+    const float *x = E + (size_t)a[pair] * D, *y = E + (size_t)b[pair] * D;
+    float xy = 0.f, xx = 0.f, yy = 0.f;
+    for (int c = lane; c < D; c += 32) {
+        const float u = x[c], v = y[c];
+        xy = fmaf(u, v, xy); xx = fmaf(u, u, xx); yy = fmaf(v, v, yy);
+    }
+    xy = warp_sum(xy); xx = warp_sum(xx); yy = warp_sum(yy);
+    if (lane == 0) {
+        const float nx = xx > 0.f ? sqrtf(xx) : 1.f, ny = yy > 0.f ? sqrtf(yy) : 1.f;   // sklearn normalize semantics
+        out[pair] = xy / (nx * ny);
+    }
+}
+
+// ---- host: symmetric tridiagonal eigen-decomposition (implicit QL with Wilkinson shifts)
+// d[0..m) diagonal, e[0..m-1) off-diagonal; on return d = eigenvalues (unsorted), z = m x m
+// eigenvectors (column c in z[r*m + c]).  Classic tql2 recurrence in double precision.
+bool tridiag_eig(std::vector<double> &d, std::vector<double> &e, std::vector<double> &z, int m) {
+    z.assign((size_t)m * m, 0.0);
+    for (int i = 0; i < m; ++i) z[(size_t)i * m + i] = 1.0;
+    e.resize(m);
+    e[m - 1] = 0.0;
+    for (int l = 0; l < m; ++l) {
+        int iter = 0, mm;
+        do {
+            for (mm = l; mm < m - 1; ++mm) {
+                const double dd = std::fabs(d[mm]) + std::fabs(d[mm + 1]);
+                if (std::fabs(e[mm]) <= 2.3e-16 * dd) break;
+            }
+            if (mm != l) {
+                if (++iter > 200) return false;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = std::hypot(g, 1.0);
+                g = d[mm] - d[l] + e[l] / (g + (g >= 0 ? std::fabs(r) : -std::fabs(r)));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int i;
+                for (i = mm - 1; i >= l; --i) {
+                    double f = s * e[i], b = c * e[i];
+                    r = std::hypot(f, g);
+                    e[i + 1] = r;
+                    if (r == 0.0) {
+                        d[i + 1] -= p;
+                        e[mm] = 0.0;
+                        break;
+                    }
+                    s = f / r;
+                    c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * b;
+                    p = s * r;
+                    d[i + 1] = g + p;
+                    g = c * r - b;
+                    for (int k = 0; k < m; ++k) {
+                        f = z[(size_t)k * m + i + 1];
+                        z[(size_t)k * m + i + 1] = s * z[(size_t)k * m + i] + c * f;
+                        z[(size_t)k * m + i] = c * z[(size_t)k * m + i] - s * f;
+                    }
+                }
+                if (r == 0.0 && i >= l) continue;
+                d[l] -= p;
+                e[l] = g;
+                e[mm] = 0.0;
+            }
+        } while (mm != l);
+    }
+    return true;
+}
+
+struct AffinityPlan {
+    int Np, Dp;
+    bool tensor;
+    int64_t off_a, off_b, off_xn, off_s, total;
+};
+AffinityPlan affinity_plan(int64_t N, int64_t D) {
+    AffinityPlan p;
+    p.Np = (int)align_up(N, 16);
+    p.Dp = (int)align_up(D, 16);
+    p.tensor = p.Np >= 128;
+    int64_t cur = 0;
+    p.off_a = cur; cur += align_up((int64_t)p.Np * 6 * p.Dp * 2, 1024);
+    p.off_b = cur; cur += align_up((int64_t)p.Np * 6 * p.Dp * 2, 1024);
+    p.off_xn = cur; cur += align_up((int64_t)p.Np * p.Dp * 4, 1024);
+    p.off_s = cur; cur += align_up((int64_t)p.Np * p.Np * 4, 1024);
+    p.total = cur;
+    return p;
+}
+
+}  // namespace
+}  // namespace spk
+
 using namespace spk;
-extern "C" int spk_affinity_laplacian(const float *, int64_t, int64_t, int64_t, float *, void *, int64_t, void *) {
-    set_error("not implemented"); return SPK_ERR_UNSUPPORTED; }
-extern "C" int64_t spk_affinity_workspace_bytes(int64_t, int64_t) { return 0; }
-extern "C" int spk_eig_smallest(const float *, int64_t, int32_t, float *, float *, void *, int64_t, void *) {
-    set_error("not implemented"); return SPK_ERR_UNSUPPORTED; }
-extern "C" int64_t spk_eig_workspace_bytes(int64_t, int32_t) { return 0; }
-extern "C" int spk_kmeans(const float *, int64_t, int32_t, int32_t, const float *, int32_t, float, int32_t *, float *,
-                          void *, int64_t, void *) { set_error("not implemented"); return SPK_ERR_UNSUPPORTED; }
-extern "C" int64_t spk_kmeans_workspace_bytes(int64_t, int32_t, int32_t) { return 0; }
-extern "C" int spk_cosine_pairs(const float *, int64_t, int64_t, const int32_t *, const int32_t *, int64_t, float *, void *) {
-    set_error("not implemented"); return SPK_ERR_UNSUPPORTED; }
+
+extern "C" int64_t spk_affinity_workspace_bytes(int64_t N, int64_t D) {
+    if (N <= 0 || D <= 0) return 0;
+    return affinity_plan(N, D).total;
+}
+
+// L must hold Np x Np floats with Np = N rounded up to 16 (row pitch Np); rows/cols >= N are not written.
+extern "C" int spk_affinity_laplacian(const float *X, int64_t N, int64_t D, int64_t keep, float *L, void *workspace,
+                                      int64_t workspace_bytes, void *stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    SPK_REQUIRE(X != nullptr && L != nullptr, "null buffer");
+    SPK_REQUIRE(N >= 2 && D >= 1 && N < (1 << 24), "bad shape N=%lld D=%lld", (long long)N, (long long)D);
+    SPK_REQUIRE(keep >= 1 && keep <= N, "keep=%lld out of range", (long long)keep);
+    int rc = require_device();
+    if (rc != SPK_OK) return rc;
+    const AffinityPlan p = affinity_plan(N, D);
+    if (workspace_bytes < p.total || workspace == nullptr) {
+        set_error("workspace too small: need %lld bytes", (long long)p.total);
+        return SPK_ERR_WORKSPACE;
+    }
+    char *ws = static_cast<char *>(workspace);
+    bf16 *A = reinterpret_cast<bf16 *>(ws + p.off_a), *B = reinterpret_cast<bf16 *>(ws + p.off_b);
+    float *Xn = reinterpret_cast<float *>(ws + p.off_xn);
+    const int Np = p.Np, Dp = p.Dp;
+    float *S = reinterpret_cast<float *>(ws + p.off_s);     // affinity, pruned in place
+    normalize_split_kernel<<<Np, 256, 0, s>>>(X, (int)N, (int)D, Np, Dp, p.tensor ? A : nullptr, p.tensor ? B : nullptr, Xn);
+    rc = check_launch("normalize_split_kernel");
+    if (rc != SPK_OK) return rc;
+    ConvArgs a{};
+    a.y = S; a.B = 1; a.H = 1; a.W = Np; a.Ho = 1; a.Wo = Np; a.Cout = Np;
+    a.KH = a.KW = a.sh = a.sw = a.dh = a.dw = 1;
+    a.out_ld = Np; a.gate_win = 1; a.gate_nwin = 1; a.M = Np;
+    if (p.tensor) {
+        a.x = A; a.w = B; a.Cin = 6 * Dp; a.K = 6 * Dp; a.in_ld = 6 * Dp;
+        if (!conv_gemm_supported(a, SPK_DT_BF16)) {
+            set_error("affinity: GEMM shape not supported (N=%d, D=%d)", Np, Dp);
+            return SPK_ERR_UNSUPPORTED;
+        }
+        rc = launch_conv_gemm(a, SPK_DT_F32, SPK_DT_F32, s);
+    } else {
+        a.x = Xn; a.w = Xn; a.Cin = Dp; a.K = Dp; a.in_ld = Dp;
+        rc = launch_conv_simt(a, SPK_DT_F32, SPK_DT_F32, SPK_DT_F32, s);
+    }
+    if (rc != SPK_OK) return rc;
+    const size_t sh = ((size_t)N + 256) * sizeof(unsigned);
+    if (sh > 200 * 1024) {
+        set_error("prune: N=%lld rows do not fit shared memory", (long long)N);
+        return SPK_ERR_UNSUPPORTED;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        SPK_CUDA_OK(cudaFuncSetAttribute(prune_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+    }
+    prune_rows_kernel<<<(unsigned)N, 256, sh, s>>>(S, (int)N, Np, (int)keep);
+    rc = check_launch("prune_rows_kernel");
+    if (rc != SPK_OK) return rc;
+    dim3 grid((unsigned)((N + 31) / 32), (unsigned)((N + 31) / 32));
+    symmetrize_neg_kernel<<<grid, 256, 0, s>>>(S, L, (int)N, Np, Np);
+    rc = check_launch("symmetrize_neg_kernel");
+    if (rc != SPK_OK) return rc;
+    laplacian_diag_kernel<<<(unsigned)N, 256, 0, s>>>(L, (int)N, Np);
+    return check_launch("laplacian_diag_kernel");
+}
+
+namespace {
+struct EigPlan { int m_max; int64_t off_V, off_w, off_h1, off_h2, off_alpha, off_beta, off_sm, off_sigma, total; };
+EigPlan eig_plan(int64_t N, int k) {
+    EigPlan p;
+    p.m_max = (int)std::min<int64_t>(N, std::max(20 * k, 320));
+    int64_t cur = 0;
+    auto take = [&](int64_t bytes) { int64_t o = cur; cur += align_up(bytes, 256); return o; };
+    p.off_V = take((int64_t)(p.m_max + 1) * N * 4);
+    p.off_w = take(N * 4);
+    p.off_h1 = take((int64_t)(p.m_max + 1) * 4);
+    p.off_h2 = take((int64_t)(p.m_max + 1) * 4);
+    p.off_alpha = take((int64_t)(p.m_max + 1) * 4);
+    p.off_beta = take((int64_t)(p.m_max + 1) * 4);
+    p.off_sm = take((int64_t)p.m_max * 32 * 4);
+    p.off_sigma = take(256);
+    p.total = cur;
+    return p;
+}
+}  // namespace
+
+extern "C" int64_t spk_eig_workspace_bytes(int64_t N, int32_t k) {
+    if (N <= 0 || k <= 0) return 0;
+    return eig_plan(N, k).total;
+}
+
+// L: [N, ld = N rounded up to 16] as written by spk_affinity_laplacian.
+extern "C" int spk_eig_smallest(const float *L, int64_t N, int32_t k, float *evals_host, float *evecs, void *workspace,
+                                int64_t workspace_bytes, void *stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    SPK_REQUIRE(L != nullptr && evals_host != nullptr && evecs != nullptr, "null buffer");
+    SPK_REQUIRE(N >= 2 && k >= 1 && k <= 32 && k <= N, "bad N=%lld k=%d (k <= 32)", (long long)N, k);
+    int rc = require_device();
+    if (rc != SPK_OK) return rc;
+    const EigPlan p = eig_plan(N, k);
+    if (workspace_bytes < p.total || workspace == nullptr) {
+        set_error("workspace too small: need %lld bytes", (long long)p.total);
+        return SPK_ERR_WORKSPACE;
+    }
+    const int n = (int)N, ld = (int)align_up(N, 16);
+    char *ws = static_cast<char *>(workspace);
+    float *V = reinterpret_cast<float *>(ws + p.off_V), *w = reinterpret_cast<float *>(ws + p.off_w);
+    float *h1 = reinterpret_cast<float *>(ws + p.off_h1), *h2 = reinterpret_cast<float *>(ws + p.off_h2);
+    float *alpha = reinterpret_cast<float *>(ws + p.off_alpha), *beta = reinterpret_cast<float *>(ws + p.off_beta);
+    float *Sm = reinterpret_cast<float *>(ws + p.off_sm), *dsigma = reinterpret_cast<float *>(ws + p.off_sigma);
+
+    gershgorin_kernel<<<1, 256, 0, s>>>(L, n, ld, dsigma);
+    float sigma = 0.f;
+    SPK_CUDA_OK(cudaMemcpyAsync(&sigma, dsigma, sizeof(float), cudaMemcpyDeviceToHost, s));
+    init_vector_kernel<<<1, 256, 0, s>>>(V, n, 0x9E3779B9u);
+    count_launch(2);
+    SPK_CUDA_OK(cudaStreamSynchronize(s));
+
+    std::vector<float> ha(p.m_max + 1), hb(p.m_max + 1);
+    std::vector<double> d, e, z;
+    int m_done = 0;
+    int m_target = std::min(p.m_max, std::max(8 * k, 96));
+    std::vector<int> order;
+    for (;;) {
+        // ---- extend the Krylov basis to m_target vectors
+        for (int j = m_done; j < m_target; ++j) {
+            float *vj = V + (size_t)j * n;
+            shifted_matvec_kernel<<<(n + 7) / 8, 256, 0, s>>>(L, n, ld, sigma, vj, w);
+            // full re-orthogonalisation, classical Gram-Schmidt applied twice
+            dots_kernel<<<j + 1, 256, 0, s>>>(V, n, j + 1, w, h1);
+            axpys_kernel<<<(n + 255) / 256, 256, 0, s>>>(V, n, j + 1, h1, w);
+            dots_kernel<<<j + 1, 256, 0, s>>>(V, n, j + 1, w, h2);
+            axpys_kernel<<<(n + 255) / 256, 256, 0, s>>>(V, n, j + 1, h2, w);
+            normalize_next_kernel<<<1, 256, 0, s>>>(w, n, V + (size_t)(j + 1) * n, h1, h2, j, alpha, beta, j);
+            count_launch(6);
+        }
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) {
+            set_error("lanczos launch failed: %s", cudaGetErrorString(le));
+            return SPK_ERR_CUDA;
+        }
+        m_done = m_target;
+        SPK_CUDA_OK(cudaMemcpyAsync(ha.data(), alpha, m_done * sizeof(float), cudaMemcpyDeviceToHost, s));
+        SPK_CUDA_OK(cudaMemcpyAsync(hb.data(), beta, m_done * sizeof(float), cudaMemcpyDeviceToHost, s));
+        SPK_CUDA_OK(cudaStreamSynchronize(s));
+        const int m = m_done;
+        d.assign(m, 0.0);
+        e.assign(m, 0.0);
+        for (int i = 0; i < m; ++i) d[i] = ha[i];
+        for (int i = 0; i + 1 < m; ++i) e[i] = hb[i];
+        if (!tridiag_eig(d, e, z, m)) {
+            set_error("tridiagonal QL did not converge");
+            return SPK_ERR_KERNEL;
+        }
+        order.resize(m);
+        for (int i = 0; i < m; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int x, int y) { return d[x] > d[y]; });   // largest of sigma*I - L
+        // residual estimate of Ritz pair c: |beta_m * z[m-1][c]|
+        double worst = 0.0;
+        for (int c = 0; c < k; ++c) worst = std::max(worst, std::fabs((double)hb[m - 1] * z[(size_t)(m - 1) * m + order[c]]));
+        const double tol = 2e-5 * std::max(1.0, (double)sigma);
+        if (worst <= tol || m_done >= p.m_max || m_done >= n) break;
+        m_target = std::min(p.m_max, m_done + std::max(4 * k, 64));
+    }
+    const int m = m_done;
+    std::vector<float> sm((size_t)m * k);
+    for (int c = 0; c < k; ++c) {
+        evals_host[c] = (float)((double)sigma - d[order[c]]);
+        for (int j = 0; j < m; ++j) sm[(size_t)j * k + c] = (float)z[(size_t)j * m + order[c]];
+    }
+    SPK_CUDA_OK(cudaMemcpyAsync(Sm, sm.data(), sm.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    ritz_kernel<<<(n + 255) / 256, 256, 0, s>>>(V, n, m, Sm, k, evecs);
+    rc = check_launch("ritz_kernel");
+    if (rc != SPK_OK) return rc;
+    SPK_CUDA_OK(cudaStreamSynchronize(s));      // sm is a host temporary
+    return m;
+}
+
+extern "C" int64_t spk_kmeans_workspace_bytes(int64_t N, int32_t d, int32_t k) {
+    (void)N;
+    return align_up((int64_t)k * d * 4, 256) + 256;
+}
+
+extern "C" int spk_kmeans(const float *pts, int64_t N, int32_t d, int32_t k, const float *init_centres_host, int32_t max_iter,
+                          float tol, int32_t *labels, float *inertia_host, void *workspace, int64_t workspace_bytes,
+                          void *stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    SPK_REQUIRE(pts != nullptr && init_centres_host != nullptr && labels != nullptr, "null buffer");
+    SPK_REQUIRE(N >= 1 && N < (1ll << 31) && d >= 1 && k >= 1 && k <= 64 && d <= 64, "bad shape N=%lld d=%d k=%d",
+                (long long)N, d, k);
+    int rc = require_device();
+    if (rc != SPK_OK) return rc;
+    SPK_REQUIRE(workspace != nullptr && workspace_bytes >= spk_kmeans_workspace_bytes(N, d, k), "workspace too small");
+    char *ws = static_cast<char *>(workspace);
+    const int64_t cb = align_up((int64_t)k * d * 4, 256);
+    float *C = reinterpret_cast<float *>(ws);
+    float *scal = reinterpret_cast<float *>(ws + cb);        // [0] inertia, [1] centre shift^2, [2] (int) changed labels
+    SPK_CUDA_OK(cudaMemcpyAsync(C, init_centres_host, (size_t)k * d * 4, cudaMemcpyHostToDevice, s));
+    SPK_CUDA_OK(cudaMemsetAsync(labels, 0xFF, (size_t)N * 4, s));
+    const int threads = 256, blocks = (int)((N + threads - 1) / threads);
+    const size_t sh = (size_t)k * d * sizeof(float);
+    int it = 0;
+    float host_scal[3];
+    bool converged = false;
+    while (it < max_iter && !converged) {
+        SPK_CUDA_OK(cudaMemsetAsync(scal, 0, 16, s));
+        kmeans_assign_kernel<<<blocks, threads, sh, s>>>(pts, (int)N, d, k, C, labels, scal, reinterpret_cast<int *>(scal + 2));
+        kmeans_update_kernel<<<k, 256, 0, s>>>(pts, (int)N, d, labels, C, scal + 1);
+        count_launch(2);
+        SPK_CUDA_OK(cudaMemcpyAsync(host_scal, scal, 12, cudaMemcpyDeviceToHost, s));
+        SPK_CUDA_OK(cudaStreamSynchronize(s));
+        int changed;
+        memcpy(&changed, &host_scal[2], 4);
+        ++it;
+        converged = (changed == 0) || (host_scal[1] <= tol);
+    }
+    // final labelling against the last centres (sklearn re-labels after the last centre update)
+    SPK_CUDA_OK(cudaMemsetAsync(scal, 0, 16, s));
+    kmeans_assign_kernel<<<blocks, threads, sh, s>>>(pts, (int)N, d, k, C, labels, scal, reinterpret_cast<int *>(scal + 2));
+    rc = check_launch("kmeans_assign_kernel");
+    if (rc != SPK_OK) return rc;
+    SPK_CUDA_OK(cudaMemcpyAsync(host_scal, scal, 12, cudaMemcpyDeviceToHost, s));
+    SPK_CUDA_OK(cudaStreamSynchronize(s));
+    if (inertia_host != nullptr) *inertia_host = host_scal[0];
+    return it;
+}
+
+extern "C" int spk_cosine_pairs(const float *E, int64_t N, int64_t D, const int32_t *a, const int32_t *b, int64_t n_pairs,
+                                float *out, void *stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    SPK_REQUIRE(n_pairs >= 0 && N >= 1 && D >= 1, "bad shape");
+    if (n_pairs == 0) return SPK_OK;
+    SPK_REQUIRE(E != nullptr && a != nullptr && b != nullptr && out != nullptr, "null buffer");
+    int rc = require_device();
+    if (rc != SPK_OK) return rc;
+    const long long blocks = (n_pairs + 7) / 8;
+    SPK_REQUIRE(blocks < (1ll << 31), "too many pairs for one call");
+    cosine_pairs_kernel<<<(unsigned)blocks, 256, 0, s>>>(E, N, (int)D, a, b, n_pairs, out);
+    return check_launch("cosine_pairs_kernel");
+}

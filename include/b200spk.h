@@ -138,19 +138,23 @@ int64_t spk_launch_count(void);
  * Replaces SpectralCluster.__call__ (speakerlab/process/cluster.py:35-57).
  */
 /* X: device [N,D] f32 (rows need not be normalised).  Writes the unnormalised Laplacian
- * L = D - M of the p-pruned, symmetrised cosine affinity (cluster.py:59-84) as dense [N,N] f32.
- * keep = N - n_elems entries survive per row (cluster.py:67-68). */
+ * L = D - M of the p-pruned, symmetrised cosine affinity (cluster.py:59-84) as dense f32 with row
+ * pitch Np = N rounded up to 16 (L must hold Np*Np floats; rows/cols >= N are not written).
+ * keep = N - n_elems entries survive per row (cluster.py:67-68); ties at the cut keep the higher
+ * column index (what a stable argsort zeroes last). */
 int spk_affinity_laplacian(const float *X, int64_t N, int64_t D, int64_t keep, float *L,
                            void *workspace, int64_t workspace_bytes, void *stream);
 int64_t spk_affinity_workspace_bytes(int64_t N, int64_t D);
-/* k smallest eigenpairs of symmetric PSD L (device [N,N] f32) by block Lanczos on sigma*I - L
- * (replaces scipy eigsh(which='SM'), cluster.py:90).  evals: host [k] ascending; evecs: device
- * [N,k] column j = eigenvector j (row-major [N,k]).  Synchronises the stream. */
+/* k <= 32 smallest eigenpairs of the symmetric PSD L written by spk_affinity_laplacian (row pitch
+ * Np) by Lanczos with full re-orthogonalisation on sigma*I - L (replaces scipy eigsh(which='SM'),
+ * cluster.py:90).  evals: host [k] ascending; evecs: device [N,k] row-major, column j =
+ * eigenvector j.  Synchronises the stream.  Returns the Krylov dimension used (> 0) or an error. */
 int spk_eig_smallest(const float *L, int64_t N, int32_t k, float *evals_host, float *evecs,
                      void *workspace, int64_t workspace_bytes, void *stream);
 int64_t spk_eig_workspace_bytes(int64_t N, int32_t k);
 /* Lloyd k-means on device points [N,d] f32 from caller-provided initial centres (host [k,d]);
- * labels: device int32 [N].  Returns iterations run (>=0) or an error code. */
+ * stops when no label changes or the summed squared centre shift is <= tol.  labels: device
+ * int32 [N].  Deterministic (fixed-order reductions).  Returns iterations run or an error. */
 int spk_kmeans(const float *pts, int64_t N, int32_t d, int32_t k, const float *init_centres_host,
                int32_t max_iter, float tol, int32_t *labels, float *inertia_host,
                void *workspace, int64_t workspace_bytes, void *stream);

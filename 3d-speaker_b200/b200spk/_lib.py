@@ -96,6 +96,11 @@ _SIGS = {
     "spk_eig_smallest": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_void_p]),
     "spk_eig_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
+    "spk_lanczos_extend": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "spk_lanczos_ritz": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_void_p]),
+    "spk_lanczos_max_dim": (C.c_int32, [C.c_int64, C.c_int32]),
     "spk_kmeans": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_float,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "spk_kmeans_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),

@@ -80,16 +80,40 @@ class SpectralCluster:
                                                 C.c_void_p(ws.data_ptr()), ws.numel(), _lib.current_stream_ptr()))
         return lap
 
-    def eig_smallest(self, lap, N, k):
+    def eig_smallest(self, lap, N, k, tol=1e-4):
+        """k smallest eigenpairs of the Laplacian: Lanczos on the GPU (spk_lanczos_extend), the small
+        tridiagonal problem by LAPACK on the host, Ritz vectors on the GPU (spk_lanczos_ritz).
+        Stops when every wanted Ritz pair has residual estimate |beta_m s_m| <= tol."""
+        from scipy.linalg import eigh_tridiagonal
         L = _lib.lib()
-        evals = np.empty(k, dtype=np.float32)
-        evecs = torch.empty((N, k), dtype=torch.float32, device=lap.device)
         ws = torch.empty(int(L.spk_eig_workspace_bytes(N, k)), dtype=torch.uint8, device=lap.device)
+        m_max = int(L.spk_lanczos_max_dim(N, k))
+        alpha = np.zeros(m_max + 1, dtype=np.float32)
+        beta = np.zeros(m_max + 1, dtype=np.float32)
+        sigma = C.c_float(0.0)
+        m_done, m_to = 0, min(m_max, max(8 * k, 96))
         with torch.cuda.device(lap.device):
-            m = _lib.check(L.spk_eig_smallest(C.c_void_p(lap.data_ptr()), N, k, evals.ctypes.data_as(C.c_void_p),
-                                              C.c_void_p(evecs.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
-                                              _lib.current_stream_ptr()))
-        self.last["krylov"] = int(m)
+            while True:
+                _lib.check(L.spk_lanczos_extend(C.c_void_p(lap.data_ptr()), N, k, m_done, m_to,
+                                                alpha.ctypes.data_as(C.c_void_p), beta.ctypes.data_as(C.c_void_p),
+                                                C.byref(sigma), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                                _lib.current_stream_ptr()))
+                m_done = m_to
+                d = alpha[:m_done].astype(np.float64)
+                e = beta[:m_done - 1].astype(np.float64)
+                theta, S = eigh_tridiagonal(d, e, select="i", select_range=(m_done - k, m_done - 1))
+                resid = np.abs(float(beta[m_done - 1]) * S[-1, :])
+                if resid.max() <= tol or m_done >= m_max or m_done >= N:
+                    break
+                m_to = min(m_max, m_done + max(6 * k, 96))
+            # largest Ritz values of sigma*I - L first == smallest eigenvalues of L first
+            theta, S = theta[::-1], np.ascontiguousarray(S[:, ::-1], dtype=np.float32)
+            evals = (float(sigma.value) - theta).astype(np.float32)
+            evecs = torch.empty((N, k), dtype=torch.float32, device=lap.device)
+            _lib.check(L.spk_lanczos_ritz(N, k, m_done, S.ctypes.data_as(C.c_void_p), C.c_void_p(evecs.data_ptr()),
+                                          C.c_void_p(ws.data_ptr()), ws.numel(), _lib.current_stream_ptr()))
+        self.last["krylov"] = int(m_done)
+        self.last["ritz_residual"] = float(resid.max())
         return evals, evecs
 
     def kmeans(self, emb, k):

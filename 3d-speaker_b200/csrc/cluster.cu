@@ -200,13 +200,31 @@ dots_kernel(const float *__restrict__ V, int N, int m, const float *__restrict__
     s = block_sum(s, sh);
     if (threadIdx.x == 0) h[j] = s;
 }
-// w -= sum_j h[j] V[j,:]; optionally accumulate alpha += h[m-1]
+// w -= sum_j h[j] V[j,:] in two deterministic stages: gridDim.y slices of the basis produce partial
+// sums (so the serial depth per thread is m / gridDim.y, not m), a second kernel folds them in order
 __global__ void __launch_bounds__(256)
-axpys_kernel(const float *__restrict__ V, int N, int m, const float *__restrict__ h, float *__restrict__ w) {
+axpys_partial_kernel(const float *__restrict__ V, int N, int m, const float *__restrict__ h, float *__restrict__ part) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int per = (m + gridDim.y - 1) / gridDim.y;
+    const int j0 = blockIdx.y * per, j1 = min(m, j0 + per);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int j = j0;
+    for (; j + 3 < j1; j += 4) {
+        s0 = fmaf(h[j], V[(size_t)j * N + i], s0);
+        s1 = fmaf(h[j + 1], V[(size_t)(j + 1) * N + i], s1);
+        s2 = fmaf(h[j + 2], V[(size_t)(j + 2) * N + i], s2);
+        s3 = fmaf(h[j + 3], V[(size_t)(j + 3) * N + i], s3);
+    }
+    for (; j < j1; ++j) s0 = fmaf(h[j], V[(size_t)j * N + i], s0);
+    part[(size_t)blockIdx.y * N + i] = (s0 + s1) + (s2 + s3);
+}
+__global__ void __launch_bounds__(256)
+axpys_finish_kernel(const float *__restrict__ part, int N, int slices, float *__restrict__ w) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float s = 0.f;
-    for (int j = 0; j < m; ++j) s = fmaf(h[j], V[(size_t)j * N + i], s);
+    for (int y = 0; y < slices; ++y) s += part[(size_t)y * N + i];
     w[i] -= s;
 }
 // beta = ||w||; V[m,:] = w / beta; record alpha (sum of the two projections on v_{m-1}) and beta
@@ -489,14 +507,18 @@ extern "C" int spk_affinity_laplacian(const float *X, int64_t N, int64_t D, int6
 }
 
 namespace {
-struct EigPlan { int m_max; int64_t off_V, off_w, off_h1, off_h2, off_alpha, off_beta, off_sm, off_sigma, total; };
+constexpr int kAxpySlices = 16;
+struct EigPlan { int m_max; int64_t off_V, off_w, off_part, off_h1, off_h2, off_alpha, off_beta, off_sm, off_sigma, total; };
 EigPlan eig_plan(int64_t N, int k) {
     EigPlan p;
-    p.m_max = (int)std::min<int64_t>(N, std::max(20 * k, 320));
+    // Krylov budget: clustered eigenvalues at the edge of the bulk (and exact multiplicities, which a
+    // single-vector Lanczos only separates through round-off) can need several hundred steps
+    p.m_max = (int)std::min<int64_t>(N, std::max(48 * k, 1024));
     int64_t cur = 0;
     auto take = [&](int64_t bytes) { int64_t o = cur; cur += align_up(bytes, 256); return o; };
     p.off_V = take((int64_t)(p.m_max + 1) * N * 4);
     p.off_w = take(N * 4);
+    p.off_part = take((int64_t)kAxpySlices * N * 4);
     p.off_h1 = take((int64_t)(p.m_max + 1) * 4);
     p.off_h2 = take((int64_t)(p.m_max + 1) * 4);
     p.off_alpha = take((int64_t)(p.m_max + 1) * 4);
@@ -513,12 +535,29 @@ extern "C" int64_t spk_eig_workspace_bytes(int64_t N, int32_t k) {
     return eig_plan(N, k).total;
 }
 
-// L: [N, ld = N rounded up to 16] as written by spk_affinity_laplacian.
-extern "C" int spk_eig_smallest(const float *L, int64_t N, int32_t k, float *evals_host, float *evecs, void *workspace,
-                                int64_t workspace_bytes, void *stream_) {
+namespace {
+struct EigBufs { float *V, *w, *part, *h1, *h2, *alpha, *beta, *Sm, *dsigma; };
+EigBufs eig_bufs(void *workspace, const EigPlan &p) {
+    char *ws = static_cast<char *>(workspace);
+    EigBufs b;
+    b.V = reinterpret_cast<float *>(ws + p.off_V); b.w = reinterpret_cast<float *>(ws + p.off_w);
+    b.part = reinterpret_cast<float *>(ws + p.off_part);
+    b.h1 = reinterpret_cast<float *>(ws + p.off_h1); b.h2 = reinterpret_cast<float *>(ws + p.off_h2);
+    b.alpha = reinterpret_cast<float *>(ws + p.off_alpha); b.beta = reinterpret_cast<float *>(ws + p.off_beta);
+    b.Sm = reinterpret_cast<float *>(ws + p.off_sm); b.dsigma = reinterpret_cast<float *>(ws + p.off_sigma);
+    return b;
+}
+}  // namespace
+
+// Extend the Krylov basis kept in `workspace` from m_from to m_to vectors (m_from = 0 starts a new
+// run: Gershgorin shift + deterministic start vector).  On return alpha_host[0..m_to) and
+// beta_host[0..m_to) hold the Lanczos tridiagonal of sigma*I - L and *sigma_host the shift.
+extern "C" int spk_lanczos_extend(const float *L, int64_t N, int32_t k, int32_t m_from, int32_t m_to, float *alpha_host,
+                                  float *beta_host, float *sigma_host, void *workspace, int64_t workspace_bytes,
+                                  void *stream_) {
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
-    SPK_REQUIRE(L != nullptr && evals_host != nullptr && evecs != nullptr, "null buffer");
-    SPK_REQUIRE(N >= 2 && k >= 1 && k <= 32 && k <= N, "bad N=%lld k=%d (k <= 32)", (long long)N, k);
+    SPK_REQUIRE(L != nullptr && alpha_host != nullptr && beta_host != nullptr && sigma_host != nullptr, "null buffer");
+    SPK_REQUIRE(N >= 2 && k >= 1 && k <= 32, "bad N=%lld k=%d", (long long)N, k);
     int rc = require_device();
     if (rc != SPK_OK) return rc;
     const EigPlan p = eig_plan(N, k);
@@ -526,47 +565,78 @@ extern "C" int spk_eig_smallest(const float *L, int64_t N, int32_t k, float *eva
         set_error("workspace too small: need %lld bytes", (long long)p.total);
         return SPK_ERR_WORKSPACE;
     }
+    SPK_REQUIRE(m_from >= 0 && m_to > m_from && m_to <= p.m_max, "bad Krylov range [%d,%d) (max %d)", m_from, m_to, p.m_max);
     const int n = (int)N, ld = (int)align_up(N, 16);
-    char *ws = static_cast<char *>(workspace);
-    float *V = reinterpret_cast<float *>(ws + p.off_V), *w = reinterpret_cast<float *>(ws + p.off_w);
-    float *h1 = reinterpret_cast<float *>(ws + p.off_h1), *h2 = reinterpret_cast<float *>(ws + p.off_h2);
-    float *alpha = reinterpret_cast<float *>(ws + p.off_alpha), *beta = reinterpret_cast<float *>(ws + p.off_beta);
-    float *Sm = reinterpret_cast<float *>(ws + p.off_sm), *dsigma = reinterpret_cast<float *>(ws + p.off_sigma);
-
-    gershgorin_kernel<<<1, 256, 0, s>>>(L, n, ld, dsigma);
-    float sigma = 0.f;
-    SPK_CUDA_OK(cudaMemcpyAsync(&sigma, dsigma, sizeof(float), cudaMemcpyDeviceToHost, s));
-    init_vector_kernel<<<1, 256, 0, s>>>(V, n, 0x9E3779B9u);
-    count_launch(2);
+    const EigBufs b = eig_bufs(workspace, p);
+    if (m_from == 0) {
+        gershgorin_kernel<<<1, 256, 0, s>>>(L, n, ld, b.dsigma);
+        init_vector_kernel<<<1, 256, 0, s>>>(b.V, n, 0x9E3779B9u);
+        count_launch(2);
+    }
+    SPK_CUDA_OK(cudaMemcpyAsync(sigma_host, b.dsigma, sizeof(float), cudaMemcpyDeviceToHost, s));
     SPK_CUDA_OK(cudaStreamSynchronize(s));
+    const float sigma = *sigma_host;
+    const int gx = (n + 255) / 256;
+    for (int j = m_from; j < m_to; ++j) {
+        float *vj = b.V + (size_t)j * n;
+        shifted_matvec_kernel<<<(n + 7) / 8, 256, 0, s>>>(L, n, ld, sigma, vj, b.w);
+        // full re-orthogonalisation: classical Gram-Schmidt applied twice
+        const int slices = std::min(kAxpySlices, (j + 1 + 31) / 32);
+        dots_kernel<<<j + 1, 256, 0, s>>>(b.V, n, j + 1, b.w, b.h1);
+        axpys_partial_kernel<<<dim3(gx, slices), 256, 0, s>>>(b.V, n, j + 1, b.h1, b.part);
+        axpys_finish_kernel<<<gx, 256, 0, s>>>(b.part, n, slices, b.w);
+        dots_kernel<<<j + 1, 256, 0, s>>>(b.V, n, j + 1, b.w, b.h2);
+        axpys_partial_kernel<<<dim3(gx, slices), 256, 0, s>>>(b.V, n, j + 1, b.h2, b.part);
+        axpys_finish_kernel<<<gx, 256, 0, s>>>(b.part, n, slices, b.w);
+        normalize_next_kernel<<<1, 256, 0, s>>>(b.w, n, b.V + (size_t)(j + 1) * n, b.h1, b.h2, j, b.alpha, b.beta, j);
+        count_launch(8);
+    }
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+        set_error("lanczos launch failed: %s", cudaGetErrorString(le));
+        return SPK_ERR_CUDA;
+    }
+    SPK_CUDA_OK(cudaMemcpyAsync(alpha_host, b.alpha, m_to * sizeof(float), cudaMemcpyDeviceToHost, s));
+    SPK_CUDA_OK(cudaMemcpyAsync(beta_host, b.beta, m_to * sizeof(float), cudaMemcpyDeviceToHost, s));
+    SPK_CUDA_OK(cudaStreamSynchronize(s));
+    return SPK_OK;
+}
 
+// Ritz vectors: evecs[N,k] = V[0..m)^T S, S = host [m,k] (eigenvectors of the tridiagonal, one per column)
+extern "C" int spk_lanczos_ritz(int64_t N, int32_t k, int32_t m, const float *S_host, float *evecs, void *workspace,
+                                int64_t workspace_bytes, void *stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    SPK_REQUIRE(S_host != nullptr && evecs != nullptr && workspace != nullptr, "null buffer");
+    SPK_REQUIRE(N >= 2 && k >= 1 && k <= 32, "bad N=%lld k=%d", (long long)N, k);
+    const EigPlan p = eig_plan(N, k);
+    SPK_REQUIRE(workspace_bytes >= p.total && m >= 1 && m <= p.m_max, "bad workspace or m=%d", m);
+    const EigBufs b = eig_bufs(workspace, p);
+    SPK_CUDA_OK(cudaMemcpyAsync(b.Sm, S_host, (size_t)m * k * sizeof(float), cudaMemcpyHostToDevice, s));
+    ritz_kernel<<<((int)N + 255) / 256, 256, 0, s>>>(b.V, (int)N, m, b.Sm, k, evecs);
+    int rc = check_launch("ritz_kernel");
+    if (rc != SPK_OK) return rc;
+    SPK_CUDA_OK(cudaStreamSynchronize(s));      // S_host may be a temporary
+    return SPK_OK;
+}
+
+extern "C" int32_t spk_lanczos_max_dim(int64_t N, int32_t k) { return (N > 0 && k > 0) ? eig_plan(N, k).m_max : 0; }
+
+// Self-contained variant for C callers: same Lanczos run, tridiagonal solved by the built-in
+// implicit-QL routine (O(m^3) with vectors - the Python mirror uses LAPACK's O(m k) instead).
+extern "C" int spk_eig_smallest(const float *L, int64_t N, int32_t k, float *evals_host, float *evecs, void *workspace,
+                                int64_t workspace_bytes, void *stream_) {
+    SPK_REQUIRE(L != nullptr && evals_host != nullptr && evecs != nullptr, "null buffer");
+    SPK_REQUIRE(N >= 2 && k >= 1 && k <= 32 && k <= N, "bad N=%lld k=%d (k <= 32)", (long long)N, k);
+    const EigPlan p = eig_plan(N, k);
     std::vector<float> ha(p.m_max + 1), hb(p.m_max + 1);
     std::vector<double> d, e, z;
-    int m_done = 0;
-    int m_target = std::min(p.m_max, std::max(8 * k, 96));
     std::vector<int> order;
+    float sigma = 0.f;
+    int m_done = 0, m_target = std::min(p.m_max, std::max(8 * k, 96));
     for (;;) {
-        // ---- extend the Krylov basis to m_target vectors
-        for (int j = m_done; j < m_target; ++j) {
-            float *vj = V + (size_t)j * n;
-            shifted_matvec_kernel<<<(n + 7) / 8, 256, 0, s>>>(L, n, ld, sigma, vj, w);
-            // full re-orthogonalisation, classical Gram-Schmidt applied twice
-            dots_kernel<<<j + 1, 256, 0, s>>>(V, n, j + 1, w, h1);
-            axpys_kernel<<<(n + 255) / 256, 256, 0, s>>>(V, n, j + 1, h1, w);
-            dots_kernel<<<j + 1, 256, 0, s>>>(V, n, j + 1, w, h2);
-            axpys_kernel<<<(n + 255) / 256, 256, 0, s>>>(V, n, j + 1, h2, w);
-            normalize_next_kernel<<<1, 256, 0, s>>>(w, n, V + (size_t)(j + 1) * n, h1, h2, j, alpha, beta, j);
-            count_launch(6);
-        }
-        cudaError_t le = cudaGetLastError();
-        if (le != cudaSuccess) {
-            set_error("lanczos launch failed: %s", cudaGetErrorString(le));
-            return SPK_ERR_CUDA;
-        }
+        int rc = spk_lanczos_extend(L, N, k, m_done, m_target, ha.data(), hb.data(), &sigma, workspace, workspace_bytes, stream_);
+        if (rc != SPK_OK) return rc;
         m_done = m_target;
-        SPK_CUDA_OK(cudaMemcpyAsync(ha.data(), alpha, m_done * sizeof(float), cudaMemcpyDeviceToHost, s));
-        SPK_CUDA_OK(cudaMemcpyAsync(hb.data(), beta, m_done * sizeof(float), cudaMemcpyDeviceToHost, s));
-        SPK_CUDA_OK(cudaStreamSynchronize(s));
         const int m = m_done;
         d.assign(m, 0.0);
         e.assign(m, 0.0);
@@ -579,12 +649,10 @@ extern "C" int spk_eig_smallest(const float *L, int64_t N, int32_t k, float *eva
         order.resize(m);
         for (int i = 0; i < m; ++i) order[i] = i;
         std::sort(order.begin(), order.end(), [&](int x, int y) { return d[x] > d[y]; });   // largest of sigma*I - L
-        // residual estimate of Ritz pair c: |beta_m * z[m-1][c]|
-        double worst = 0.0;
+        double worst = 0.0;      // residual estimate of Ritz pair c: |beta_m * z[m-1][c]|
         for (int c = 0; c < k; ++c) worst = std::max(worst, std::fabs((double)hb[m - 1] * z[(size_t)(m - 1) * m + order[c]]));
-        const double tol = 2e-5 * std::max(1.0, (double)sigma);
-        if (worst <= tol || m_done >= p.m_max || m_done >= n) break;
-        m_target = std::min(p.m_max, m_done + std::max(4 * k, 64));
+        if (worst <= 1e-4 || m_done >= p.m_max || m_done >= (int)N) break;
+        m_target = std::min(p.m_max, m_done + std::max(6 * k, 96));
     }
     const int m = m_done;
     std::vector<float> sm((size_t)m * k);
@@ -592,12 +660,8 @@ extern "C" int spk_eig_smallest(const float *L, int64_t N, int32_t k, float *eva
         evals_host[c] = (float)((double)sigma - d[order[c]]);
         for (int j = 0; j < m; ++j) sm[(size_t)j * k + c] = (float)z[(size_t)j * m + order[c]];
     }
-    SPK_CUDA_OK(cudaMemcpyAsync(Sm, sm.data(), sm.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-    ritz_kernel<<<(n + 255) / 256, 256, 0, s>>>(V, n, m, Sm, k, evecs);
-    rc = check_launch("ritz_kernel");
-    if (rc != SPK_OK) return rc;
-    SPK_CUDA_OK(cudaStreamSynchronize(s));      // sm is a host temporary
-    return m;
+    int rc = spk_lanczos_ritz(N, k, m, sm.data(), evecs, workspace, workspace_bytes, stream_);
+    return rc == SPK_OK ? m : rc;
 }
 
 extern "C" int64_t spk_kmeans_workspace_bytes(int64_t N, int32_t d, int32_t k) {

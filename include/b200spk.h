@@ -152,6 +152,17 @@ int64_t spk_affinity_workspace_bytes(int64_t N, int64_t D);
 int spk_eig_smallest(const float *L, int64_t N, int32_t k, float *evals_host, float *evecs,
                      void *workspace, int64_t workspace_bytes, void *stream);
 int64_t spk_eig_workspace_bytes(int64_t N, int32_t k);
+/* The same eigensolver in two steps, for hosts that bring their own tridiagonal solver (the
+ * Python mirror uses LAPACK through scipy.linalg.eigh_tridiagonal): spk_lanczos_extend grows the
+ * Krylov basis kept in the workspace from m_from to m_to vectors (m_from = 0 starts a run) and
+ * returns the tridiagonal of sigma*I - L (alpha/beta, host) and the shift sigma;
+ * spk_lanczos_ritz turns S (host [m,k], eigenvectors of that tridiagonal) into evecs [N,k]. */
+int spk_lanczos_extend(const float *L, int64_t N, int32_t k, int32_t m_from, int32_t m_to, float *alpha_host,
+                       float *beta_host, float *sigma_host, void *workspace, int64_t workspace_bytes,
+                       void *stream);
+int spk_lanczos_ritz(int64_t N, int32_t k, int32_t m, const float *S_host, float *evecs, void *workspace,
+                     int64_t workspace_bytes, void *stream);
+int32_t spk_lanczos_max_dim(int64_t N, int32_t k);
 /* Lloyd k-means on device points [N,d] f32 from caller-provided initial centres (host [k,d]);
  * stops when no label changes or the summed squared centre shift is <= tol.  labels: device
  * int32 [N].  Deterministic (fixed-order reductions).  Returns iterations run or an error. */

@@ -16,5 +16,6 @@ from .fbank import FBank, fbank_batch, num_frames  # noqa: F401
 from .campplus import CAMPPlus  # noqa: F401
 from .cluster import SpectralCluster, cosine_pairs  # noqa: F401
 from .extract import EmbeddingExtractor  # noqa: F401
+from .diarize import Diarizer, cut_windows, gather_embeddings, shard_range  # noqa: F401
 
-__all__ = ["FBank", "CAMPPlus", "SpectralCluster", "cosine_pairs", "EmbeddingExtractor", "SpkError", "fbank_batch", "num_frames", "lib"]
+__all__ = ["FBank", "CAMPPlus", "SpectralCluster", "cosine_pairs", "EmbeddingExtractor", "Diarizer", "SpkError", "fbank_batch", "num_frames", "lib"]

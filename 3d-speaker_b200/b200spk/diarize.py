@@ -1,0 +1,131 @@
+"""Sub-segment diarization pipeline on the GPU: the hot loop of
+``Diarization3Dspeaker.__call__`` (speakerlab/bin/infer_diarization.py:256-315) without VAD and
+RTTM writing: chunk -> windows -> fbank -> embeddings -> spectral clustering.
+
+Multi-GPU (new behaviour): the N sub-segments of ONE recording are sharded
+contiguously over the ranks of a ``torch.distributed`` group (no data-path collective during
+extraction), then ONE ``all_gather`` of the ``[N/G, E]`` embedding shards feeds the clustering
+stage, which runs on every rank (identical inputs -> identical labels) or only where needed.
+"""
+import math
+
+import numpy as np
+import torch
+
+FS = 16000
+
+
+def chunk(st, ed, dur=1.5, step=0.75):
+    """Sub-segment boundaries of one voiced region (infer_diarization.py:606-619)."""
+    out = []
+    if ed - st <= 0:
+        return out
+    s, made = st, False
+    while s + dur < ed + step:
+        out.append([s, min(s + dur, ed)])
+        s += step
+        made = True
+    if not made:
+        out.append([st, ed])
+    return out
+
+
+def circle_pad(x, target_len):
+    """speakerlab/utils/utils.py:232-238 for 1-D tensors."""
+    n = x.shape[0]
+    if n >= target_len:
+        return x
+    reps = int(math.ceil(target_len / n))
+    return x.repeat(reps)[:target_len]
+
+
+def cut_windows(wav, chunks, fs=FS):
+    """infer_diarization.py:624-627 on a resident waveform: slice every chunk, circle-pad to the
+    longest and stack -> [N, L].  wav: 1-D tensor (any device); the gather runs on that device,
+    so a waveform already in HBM never travels back to the host."""
+    starts = torch.tensor([int(st * fs) for st, _ in chunks], dtype=torch.long)
+    ends = torch.tensor([int(ed * fs) for _, ed in chunks], dtype=torch.long)
+    lens = ends - starts
+    L = int(lens.max())
+    full = lens == L
+    idx = starts.to(wav.device)[:, None] + torch.arange(L, device=wav.device)[None, :]
+    idx = torch.minimum(idx, torch.tensor(wav.shape[0] - 1, device=wav.device))
+    out = wav[idx]
+    for i in torch.nonzero(~full).flatten().tolist():       # ragged tail windows: the reference's circle_pad
+        out[i] = circle_pad(wav[int(starts[i]):int(ends[i])], L)
+    return out
+
+
+def shard_range(n, rank, world):
+    """Contiguous shard [lo, hi) of n items for this rank; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_embeddings(local, n_total, group=None):
+    """all_gather the per-rank embedding shards (padded to equal rows) -> [n_total, E] on every rank."""
+    import torch.distributed as dist
+    if group is None and not (dist.is_available() and dist.is_initialized()):
+        return local
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    per = (n_total + world - 1) // world
+    pad = torch.zeros((per, local.shape[1]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = torch.empty((world * per, local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    rows = []
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        rows.append(out[r * per:r * per + (hi - lo)])
+    return torch.cat(rows, dim=0)
+
+
+class Diarizer:
+    """feature_extractor: b200spk.FBank; embedding_model: b200spk.CAMPPlus (on `device`);
+    cluster: b200spk.SpectralCluster."""
+
+    def __init__(self, feature_extractor, embedding_model, cluster, device="cuda:0", batchsize=2048,
+                 seg_dur=1.5, seg_shift=0.75, group=None):
+        self.fe, self.model, self.cluster = feature_extractor, embedding_model, cluster
+        self.device = torch.device(device)
+        self.batchsize, self.seg_dur, self.seg_shift = batchsize, seg_dur, seg_shift
+        self.group = group
+        self.fs = feature_extractor.sample_rate
+
+    def subsegments(self, vad_segments):
+        return [c for st, ed in vad_segments for c in chunk(st, ed, self.seg_dur, self.seg_shift)]
+
+    def extract(self, wav_dev, chunks):
+        """Embeddings of this rank's shard of the sub-segments -> [n_local, E] on the device."""
+        import torch.distributed as dist
+        rank, world = 0, 1
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        lo, hi = shard_range(len(chunks), rank, world)
+        outs = []
+        with torch.no_grad():
+            for st in range(lo, hi, self.batchsize):
+                wins = cut_windows(wav_dev, chunks[st:min(hi, st + self.batchsize)], self.fs)
+                outs.append(self.model(self.fe.batch(wins)))
+        if not outs:
+            return torch.zeros((0, self.model.embedding_size), device=self.device)
+        return torch.cat(outs, dim=0)
+
+    def __call__(self, wav, vad_segments=None, speaker_num=None):
+        """wav: [T] or [1,T] float tensor/array at 16 kHz; vad_segments: [[st, ed], ...] in seconds
+        (default: the whole recording).  Returns (chunks, labels)."""
+        wav = torch.as_tensor(wav, dtype=torch.float32)
+        if wav.dim() == 2:
+            wav = wav[0]
+        if vad_segments is None:
+            vad_segments = [[0.0, wav.shape[0] / self.fs]]
+        chunks = self.subsegments(vad_segments)
+        wav_dev = wav.to(self.device, non_blocking=True)
+        local = self.extract(wav_dev, chunks)
+        emb = gather_embeddings(local, len(chunks), self.group)
+        kw = {} if speaker_num is None else {"speaker_num": speaker_num}
+        labels = self.cluster(emb, **kw)
+        return chunks, labels

@@ -1,0 +1,66 @@
+"""GPU: the whole path on a synthetic meeting: windows -> fbank -> CAM++ -> spectral clustering."""
+import numpy as np
+import pytest
+import torch
+
+import b200spk
+from oracle import campplus_oracle, cluster_oracle, fbank_oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _pipeline(precision="fp32", seed=1):
+    torch.manual_seed(seed)                           # default init, BN not randomised
+    model = b200spk.CAMPPlus(embedding_size=192, precision=precision).cuda().eval()
+    fb = b200spk.FBank(80, 16000, mean_nor=True)
+    sc = b200spk.SpectralCluster(min_num_spks=1, max_num_spks=15, pval=0.012)
+    return model, fb, sc
+
+
+@pytest.mark.parametrize("n_spk", [4])
+def test_meeting_end_to_end(n_spk):
+    seconds = 1200.0
+    wav, turns = synth.fm_meeting(seconds, n_spk, seed=17)
+    model, fb, sc = _pipeline()
+    dz = b200spk.Diarizer(fb, model, sc, batchsize=512)
+    np.random.seed(0)
+    chunks, labels = dz(torch.from_numpy(wav))
+    assert len(chunks) == len(synth.chunk(0.0, seconds)) == 1599
+    truth, pure = synth.turn_labels(chunks, turns)
+    # (1) embeddings parity against the CPU oracle on a subsample
+    pick = np.arange(0, len(chunks), 50)
+    wins = synth.cut_windows(wav, [chunks[i] for i in pick])
+    ref = campplus_oracle.forward({k: v.detach().cpu() for k, v in model.state_dict().items()},
+                                  fbank_oracle.fbank_batch(wins)).numpy()
+    with torch.no_grad():
+        got = model(fb.batch(torch.from_numpy(wins).cuda())).cpu().numpy()
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-3        # fbank fp32 noise included
+    cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
+    assert cos.min() >= 0.9999
+    # (2) clustering parity at scale: the oracle back end on the SAME embeddings
+    with torch.no_grad():
+        emb = dz.extract(torch.from_numpy(wav).cuda(), chunks).cpu().numpy()
+    np.random.seed(0)
+    ref_labels, st = cluster_oracle.spectral_cluster(emb, 1, 15, 0.012, return_stages=True)
+    assert sc.last["k"] == st["k"]
+    mapped = cluster_oracle.match_labels(ref_labels, labels)
+    assert np.array_equal(mapped[pure], ref_labels[pure])                 # identical on single-speaker segments
+    assert (mapped != ref_labels).sum() <= 3                              # straddling segments may flip
+    # (3) and the result is right: k = number of speakers, pure segments all correct
+    assert sc.last["k"] == n_spk
+    acc = (cluster_oracle.match_labels(truth, labels)[pure] == truth[pure]).mean()
+    assert acc >= 0.99, acc
+
+
+def test_bf16_meeting_labels_match_fp32():
+    wav, turns = synth.fm_meeting(600.0, 3, seed=23)
+    out = {}
+    for prec in ("fp32", "bf16"):
+        model, fb, sc = _pipeline(prec)
+        np.random.seed(0)
+        chunks, labels = b200spk.Diarizer(fb, model, sc)(torch.from_numpy(wav))
+        out[prec] = (labels, sc.last["k"])
+    truth, pure = synth.turn_labels(chunks, turns)
+    assert out["fp32"][1] == out["bf16"][1]
+    m = cluster_oracle.match_labels(out["fp32"][0], out["bf16"][0])
+    assert np.array_equal(m[pure], out["fp32"][0][pure])

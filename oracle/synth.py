@@ -23,7 +23,12 @@ def white_noise(n_utts, n_samples, seed, scale=0.1):
     return (scale * rng.standard_normal((n_utts, n_samples))).astype(np.float32)
 
 
-_FM_RATES = (2.0, 3.0, 4.5, 6.0, 8.0, 11.0, 14.0, 18.0)
+# FM rates are multiples of 8/3 Hz: FM period and the AM period (rate r/2) both divide the 0.75 s
+# sub-segment hop, so every window of a speaker sees the same modulation phase.  With free-running
+# rates the within-speaker embeddings trace a phase loop, the 58-nearest-neighbour graph of a speaker
+# becomes a ring with many near-zero Laplacian modes, and the reference's eigengap rule returns
+# k = 14 instead of the number of speakers (measured with the CPU oracle).
+_FM_RATES = tuple(8.0 / 3.0 * n for n in range(1, 9))
 
 
 def _fm_voice(k, n_spk, t):

@@ -171,6 +171,63 @@ def workload_config(args, batch):
             "l2": "inputs larger than L2 (%.0f MB of windows per step)" % (args.segments * N_SAMPLES * 4 / 1e6)}
 
 
+# ----------------------------------------------------------------------------- diarization leg
+def diarization_leg(args, dev, rank, world, dist):
+    """BASELINE config 3: a synthetic 1-hour meeting -> 4799 sub-segments -> CAM++ (192-d) ->
+    cosine affinity + spectral clustering, sub-segments sharded over the ranks, one all_gather of
+    the embeddings.  Timed end to end from the waveform in pinned host memory to labels on the
+    host; RTF = wall / audio seconds."""
+    import b200spk
+    from oracle import cluster_oracle, synth
+    secs, K = args.meeting_seconds, args.meeting_speakers
+    n = int(round(secs * 16000))
+    if rank == 0:
+        wav_np, turns = synth.fm_meeting(secs, K, seed=18)
+        wav = torch.from_numpy(wav_np).pin_memory()
+    else:
+        wav, turns = torch.empty(n, dtype=torch.float32).pin_memory(), None
+    if dist is not None:
+        tmp = wav.to(dev)
+        dist.broadcast(tmp, src=0)
+        wav.copy_(tmp)
+        del tmp
+    torch.manual_seed(1)                                   # default init, BN not randomised (SURVEY 8d config 4)
+    model = b200spk.CAMPPlus(embedding_size=192, precision=args.precision).to(dev).eval()
+    dz = b200spk.Diarizer(b200spk.FBank(80, 16000, mean_nor=True), model,
+                          b200spk.SpectralCluster(min_num_spks=1, max_num_spks=15, pval=0.012, device=dev),
+                          device=dev, batchsize=args.batch)
+    times = []
+    for it in range(4):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        chunks, labels = dz(wav)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    t = torch.tensor([sorted(times[1:])[1]], device=dev)    # median of the 3 timed runs
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t.item())
+    if rank != 0:
+        return None
+    truth, pure = synth.turn_labels(chunks, turns)
+    purity = sum(np.bincount(truth[pure & (labels == c)]).max() for c in np.unique(labels[pure])) / pure.sum()
+    # parity of the back end at full size: the CPU oracle on the SAME embeddings
+    with torch.no_grad():
+        emb = b200spk.gather_embeddings(dz.extract(wav.to(dev), chunks), len(chunks)).cpu().numpy() if world == 1 else None
+    parity = None
+    if emb is not None:
+        np.random.seed(0)
+        ref, st = cluster_oracle.spectral_cluster(emb, 1, 15, 0.012, return_stages=True)
+        m = cluster_oracle.match_labels(ref, labels)
+        parity = {"k_oracle": int(st["k"]), "mismatch_pure": int((m != ref)[pure].sum()), "mismatch_total": int((m != ref).sum())}
+    return {"audio_seconds": secs, "n_subsegments": len(chunks), "speakers": K, "wall_s": wall, "rtf": wall / secs,
+            "k": int(dz.cluster.last["k"]), "purity_on_single_speaker_segments": float(purity),
+            "krylov_dim": int(dz.cluster.last["krylov"]), "vs_oracle_backend": parity}
+
+
 # ----------------------------------------------------------------------------- GPU leg
 def main():
     ap = argparse.ArgumentParser()
@@ -185,6 +242,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-meeting", action="store_true", help="skip the 1-hour diarization leg")
+    ap.add_argument("--meeting-seconds", type=float, default=3600.0)
+    ap.add_argument("--meeting-speakers", type=int, default=8)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -283,6 +343,8 @@ def main():
     e2e = world * S * args.steps / e2e_s
     assert emb_host.shape == (S, EMB) and bool(torch.isfinite(emb_host).all())
 
+    meeting = None if args.no_meeting else diarization_leg(args, dev, rank, world, dist)
+
     if rank == 0:
         pk = peaks()
         calls = len(fw_ms)
@@ -309,6 +371,8 @@ def main():
                                "bytes_per_launch": FBANK_BYTES_PER_SEG * segs_per_call, "ms_per_launch": fb_avg},
             "clocks": clk.summary(),
         }
+        if meeting is not None:
+            line["diarization"] = meeting
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_reference(args.cpu_seconds)
         print(json.dumps(line))

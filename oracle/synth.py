@@ -49,9 +49,14 @@ def _fm_voice(k, n_spk, t):
     return x
 
 
-def fm_meeting(seconds, n_spk, seed, fs=FS):
-    """Synthetic meeting: random turns U(2,20) s, no immediate repeats, ~100 % speech,
-    peak 0.2, white noise floor at -40 dB re peak.  Returns (wav float32 [n], turns)."""
+def fm_meeting(seconds, n_spk, seed, fs=FS, noise_db=-25.0):
+    """Synthetic meeting: random turns U(2,20) s, no immediate repeats, ~100 % speech, peak 0.2,
+    white noise floor at ``noise_db`` re peak.  The noise floor matters: with phase-locked voices the
+    windows of a speaker differ only through it, and at -40 dB they are so alike that the
+    58-nearest-neighbour pruning is an arbitrary pick among near-ties (cosines equal to 1e-7);
+    at -25 dB the CPU oracle returns k = 8 with 100 % pure-segment accuracy for 8 speakers / 1 hour
+    and is stable under 1e-6 relative perturbations of the embeddings (measured).
+    Returns (wav float32 [n], turns)."""
     rng = np.random.default_rng([seed, 0x3EE7])
     n = int(round(seconds * fs))
     t = np.arange(n, dtype=np.float64) / fs
@@ -71,7 +76,7 @@ def fm_meeting(seconds, n_spk, seed, fs=FS):
         turns.append((pos, end, spk))
         pos, prev = end, spk
     wav *= 0.2 / max(np.abs(wav).max(), 1e-9)
-    wav += 0.2 * 10 ** (-40 / 20) * rng.standard_normal(n)
+    wav += 0.2 * 10 ** (noise_db / 20) * rng.standard_normal(n)
     return wav.astype(np.float32), turns
 
 

@@ -95,14 +95,14 @@ def test_two_seg_windows_and_ragged_T():
 
 # torch's own CPU bf16 execution of the reference graph on the same weights/inputs, measured in
 # this repo's container (tools/diag_bf16.py + the snippet in DESIGN.md): min cosine vs fp32.
-TORCH_CPU_BF16_COS = {"noise_bnrand7": 0.999066, "fm_freshbn104": 0.999801, "fm_bnrand101": 0.959640}
+TORCH_CPU_BF16_COS = {"noise_bnrand7": 0.999066, "fm_freshbn104": 0.999910, "fm_bnrand101": 0.991871}
 
 
 @pytest.mark.parametrize("case", ["noise_bnrand7", "fm_freshbn104", "fm_bnrand101"])
 def test_bf16_mode(case):
     """bf16 = tcgen05 tensor-core path.  North-star tolerance: cosine >= 0.999 vs the CPU fp32
     reference path.  Weight set 101 (randomised BN) is ill-conditioned - PyTorch's own bf16 run of
-    the reference graph only reaches 0.9596 on it - so there the bar is 'no worse than torch bf16'."""
+    the reference graph only reaches 0.9919 on it - so there the bar is 'no worse than torch bf16'."""
     wseed, bnrand = {"noise_bnrand7": (7, True), "fm_freshbn104": (104, False), "fm_bnrand101": (101, True)}[case]
     if case.startswith("noise"):
         wavs = synth.white_noise(16, 24000, seed=123)

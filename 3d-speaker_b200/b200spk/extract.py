@@ -15,22 +15,45 @@ class EmbeddingExtractor:
         self._copy_stream = None
 
     def __call__(self, wavs):
-        """wavs: host tensor [N, L] (pinned for async copies) or [N, 1, L] -> host [N, E]."""
+        """wavs: host tensor [N, L] (pinned for async copies) or [N, 1, L] -> host [N, E].
+
+        Same per-batch H2D / fbank / forward / D2H sequence as the reference loop; the copy of batch
+        i+1 runs on a second stream while batch i computes (the reference serialises them)."""
         if wavs.dim() == 3:
             wavs = wavs[:, 0, :]
         N = wavs.shape[0]
+        if N == 0:
+            return torch.empty((0, self.embedding_model.embedding_size))
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        cs = self._copy_stream
+        starts = list(range(0, N, self.batchsize))
+
+        def stage(st):
+            with torch.cuda.stream(cs):
+                buf = wavs[st:st + self.batchsize].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            return buf, ev
+
         out = None
+        nxt = stage(starts[0])
         with torch.no_grad():
-            for st in range(0, N, self.batchsize):
-                wb = wavs[st:st + self.batchsize].to(self.device, non_blocking=True)
+            for i, st in enumerate(starts):
+                wb, ev = nxt
+                if i + 1 < len(starts):
+                    nxt = stage(starts[i + 1])
+                main.wait_event(ev)
+                wb.record_stream(main)
                 feats = self.feature_extractor.batch(wb)
                 emb = self.embedding_model(feats)
                 if out is None:
-                    out = torch.empty((N, emb.shape[1]), dtype=torch.float32,
-                                      pin_memory=wavs.is_pinned())
+                    out = torch.empty((N, emb.shape[1]), dtype=torch.float32, pin_memory=wavs.is_pinned())
                 out[st:st + emb.shape[0]].copy_(emb, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return out if out is not None else torch.empty((0, 0))
+        main.synchronize()
+        return out
 
     def extract_device(self, wavs_dev):
         """Same loop with inputs already resident in HBM; returns device embeddings."""

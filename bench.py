@@ -235,7 +235,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--segments", type=int, default=4096, help="1.5 s windows per GPU per step")
+    ap.add_argument("--segments", type=int, default=16384, help="1.5 s windows per GPU per step")
     ap.add_argument("--batch", type=int, default=2048, help="windows per fbank/forward call")
     ap.add_argument("--chunk", type=int, default=0, help="coarse sub-batch (D-TDNN part), 0 = auto")
     ap.add_argument("--fine", type=int, default=0, help="fine sub-batch (2-D front), 0 = auto")

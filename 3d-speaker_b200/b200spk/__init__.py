@@ -14,8 +14,9 @@ without an sm_100 device every compute call raises ``SpkError``.
 from ._lib import SpkError, lib, LIB_PATH  # noqa: F401
 from .fbank import FBank, fbank_batch, num_frames  # noqa: F401
 from .campplus import CAMPPlus  # noqa: F401
+from .eres2netv2 import ERes2NetV2  # noqa: F401
 from .cluster import SpectralCluster, cosine_pairs  # noqa: F401
 from .extract import EmbeddingExtractor  # noqa: F401
 from .diarize import Diarizer, cut_windows, gather_embeddings, shard_range  # noqa: F401
 
-__all__ = ["FBank", "CAMPPlus", "SpectralCluster", "cosine_pairs", "EmbeddingExtractor", "Diarizer", "SpkError", "fbank_batch", "num_frames", "lib"]
+__all__ = ["FBank", "CAMPPlus", "ERes2NetV2", "SpectralCluster", "cosine_pairs", "EmbeddingExtractor", "Diarizer", "SpkError", "fbank_batch", "num_frames", "lib"]

@@ -23,7 +23,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .program import Model, Program, conv_out, fold_bn, pack_conv1d, pack_conv2d
+from .program import EngineBase, EngineModule, Program, conv_out
 
 SEG_LEN = 100   # CAMLayer.seg_pooling (layers.py:100)
 
@@ -51,7 +51,7 @@ def _res_block(cin, cout, stride):
     return t
 
 
-class CAMPPlus(nn.Module):
+class CAMPPlus(EngineModule):
     def __init__(self, feat_dim=80, embedding_size=512, growth_rate=32, bn_size=4, init_channels=128,
                  config_str='batchnorm-relu', memory_efficient=True, precision="fp32", chunk=None):
         super().__init__()
@@ -60,8 +60,7 @@ class CAMPPlus(nn.Module):
         self.feat_dim, self.embedding_size = feat_dim, embedding_size
         self.growth_rate, self.bn_channels, self.init_channels = growth_rate, bn_size * growth_rate, init_channels
         self.block_cfg = ((12, 3, 1), (24, 3, 2), (16, 3, 2))   # DTDNN.py:77-78
-        self.precision = precision
-        self.chunk = chunk
+        self._init_engine(precision, chunk)
         m = 32
         self.head = _Tree(conv1=nn.Conv2d(1, m, 3, padding=1, bias=False), bn1=nn.BatchNorm2d(m),
                           layer1=nn.Sequential(_res_block(m, m, 2), _res_block(m, m, 1)),
@@ -99,81 +98,14 @@ class CAMPPlus(nn.Module):
                 nn.init.kaiming_normal_(mod.weight.data)
                 if mod.bias is not None:
                     nn.init.zeros_(mod.bias)
-        self._engine = None
-        self._engine_key = None
         self.eval()
-
-    # ------------------------------------------------------------------ engine management
-    def invalidate(self):
-        """Drop the compiled engine (call after editing weights in place; load_state_dict and
-        .to()/.cuda() do it automatically)."""
-        if getattr(self, "_engine", None) is not None:
-            self._engine.close()
-        self._engine = None
-        self._engine_key = None
-
-    def load_state_dict(self, *args, **kwargs):
-        out = super().load_state_dict(*args, **kwargs)
-        self.invalidate()
-        return out
-
-    def _apply(self, fn, *args, **kwargs):
-        out = super()._apply(fn, *args, **kwargs)
-        self.invalidate()
-        return out
-
-    def _get_engine(self, device):
-        key = (str(device), self.precision)
-        if self._engine is None or self._engine_key != key:
-            self.invalidate()
-            prec = _lib.PREC_BF16 if self.precision in ("bf16", "bfloat16") else _lib.PREC_F32
-            self._engine = _Engine(self, Model(prec, device))
-            self._engine_key = key
-        return self._engine
 
     def forward(self, x):
         """x [B, T, feat_dim] -> [B, embedding_size] (float32, same device)."""
-        assert not self.training, "b200spk.CAMPPlus is an inference engine: call .eval()"
-        assert x.dim() == 3 and x.shape[2] == self.feat_dim
-        if not x.is_cuda:
-            raise RuntimeError("b200spk.CAMPPlus needs CUDA tensors (no CPU fallback); move the model and "
-                               "features to a B200 device")
-        x = x.to(torch.float32).contiguous()
-        eng = self._get_engine(x.device)
-        return eng.run(x, self.chunk)
+        return self._run(x, self.feat_dim, self.embedding_size)
 
 
-class _Engine:
-    def __init__(self, module, model):
-        self.m = module
-        self.model = model
-        self.sd = {k: v.detach().float().cpu() for k, v in module.state_dict().items()}
-        self._pcache = {}
-        self._compiled = set()
-
-    def close(self):
-        self.model.close()
-
-    # parameters are uploaded once and shared by every per-T program
-    def _p(self, key, fn):
-        if key not in self._pcache:
-            self._pcache[key] = self.model.param(fn())
-        return self._pcache[key]
-
-    def _bn(self, prefix, affine=True):
-        s = self._p(("bn_s", prefix), lambda: fold_bn(self.sd, prefix, affine)[0])
-        b = self._p(("bn_b", prefix), lambda: fold_bn(self.sd, prefix, affine)[1])
-        return s, b
-
-    def _w2d(self, key):
-        return self._p(("w", key), lambda: pack_conv2d(self.sd[key]))
-
-    def _w1d(self, key):
-        return self._p(("w", key), lambda: pack_conv1d(self.sd[key]))
-
-    def _raw(self, key):
-        return self._p(("raw", key), lambda: self.sd[key].reshape(-1))
-
+class _Engine(EngineBase):
     def default_chunks(self, T):
         """(coarse, fine) sub-batch sizes.  Measured on B200 (bench.py sweeps): launch
         count and pipeline fill matter more than L2 residency of the 2-D front, so both are large;
@@ -290,13 +222,6 @@ class _Engine:
         prog.op(_lib.OP_CONV, in_buf=stats, in_ld=2 * ch, out_buf=1, out_ld=E, H=1, W=1, Cin=2 * ch, Ho=1, Wo=1,
                 Cout=E, w=self._w1d("xvector.dense.linear.weight"), epi_scale=es, epi_shift=eb)
         self.model.set_program(T, prog)
-        self._compiled.add(T)
 
-    def run(self, feats, chunk=None):
-        T = feats.shape[1]
-        if T not in self._compiled:
-            self.compile(T)
-        coarse, fine = self.default_chunks(T)
-        if chunk:
-            coarse, fine = (chunk if isinstance(chunk, (tuple, list)) else (chunk, min(fine, chunk)))
-        return self.model.forward(T, feats, self.m.embedding_size, coarse, fine)
+
+CAMPPlus.engine_cls = _Engine

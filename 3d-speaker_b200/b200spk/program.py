@@ -134,3 +134,101 @@ class Program:
 
 def conv_out(n, k, s, p, d=1):
     return (n + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+class EngineBase:
+    """Shared host-side plumbing of a compiled network: parameter cache (uploaded once, shared by
+    every per-T program) and lazy per-T compilation."""
+
+    def __init__(self, module, model):
+        self.m = module
+        self.model = model
+        self.sd = {k: v.detach().float().cpu() for k, v in module.state_dict().items()}
+        self._pcache = {}
+        self._compiled = set()
+
+    def close(self):
+        self.model.close()
+
+    def _p(self, key, fn):
+        if key not in self._pcache:
+            self._pcache[key] = self.model.param(fn())
+        return self._pcache[key]
+
+    def _bn(self, prefix, affine=True):
+        s = self._p(("bn_s", prefix), lambda: fold_bn(self.sd, prefix, affine)[0])
+        b = self._p(("bn_b", prefix), lambda: fold_bn(self.sd, prefix, affine)[1])
+        return s, b
+
+    def _w2d(self, key):
+        return self._p(("w", key), lambda: pack_conv2d(self.sd[key]))
+
+    def _w1d(self, key):
+        return self._p(("w", key), lambda: pack_conv1d(self.sd[key]))
+
+    def _raw(self, key):
+        return self._p(("raw", key), lambda: self.sd[key].reshape(-1))
+
+    def default_chunks(self, T):
+        raise NotImplementedError
+
+    def compile(self, T):
+        raise NotImplementedError
+
+    def run(self, feats, emb_dim, chunk=None):
+        T = feats.shape[1]
+        if T not in self._compiled:
+            self.compile(T)
+            self._compiled.add(T)
+        coarse, fine = self.default_chunks(T)
+        if chunk:
+            coarse, fine = (chunk if isinstance(chunk, (tuple, list)) else (chunk, min(fine, chunk)))
+        return self.model.forward(T, feats, emb_dim, coarse, fine)
+
+
+class EngineModule(torch.nn.Module):
+    """nn.Module side of a drop-in model: holds the reference-layout parameters, owns the compiled
+    engine and invalidates it when weights or device change."""
+    engine_cls = None
+
+    def _init_engine(self, precision, chunk):
+        self.precision = precision
+        self.chunk = chunk
+        self._engine = None
+        self._engine_key = None
+
+    def invalidate(self):
+        """Drop the compiled engine (call after editing weights in place; load_state_dict and
+        .to()/.cuda() do it automatically)."""
+        if getattr(self, "_engine", None) is not None:
+            self._engine.close()
+        self._engine = None
+        self._engine_key = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
+
+    def _get_engine(self, device):
+        key = (str(device), self.precision)
+        if self._engine is None or self._engine_key != key:
+            self.invalidate()
+            prec = _lib.PREC_BF16 if self.precision in ("bf16", "bfloat16") else _lib.PREC_F32
+            self._engine = self.engine_cls(self, Model(prec, device))
+            self._engine_key = key
+        return self._engine
+
+    def _run(self, x, feat_dim, emb_dim):
+        assert not self.training, "b200spk models are inference engines: call .eval()"
+        assert x.dim() == 3 and x.shape[2] == feat_dim
+        if not x.is_cuda:
+            raise RuntimeError("b200spk models need CUDA tensors (no CPU fallback); move the model and "
+                               "features to a B200 device")
+        x = x.to(torch.float32).contiguous()
+        return self._get_engine(x.device).run(x, emb_dim, self.chunk)

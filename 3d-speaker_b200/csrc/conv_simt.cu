@@ -337,13 +337,13 @@ stats_pool_kernel(const StatsPoolArgs a) {
 }
 
 // ------------------------------------------------------------------ AFF blend
-template <typename T>
+template <typename T, typename TO>
 __global__ void __launch_bounds__(256)
 aff_blend_kernel(const AffBlendArgs a) {
     const int cg = a.C / 4;
     const long long total = a.M * cg;
     const T *x = static_cast<const T *>(a.x), *y = static_cast<const T *>(a.y), *z = static_cast<const T *>(a.z);
-    T *o = static_cast<T *>(a.out);
+    TO *o = static_cast<TO *>(a.out);
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(idx % cg) * 4;
@@ -351,13 +351,18 @@ aff_blend_kernel(const AffBlendArgs a) {
         float xv[4], yv[4], zv[4], ov[4];
         Vec4<T>::load(x + m * a.x_ld + a.x_choff + c, xv);
         Vec4<T>::load(y + m * a.y_ld + a.y_choff + c, yv);
-        Vec4<T>::load(z + m * a.z_ld + a.z_choff + c, zv);
+        if (z != nullptr) {
+            Vec4<T>::load(z + m * a.z_ld + a.z_choff + c, zv);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float gq = 1.f + tanhf(zv[i]);
-            ov[i] = xv[i] * gq + yv[i] * (2.f - gq);
+            for (int i = 0; i < 4; ++i) {
+                const float gq = 1.f + tanhf(zv[i]);
+                ov[i] = xv[i] * gq + yv[i] * (2.f - gq);
+            }
+        } else {                                   // plain sum (Res2Net hierarchical add, ERes2NetV2.py:75)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ov[i] = xv[i] + yv[i];
         }
-        Vec4<T>::store(o + m * a.out_ld + a.out_choff + c, ov);
+        Vec4<TO>::store(o + m * a.out_ld + a.out_choff + c, ov);
     }
 }
 
@@ -469,15 +474,21 @@ int launch_stats_pool(const StatsPoolArgs &a, int in_dtype, cudaStream_t s) {
     return check_launch("stats_pool_kernel");
 }
 
-int launch_aff_blend(const AffBlendArgs &a, int dtype, cudaStream_t s) {
+int launch_aff_blend(const AffBlendArgs &a, int dtype, int out_dtype, cudaStream_t s) {
     if (a.C % 4 != 0) {
         set_error("aff_blend: C must be a multiple of 4");
         return SPK_ERR_UNSUPPORTED;
     }
     const long long work = a.M * (a.C / 4);
     if (work == 0) return SPK_OK;
-    if (dtype == SPK_DT_F32) aff_blend_kernel<float><<<grid_for(work, 256), 256, 0, s>>>(a);
-    else aff_blend_kernel<bf16><<<grid_for(work, 256), 256, 0, s>>>(a);
+    const int g = grid_for(work, 256);
+    if (dtype == SPK_DT_F32 && out_dtype == SPK_DT_F32) aff_blend_kernel<float, float><<<g, 256, 0, s>>>(a);
+    else if (dtype == SPK_DT_BF16 && out_dtype == SPK_DT_BF16) aff_blend_kernel<bf16, bf16><<<g, 256, 0, s>>>(a);
+    else if (dtype == SPK_DT_BF16 && out_dtype == SPK_DT_F32) aff_blend_kernel<bf16, float><<<g, 256, 0, s>>>(a);
+    else {
+        set_error("aff_blend: unsupported dtype combination");
+        return SPK_ERR_UNSUPPORTED;
+    }
     return check_launch("aff_blend_kernel");
 }
 

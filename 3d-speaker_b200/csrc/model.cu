@@ -307,7 +307,7 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                     a.M = (long long)n * o.H * o.W; a.C = o.Cin;
                     a.x_ld = o.in_ld; a.x_choff = o.in_choff; a.y_ld = o.res_ld; a.y_choff = o.res_choff;
                     a.z_ld = o.iaux[0]; a.z_choff = o.iaux[1]; a.out_ld = o.out_ld; a.out_choff = o.out_choff;
-                    rc = launch_aff_blend(a, dt(o.in_buf), s);
+                    rc = launch_aff_blend(a, dt(o.in_buf), dt(o.out_buf), s);
                     break;
                 }
                 default:

@@ -65,7 +65,7 @@ struct AffBlendArgs {
     long long M;
     int C, x_ld, x_choff, y_ld, y_choff, z_ld, z_choff, out_ld, out_choff;
 };
-int launch_aff_blend(const AffBlendArgs &a, int dtype, cudaStream_t s);
+int launch_aff_blend(const AffBlendArgs &a, int dtype, int out_dtype, cudaStream_t s);
 
 int launch_f32_to_bf16(const float *src, __nv_bfloat16 *dst, long long n, cudaStream_t s);
 int launch_widen(const void *src, int dtype, float *dst, long long n, cudaStream_t s);

@@ -34,6 +34,11 @@ def import_reference():
     return FBank, CAMPPlus, SpectralCluster
 
 
+def import_eres2netv2():
+    from speakerlab.models.eres2net.ERes2NetV2 import ERes2NetV2
+    return ERes2NetV2
+
+
 def versions():
     import scipy, sklearn, torch, torchaudio
     return json.dumps(dict(numpy=np.__version__, torch=torch.__version__, torchaudio=torchaudio.__version__,
@@ -73,6 +78,15 @@ def campplus_input(batch, n_samples, seed):
     wav, _ = synth.fm_meeting(secs * (batch + 1), 3, seed=seed)
     ch = [[i * secs * 0.5, i * secs * 0.5 + secs] for i in range(batch)]
     return synth.cut_windows(wav, ch)
+
+
+def eres2netv2_cases():
+    """(name, ctor kwargs, batch, n_samples, weight seed)"""
+    return [
+        ("w26s2e2_t148", dict(baseWidth=26, scale=2, expansion=2), 2, 24000, 201),
+        ("w24s4e4_t148", dict(baseWidth=24, scale=4, expansion=4), 2, 24000, 202),
+        ("w26s2e2_t298", dict(baseWidth=26, scale=2, expansion=2), 1, 48000, 203),
+    ]
 
 
 def cluster_cases():
@@ -150,6 +164,27 @@ def main():
     with open(os.path.join(OUT, "state_dict_layouts.json"), "w") as f:
         json.dump(layouts, f)
     print("campplus goldens:", [k for k in out if k.endswith(".emb")])
+
+    # ---- ERes2NetV2
+    ERes2NetV2 = import_eres2netv2()
+    out = {"versions": ver}
+    for name, kw, batch, n_samples, wseed in eres2netv2_cases():
+        torch.manual_seed(0)
+        model = ERes2NetV2(feat_dim=80, embedding_size=192, **kw).eval()
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        layouts["eres2netv2_w%ds%de%d" % (kw["baseWidth"], kw["scale"], kw["expansion"])] = {k: list(v) for k, v in shapes.items()}
+        sd = synth.fill_state_dict(shapes, wseed, randomize_bn=True)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        wavs = campplus_input(batch, n_samples, seed=wseed + 1000)
+        feats = torch.vmap(fb)(torch.from_numpy(wavs).unsqueeze(1))
+        with torch.no_grad():
+            e = model(feats.clone())
+        out[name + ".feats"] = feats.numpy()
+        out[name + ".emb"] = e.numpy()
+    np.savez_compressed(os.path.join(OUT, "eres2netv2.npz"), **out)
+    with open(os.path.join(OUT, "state_dict_layouts.json"), "w") as f:
+        json.dump(layouts, f)
+    print("eres2netv2 goldens:", [k for k in out if k.endswith(".emb")])
 
     # ---- SpectralCluster
     out = {"versions": ver}

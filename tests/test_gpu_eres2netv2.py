@@ -1,0 +1,69 @@
+"""GPU: ERes2NetV2 forward through the C ABI vs the oracle and the golden vectors."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import b200spk
+from oracle import eres2netv2_oracle, gen_golden, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "eres2netv2.npz"))
+
+
+def _model(kw, wseed, precision="fp32", chunk=None):
+    m = b200spk.ERes2NetV2(precision=precision, chunk=chunk, **kw)
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = synth.fill_state_dict(shapes, wseed, randomize_bn=True)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return m.cuda().eval(), sd
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def _cos_min(a, b):
+    return float(((a * b).sum(1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1))).min())
+
+
+@pytest.mark.parametrize("case", gen_golden.eres2netv2_cases(), ids=lambda c: c[0])
+def test_fp32_vs_golden(gold, case):
+    name, kw, batch, n_samples, wseed = case
+    model, _ = _model(kw, wseed)
+    feats = torch.from_numpy(gold[name + ".feats"]).cuda()
+    keep = feats.clone()
+    with torch.no_grad():
+        got = model(feats).cpu().numpy()
+    assert torch.equal(feats, keep)                 # the caller's tensor is left alone
+    ref = gold[name + ".emb"]
+    assert got.shape == ref.shape
+    assert _rel(got, ref) <= 1e-4, _rel(got, ref)
+    assert _cos_min(got, ref) >= 0.9999
+
+
+@pytest.mark.parametrize("case", gen_golden.eres2netv2_cases()[:2], ids=lambda c: c[0])
+def test_bf16_vs_oracle(case):
+    name, kw, batch, n_samples, wseed = case
+    wavs = gen_golden.campplus_input(6, n_samples, seed=77)
+    feats = b200spk.fbank_batch(torch.from_numpy(wavs).cuda())
+    model, sd = _model(kw, wseed, precision="bf16")
+    ref = eres2netv2_oracle.forward(sd, feats.cpu().numpy(), scale=kw["scale"]).numpy()
+    with torch.no_grad():
+        got = model(feats).cpu().numpy()
+    assert _cos_min(got, ref) >= 0.999, _cos_min(got, ref)
+
+
+def test_chunking_is_invisible():
+    name, kw, batch, n_samples, wseed = gen_golden.eres2netv2_cases()[0]
+    feats = b200spk.fbank_batch(torch.from_numpy(gen_golden.campplus_input(5, n_samples, seed=8)).cuda())
+    a, _ = _model(kw, wseed, chunk=2)
+    b, _ = _model(kw, wseed, chunk=8)
+    with torch.no_grad():
+        assert torch.equal(a(feats), b(feats))

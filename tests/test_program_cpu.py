@@ -1,0 +1,93 @@
+"""CPU: the host-side compilers (state_dict -> fused-op list) run against a recording mock of the
+device model, and every op is checked for internal consistency (weight sizes, buffer extents,
+channel windows, alignment rules of the kernels)."""
+import numpy as np
+import pytest
+import torch
+
+import b200spk
+from b200spk import _lib, campplus, eres2netv2
+from b200spk.program import conv_out
+
+
+class MockModel:
+    def __init__(self, precision):
+        self.precision = precision
+        self.act_dtype = _lib.DT_BF16 if precision == _lib.PREC_BF16 else _lib.DT_F32
+        self.params = []
+        self.programs = {}
+
+    def param(self, t):
+        self.params.append(tuple(t.shape) if hasattr(t, "shape") else None)
+        self.sizes = getattr(self, "sizes", [])
+        self.sizes.append(int(t.numel()))
+        return len(self.params) - 1
+
+    def set_program(self, T, prog):
+        self.programs[T] = prog
+
+    def close(self):
+        pass
+
+
+def _check_program(model, prog, T, F=80):
+    bufs = prog.bufs
+    written = {0}
+    for i, op in enumerate(prog.ops):
+        def extent(buf, ld, choff, C, H, W):
+            assert 0 <= buf < len(bufs), (i, buf)
+            assert choff + C <= ld, (i, "channel window exceeds the pixel pitch", choff, C, ld)
+            assert H * W * ld <= bufs[buf].elems, (i, "buffer too small", buf, H, W, ld, bufs[buf].elems)
+        if op.kind == _lib.OP_CONV:
+            assert model.sizes[op.w] == op.Cout * op.KH * op.KW * op.Cin, (i, "weight size")
+            assert op.Ho == conv_out(op.H, op.KH, op.sh, op.ph, op.dh) and op.Wo == conv_out(op.W, op.KW, op.sw, op.pw, op.dw), i
+            extent(op.in_buf, op.in_ld, op.in_choff, op.Cin, op.H, op.W)
+            extent(op.out_buf, op.out_ld, op.out_choff, op.Cout, op.Ho, op.Wo)
+            assert op.Cin % 16 == 0 and op.in_ld % 8 == 0 and op.in_choff % 8 == 0, (i, "input alignment")
+            assert op.out_ld % 8 == 0 and op.out_choff % 8 == 0, (i, "output alignment")
+            if op.res_buf >= 0:
+                extent(op.res_buf, op.res_ld, op.res_choff, op.Cout, op.Ho, op.Wo)
+                assert op.res_buf in written, (i, "residual read before written")
+            for pid, n in ((op.pro_scale, op.Cin), (op.pro_shift, op.Cin), (op.epi_scale, op.Cout), (op.epi_shift, op.Cout)):
+                if pid >= 0:
+                    assert model.sizes[pid] == n, (i, "affine vector length", model.sizes[pid], n)
+            assert not (op.in_buf == op.out_buf and not (op.out_choff >= op.in_choff + op.Cin or op.out_choff + op.Cout <= op.in_choff)), \
+                (i, "conv writes the channels it reads")
+        elif op.kind == _lib.OP_STEM:
+            assert model.sizes[op.w] == op.Cout * 9
+            extent(op.out_buf, op.out_ld, op.out_choff, op.Cout, op.H, op.W)
+        elif op.kind == _lib.OP_AFF_BLEND:
+            extent(op.in_buf, op.in_ld, op.in_choff, op.Cin, op.H, op.W)
+            extent(op.res_buf, op.res_ld, op.res_choff, op.Cin, op.H, op.W)
+            extent(op.out_buf, op.out_ld, op.out_choff, op.Cin, op.H, op.W)
+            if op.gate_buf >= 0:
+                extent(op.gate_buf, op.iaux[0], op.iaux[1], op.Cin, op.H, op.W)
+        elif op.kind == _lib.OP_CAM_GATE:
+            extent(op.in_buf, op.in_ld, op.in_choff, op.Cin, 1, op.W)
+        elif op.kind == _lib.OP_STATS_POOL:
+            extent(op.in_buf, op.in_ld, op.in_choff, op.Cin, op.H, op.W)
+            assert bufs[op.out_buf].elems >= 2 * op.H * op.Cin
+        assert op.in_buf in written, (i, "input read before written", op.in_buf)
+        written.add(op.out_buf)
+    assert 1 in written            # the embedding buffer is produced
+
+
+@pytest.mark.parametrize("prec", [_lib.PREC_F32, _lib.PREC_BF16])
+@pytest.mark.parametrize("T", [148, 298, 61])
+def test_campplus_program(prec, T):
+    mod = b200spk.CAMPPlus(embedding_size=192)
+    eng = campplus._Engine(mod, MockModel(prec))
+    eng.compile(T)
+    prog = eng.model.programs[T]
+    _check_program(eng.model, prog, T)
+    assert sum(1 for o in prog.ops if o.kind == _lib.OP_CONV) == 11 + 1 + 52 * 2 + 3 + 1     # FCM (8 + 2 shortcuts + conv2), tdnn, 52 x (bottleneck, local), 3 transit, dense
+
+
+@pytest.mark.parametrize("prec", [_lib.PREC_F32, _lib.PREC_BF16])
+@pytest.mark.parametrize("kw", [dict(), dict(baseWidth=24, scale=4, expansion=4)], ids=["w26s2e2", "w24s4e4"])
+@pytest.mark.parametrize("T", [148, 298])
+def test_eres2netv2_program(prec, kw, T):
+    mod = b200spk.ERes2NetV2(**kw)
+    eng = eres2netv2._Engine(mod, MockModel(prec))
+    eng.compile(T)
+    _check_program(eng.model, eng.model.programs[T], T)

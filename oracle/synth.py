@@ -133,10 +133,11 @@ def _key_rng(seed, key):
     return np.random.default_rng([seed, zlib.crc32(key.encode())])
 
 
-def fill_state_dict(shapes, seed, randomize_bn=True):
+def fill_state_dict(shapes, seed, randomize_bn=True, gain=2.0 ** 0.5):
     """Deterministic weights for a {name: shape} table (a model's state_dict layout).
 
-    conv/linear weights ~ N(0, 2/fan_in) (He), biases ~ N(0, 0.05); with
+    conv/linear weights ~ N(0, gain^2/fan_in) (He for the default gain sqrt(2); deep residual nets
+    need a smaller gain to stay out of the chaotic regime), biases ~ N(0, 0.05); with
     ``randomize_bn`` every BatchNorm gets running_mean~N(0,0.1), running_var~U(0.5,1.5),
     weight~U(0.5,1.5), bias~N(0,0.1) so BN folding is exercised (SURVEY.md section 8d
     config 1); otherwise fresh-BN values (mean 0, var 1, weight 1, bias 0).
@@ -164,7 +165,7 @@ def fill_state_dict(shapes, seed, randomize_bn=True):
             out[key] = (0.05 * rng.standard_normal(shape)).astype(np.float32)
         else:  # conv / linear weight
             fan_in = int(np.prod(shape[1:])) if len(shape) > 1 else shape[0]
-            out[key] = (np.sqrt(2.0 / fan_in) * rng.standard_normal(shape)).astype(np.float32)
+            out[key] = (gain / np.sqrt(fan_in) * rng.standard_normal(shape)).astype(np.float32)
     return out
 
 

@@ -20,7 +20,7 @@ def gold(golden_dir):
 def _model(kw, wseed, precision="fp32", chunk=None):
     m = b200spk.ERes2NetV2(precision=precision, chunk=chunk, **kw)
     shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
-    sd = synth.fill_state_dict(shapes, wseed, randomize_bn=True)
+    sd = synth.fill_state_dict(shapes, wseed, randomize_bn=True, gain=gen_golden.ERES_GAIN)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
     return m.cuda().eval(), sd
 

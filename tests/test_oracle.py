@@ -134,3 +134,15 @@ def test_circle_pad():
     x = np.arange(5)
     assert synth.circle_pad(x, 12).tolist() == [0, 1, 2, 3, 4, 0, 1, 2, 3, 4, 0, 1]
     assert synth.circle_pad(x, 3) is x
+
+
+@pytest.mark.parametrize("case", gen_golden.eres2netv2_cases(), ids=lambda c: c[0])
+def test_eres2netv2_oracle_matches_reference(golden_dir, layouts, case):
+    from oracle import eres2netv2_oracle
+    gold = np.load(os.path.join(golden_dir, "eres2netv2.npz"))
+    name, kw, batch, n_samples, wseed = case
+    key = "eres2netv2_w%ds%de%d" % (kw["baseWidth"], kw["scale"], kw["expansion"])
+    sd = synth.fill_state_dict(layouts[key], wseed, randomize_bn=True, gain=gen_golden.ERES_GAIN)
+    got = eres2netv2_oracle.forward(sd, gold[name + ".feats"], scale=kw["scale"]).numpy()
+    ref = gold[name + ".emb"]
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-5

@@ -62,23 +62,55 @@ def make_windows(n, seed):
 
 
 class ClockSampler:
-    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock + throttle-reason sampler running DURING the timed region (B200_PROFILING.md clocks
+    line).  NVML in-process (pynvml) every 20 ms; falls back to polling nvidia-smi."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.sm, self.max_sm, self.reasons = index, [], None, set()
+        self._stop, self._t, self.src = threading.Event(), None, "nvml"
 
-    def _run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        # map the torch device index to NVML through the UUID (CUDA_VISIBLE_DEVICES may remap)
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        while not self._stop.is_set():
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for name, bit in bits.items():
+                if r & bit:
+                    self.reasons.add(name)
+            self._stop.wait(0.02)
+
+    def _run_smi(self):
+        self.src = "nvidia-smi"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
                 if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+                    c = [x.strip() for x in out.stdout.strip().split(",")]
+                    self.sm.append(float(c[0]))
+                    self.max_sm = float(c[1])
+                    self.reasons.update(n for i, n in enumerate(names) if c[2 + i].lower().startswith("active"))
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.1)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -90,13 +122,11 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(r[0]) for r in self.rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": [], "samples": 0, "source": self.src}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": self.src}
 
 
 # ----------------------------------------------------------------------------- CPU oracle leg

@@ -11,8 +11,8 @@ Op mapping (reference file:line -> fused op):
   head conv2+bn2+relu, reshape       DTDNN.py:44-48        CONV; reshape is free (tdnn reads [10,T,32] as K=(f,k,c))
   TDNNLayer k5 s2 +bn+relu           layers.py:40-67       CONV KH=10,KW=5 writing channels [0,128) of block1's buffer
   CAMDenseTDNNLayer.bn_function      layers.py:140-141     CONV 1x1, BN-ReLU prologue on the growing concat, BN-ReLU epilogue
-  CAMLayer context + gate            layers.py:95-98       CAM_GATE (evaluated once per distinct 100-frame window)
-  CAMLayer.linear_local * gate, cat  layers.py:94,99,179   CONV k3 (dilated) with gate epilogue, written in place into the concat
+  CAMLayer (context gate, local     layers.py:93-99,179   CAM_LOCAL: gate evaluated once per distinct 100-frame window,
+  conv, gating) + torch.cat                                dilated k3 conv x gate written in place into the concat buffer
   TransitLayer                       layers.py:193-196     CONV 1x1 with BN-ReLU prologue (transit3 also folds out_nonlinear)
   StatsPool                          layers.py:26-37       STATS_POOL (unbiased std)
   DenseLayer + BatchNorm1d(affine=F) layers.py:209-215     CONV 1x1 on [1024] with folded BN epilogue
@@ -197,13 +197,14 @@ class _Engine(EngineBase):
                         Cout=BNC, w=self._w1d(p + ".linear1.weight"), pro_scale=ps, pro_shift=pb, pro_relu=1,
                         epi_scale=es, epi_shift=eb, act=_lib.ACT_RELU)
                 c = p + ".cam_layer"
-                prog.op(_lib.OP_CAM_GATE, in_buf=hbuf, in_ld=BNC, out_buf=gbuf, W=T2, Cin=BNC, Cout=G,
+                # whole CAMLayer as one op: context gate + dilated local conv + gating, written in place
+                # into the block's concat buffer (fused kernel in bf16 mode, gate + gated conv otherwise)
+                prog.op(_lib.OP_CAM_LOCAL, in_buf=hbuf, in_ld=BNC, out_buf=xb, out_ld=ld, out_choff=cin, H=1, W=T2,
+                        Cin=BNC, Ho=1, Wo=T2, Cout=G, KH=1, KW=k, pw=dil * (k - 1) // 2, dw=dil,
+                        w=self._w1d(c + ".linear_local.weight"), gate_buf=gbuf, gate_win=SEG_LEN,
                         aux=[self._raw(c + ".linear1.weight"), self._raw(c + ".linear1.bias"),
                              self._raw(c + ".linear2.weight"), self._raw(c + ".linear2.bias")],
                         iaux=[BNC // 2, SEG_LEN])
-                prog.op(_lib.OP_CONV, in_buf=hbuf, in_ld=BNC, out_buf=xb, out_ld=ld, out_choff=cin, H=1, W=T2,
-                        Cin=BNC, Ho=1, Wo=T2, Cout=G, KH=1, KW=k, pw=dil * (k - 1) // 2, dw=dil,
-                        w=self._w1d(c + ".linear_local.weight"), gate_buf=gbuf, gate_win=SEG_LEN)
             ch = ch + n_layers * G
             p = "xvector.transit%d" % (bi + 1)
             ps, pb = self._bn(p + ".nonlinear.batchnorm")

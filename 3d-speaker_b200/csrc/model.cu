@@ -100,6 +100,11 @@ int validate(const spk_model *m, const spk_program &p) {
                 for (int j = 0; j < 4; ++j) ok = ok && par_ok(o.aux[j], false);
                 ok = ok && o.iaux[0] > 0 && o.iaux[1] > 0;
                 break;
+            case SPK_OP_CAM_LOCAL:
+                for (int j = 0; j < 4; ++j) ok = ok && par_ok(o.aux[j], false);
+                ok = ok && par_ok(o.w, false) && o.iaux[0] > 0 && o.iaux[1] > 0 && o.gate_buf >= 0 && o.KH == 1 && o.H == 1;
+                if (ok && m->param_n[o.w] != (int64_t)o.Cout * o.KW * o.Cin) ok = false;
+                break;
             case SPK_OP_STATS_POOL:
             case SPK_OP_AFF_BLEND:
                 break;
@@ -236,7 +241,8 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                     rc = launch_stem(a, dt(o.out_buf), s);
                     break;
                 }
-                case SPK_OP_CONV: {
+                case SPK_OP_CONV:
+                case SPK_OP_CAM_LOCAL: {
                     ConvArgs a{};
                     a.x = ptr(o.in_buf); a.y = ptr(o.out_buf); a.res = ptr(o.res_buf);
                     a.gate = static_cast<const float *>(ptr(o.gate_buf));
@@ -252,6 +258,34 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                     a.pro_relu = o.pro_relu; a.act = o.act;
                     a.K = o.KH * o.KW * o.Cin;
                     a.M = (long long)n * o.Ho * o.Wo;
+                    if (o.kind == SPK_OP_CAM_LOCAL) {
+                        const int hidden = o.iaux[0], seg_len = o.iaux[1];
+                        a.gate_win = seg_len;
+                        a.gate_nwin = (o.Wo + seg_len - 1) / seg_len;
+                        ConvArgs f = a;
+                        f.gate = nullptr;
+                        if (m->precision == SPK_PREC_BF16 &&
+                            cam_local_supported(f, dt(o.in_buf), dt(o.out_buf), hidden, seg_len)) {
+                            const __nv_bfloat16 *wb = nullptr;
+                            rc = param_bf16(m, o.w, &wb, s);
+                            if (rc == SPK_OK) {
+                                f.w = wb;
+                                rc = launch_cam_local(f, param(m, o.aux[0]), param(m, o.aux[1]), param(m, o.aux[2]),
+                                                      param(m, o.aux[3]), hidden, seg_len, s);
+                            }
+                            break;
+                        }
+                        // unfused: context gate into the scratch buffer, then the gated conv below
+                        CamGateArgs cg{};
+                        cg.x = ptr(o.in_buf);
+                        cg.gate = static_cast<float *>(ptr(o.gate_buf));
+                        cg.w1 = param(m, o.aux[0]); cg.b1 = param(m, o.aux[1]);
+                        cg.w2 = param(m, o.aux[2]); cg.b2 = param(m, o.aux[3]);
+                        cg.B = n; cg.T = o.W; cg.C = o.Cin; cg.in_ld = o.in_ld; cg.in_choff = o.in_choff;
+                        cg.hidden = hidden; cg.seg_len = seg_len; cg.Cout = o.Cout; cg.nwin = a.gate_nwin;
+                        rc = launch_cam_gate(cg, dt(o.in_buf), s);
+                        if (rc != SPK_OK) break;
+                    }
                     if (m->precision == SPK_PREC_BF16 &&
                         conv_slab_supported(a, dt(o.in_buf), dt(o.out_buf), dt(o.res_buf))) {
                         const __nv_bfloat16 *wb = nullptr;

@@ -34,6 +34,11 @@ int launch_conv_gemm(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream
 bool conv_slab_supported(const ConvArgs &a, int in_dtype, int out_dtype, int res_dtype);
 int launch_conv_slab(const ConvArgs &a, cudaStream_t s);
 
+// fused CAM layer (cam_local.cu): dilated k=3 conv (128->32) + context gate + gating multiply
+bool cam_local_supported(const ConvArgs &a, int in_dtype, int out_dtype, int hidden, int seg_len);
+int launch_cam_local(const ConvArgs &a, const float *w1, const float *b1, const float *w2, const float *b2, int hidden,
+                     int seg_len, cudaStream_t s);
+
 struct StemArgs {
     const float *feats;   // [B,T,F]
     const float *w;       // [Cout][3][3]  (kh over F, kw over T)

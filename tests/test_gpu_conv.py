@@ -206,3 +206,52 @@ def test_conv_many_tiles_persistent_loop():
     w = torch.randn(128, 1, 1, 256, generator=g) / 16
     y, ref = run_conv(x, w, precision="bf16")
     _check(y, ref, 2e-5)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("W,B,dil", [(74, 7, 2), (74, 3, 1), (149, 5, 2), (230, 2, 2), (61, 9, 2)])
+def test_cam_local_fused_op(precision, W, B, dil):
+    """The whole CAMLayer as one op (fused tcgen05 kernel in bf16 mode, gate + gated conv in fp32):
+    ragged last item (B not a multiple of the segments per CTA), 1-3 context windows, both dilations."""
+    g = torch.Generator().manual_seed(W * 10 + B)
+    C, G, hidden, seg = 128, 32, 64, 100
+    bf = precision == "bf16"
+    AD = _lib.DT_BF16 if bf else _lib.DT_F32
+    x = torch.randn(B, 1, W, C, generator=g)
+    w = torch.randn(G, 1, 3, C, generator=g) / math.sqrt(3 * C)
+    w1, b1 = torch.randn(hidden, C, generator=g) / math.sqrt(C), 0.1 * torch.randn(hidden, generator=g)
+    w2, b2 = torch.randn(G, hidden, generator=g) / 8, 0.1 * torch.randn(G, generator=g)
+    model = Model(_lib.PREC_BF16 if bf else _lib.PREC_F32, "cuda:0")
+    nwin = math.ceil(W / seg)
+    prog = Program(W * C, W * G)
+    xin = prog.buf("x", W * C, AD)
+    ybuf = prog.buf("y", W * G, AD)
+    gbuf = prog.buf("gate", nwin * G, _lib.DT_F32)
+    prog.op(_lib.OP_CONV, in_buf=0, in_ld=C, out_buf=xin, out_ld=C, H=1, W=W, Cin=C, Ho=1, Wo=W, Cout=C,
+            w=model.param(torch.eye(C).reshape(C, 1, 1, C)))
+    prog.op(_lib.OP_CAM_LOCAL, in_buf=xin, in_ld=C, out_buf=ybuf, out_ld=G, H=1, W=W, Cin=C, Ho=1, Wo=W, Cout=G, KH=1, KW=3,
+            pw=dil, dw=dil, w=model.param(w), gate_buf=gbuf, gate_win=seg,
+            aux=[model.param(w1), model.param(b1), model.param(w2), model.param(b2)], iaux=[hidden, seg])
+    prog.op(_lib.OP_CONV, in_buf=ybuf, in_ld=G, out_buf=1, out_ld=G, H=1, W=W, Cin=G, Ho=1, Wo=W, Cout=G,
+            w=model.param(torch.eye(G).reshape(G, 1, 1, G)))
+    model.set_program(1, prog)
+    out = model.forward(1, x.reshape(B, -1).cuda().contiguous(), W * G, B)
+    torch.cuda.synchronize()
+    y = out.cpu().view(B, 1, W, G).double()
+    model.close()
+    xr = _bf16_round(x) if bf else x
+    wr = _bf16_round(w) if bf else w
+    ref = F.conv2d(xr.permute(0, 3, 1, 2).double(), wr.permute(0, 3, 1, 2).double(), padding=(0, dil), dilation=(1, dil)).permute(0, 2, 3, 1)
+    xs = xr.double()
+    tot = xs.mean(dim=2, keepdim=True)
+    gate = torch.zeros(B, 1, W, G, dtype=torch.float64)
+    for wi in range(nwin):
+        a0, a1 = wi * seg, min(W, (wi + 1) * seg)
+        ctx = (tot + xs[:, :, a0:a1].mean(dim=2, keepdim=True)).squeeze(2).squeeze(1)
+        h = torch.relu(ctx @ w1.double().t() + b1.double())
+        gate[:, :, a0:a1, :] = torch.sigmoid(h @ w2.double().t() + b2.double())[:, None, None, :]
+    ref = ref * gate
+    y.bf16_stored = bf
+    if bf:
+        ref = _bf16_round(ref.float()).double()
+    _check(y, ref, 1e-4)

@@ -38,7 +38,7 @@ def _check_program(model, prog, T, F=80):
             assert 0 <= buf < len(bufs), (i, buf)
             assert choff + C <= ld, (i, "channel window exceeds the pixel pitch", choff, C, ld)
             assert H * W * ld <= bufs[buf].elems, (i, "buffer too small", buf, H, W, ld, bufs[buf].elems)
-        if op.kind == _lib.OP_CONV:
+        if op.kind in (_lib.OP_CONV, _lib.OP_CAM_LOCAL):
             assert model.sizes[op.w] == op.Cout * op.KH * op.KW * op.Cin, (i, "weight size")
             assert op.Ho == conv_out(op.H, op.KH, op.sh, op.ph, op.dh) and op.Wo == conv_out(op.W, op.KW, op.sw, op.pw, op.dw), i
             extent(op.in_buf, op.in_ld, op.in_choff, op.Cin, op.H, op.W)
@@ -80,7 +80,8 @@ def test_campplus_program(prec, T):
     eng.compile(T)
     prog = eng.model.programs[T]
     _check_program(eng.model, prog, T)
-    assert sum(1 for o in prog.ops if o.kind == _lib.OP_CONV) == 11 + 1 + 52 * 2 + 3 + 1     # FCM (8 + 2 shortcuts + conv2), tdnn, 52 x (bottleneck, local), 3 transit, dense
+    assert sum(1 for o in prog.ops if o.kind == _lib.OP_CONV) == 11 + 1 + 52 + 3 + 1     # FCM (8 + 2 shortcuts + conv2), tdnn, 52 bottlenecks, 3 transit, dense
+    assert sum(1 for o in prog.ops if o.kind == _lib.OP_CAM_LOCAL) == 52
 
 
 @pytest.mark.parametrize("prec", [_lib.PREC_F32, _lib.PREC_BF16])

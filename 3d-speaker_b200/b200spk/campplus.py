@@ -204,7 +204,9 @@ class _Engine(EngineBase):
                         w=self._w1d(c + ".linear_local.weight"), gate_buf=gbuf, gate_win=SEG_LEN,
                         aux=[self._raw(c + ".linear1.weight"), self._raw(c + ".linear1.bias"),
                              self._raw(c + ".linear2.weight"), self._raw(c + ".linear2.bias")],
-                        iaux=[BNC // 2, SEG_LEN])
+                        iaux=[BNC // 2, SEG_LEN,
+                              self._p(("w1t", c), lambda c=c: self.sd[c + ".linear1.weight"][:, :, 0].t().contiguous()),
+                              self._p(("w2t", c), lambda c=c: self.sd[c + ".linear2.weight"][:, :, 0].t().contiguous())])
             ch = ch + n_layers * G
             p = "xvector.transit%d" % (bi + 1)
             ps, pb = self._bn(p + ".nonlinear.batchnorm")

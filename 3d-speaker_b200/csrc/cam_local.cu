@@ -127,14 +127,13 @@ struct CamGeom {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1, const float *__restrict__ b1,
-                 const float *__restrict__ w2, const float *__restrict__ b2, int n_items) {
+cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1t, const float *__restrict__ b1,
+                 const float *__restrict__ w2t, const float *__restrict__ b2, int n_items) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t s0 = smem_u32(smem);
     const uint32_t s_w = s0 + g.off_w, s_slab0 = s0 + g.off_slab, s_bar = s0 + g.off_bar;
-    float *part = reinterpret_cast<float *>(smem + g.off_part);     // [16][128]
+    float *part = reinterpret_cast<float *>(smem + g.off_part);     // [2][16][128]
     float *win = reinterpret_cast<float *>(smem + g.off_win);       // [2][G][nwin][128]   (per slab buffer)
-    float *tot = reinterpret_cast<float *>(smem + g.off_tot);       // [G][128]
     float *hid = reinterpret_cast<float *>(smem + g.off_hid);       // [G*nwin][hidden]
     float *gate = reinterpret_cast<float *>(smem + g.off_gate);     // [2][G][nwin][32]
     auto sfull = [&](int i) { return s_bar + 8u * i; };
@@ -246,81 +245,112 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
             float *winb = win + (size_t)buf * g.G * g.nwin * kCin;
             float *gateb = gate + (size_t)buf * g.G * g.nwin * kCout;
             mbar_wait(sfull(buf), ph);
-            // ---- column sums of the staged rows: thread (plane c = et & 15, row group rg = et >> 4)
+            const int combos = g_valid * g.nwin;
+            // ---- column sums of the staged rows: thread (plane c = et & 15, row group rg = et >> 4) sums its
+            // rows of one (segment, window), the 16 row groups are folded in a fixed order (deterministic).
+            // `part` is double buffered so each round needs one barrier only.
             {
                 const int c = et & 15, rg = et >> 4;
-                for (int gs = 0; gs < g_valid; ++gs)
-                    for (int w = 0; w < g.nwin; ++w) {
-                        const int t0 = w * g.seg_len, t1 = min(g.T, t0 + g.seg_len);
-                        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        for (int t = t0 + rg; t < t1; t += 16) {
-                            const uint4 v = lds16(sb + c * plane + (uint32_t)(gs * g.P + g.d + t) * 16u);
-                            const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+                for (int cb = 0; cb < combos; ++cb) {
+                    const int gs = cb / g.nwin, w = cb - gs * g.nwin;
+                    const int t0 = w * g.seg_len, t1 = min(g.T, t0 + g.seg_len);
+                    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    for (int t = t0 + rg; t < t1; t += 16) {
+                        const uint4 v = lds16(sb + c * plane + (uint32_t)(gs * g.P + g.d + t) * 16u);
+                        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                const float2 f = unpack2(vv[h]);
-                                acc[2 * h] += f.x;
-                                acc[2 * h + 1] += f.y;
-                            }
+                        for (int h = 0; h < 4; ++h) {
+                            const float2 f = unpack2(vv[h]);
+                            acc[2 * h] += f.x;
+                            acc[2 * h + 1] += f.y;
                         }
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) part[rg * kCin + c * 8 + e] = acc[e];
-                        epi_bar_sync();
-                        if (et < kCin) {
-                            float s = 0.f;
-#pragma unroll
-                            for (int r = 0; r < 16; ++r) s += part[r * kCin + et];
-                            winb[(gs * g.nwin + w) * kCin + et] = s;
-                        }
-                        epi_bar_sync();
                     }
+                    float *pp = part + (cb & 1) * 16 * kCin;
+                    *reinterpret_cast<float4 *>(&pp[rg * kCin + c * 8]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    *reinterpret_cast<float4 *>(&pp[rg * kCin + c * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                    epi_bar_sync();
+                    if (et < kCin) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) s += pp[r * kCin + et];
+                        winb[cb * kCin + et] = s;
+                    }
+                }
             }
             // the slab is no longer needed by these threads
             mbar_arrive(sempty(buf));
-            // ---- ctx = tot/T + win/len ; hidden = relu(W1 ctx + b1) ; gate = sigmoid(W2 hidden + b2)
+            // ---- ctx = tot/T + win/len, in place (thread et owns channel et of every combo: no barrier needed)
             if (et < kCin) {
                 for (int gs = 0; gs < g_valid; ++gs) {
                     float t = 0.f;
                     for (int w = 0; w < g.nwin; ++w) t += winb[(gs * g.nwin + w) * kCin + et];
-                    tot[gs * kCin + et] = t / (float)g.T;
-                }
-            }
-            epi_bar_sync();
-            if (et < kCin) {
-                for (int gs = 0; gs < g_valid; ++gs)
+                    t /= (float)g.T;
                     for (int w = 0; w < g.nwin; ++w) {
                         const int len = min(g.T, (w + 1) * g.seg_len) - w * g.seg_len;
                         float *p = &winb[(gs * g.nwin + w) * kCin + et];
-                        *p = tot[gs * kCin + et] + *p / (float)len;            // ctx in place
+                        *p = t + *p / (float)len;
                     }
-            }
-            epi_bar_sync();
-            const int combos = g_valid * g.nwin;
-            for (int j = ew; j < g.hidden; j += 8) {
-                const float4 wv = __ldg(reinterpret_cast<const float4 *>(w1 + (size_t)j * kCin + lane * 4));
-                const float bj = __ldg(b1 + j);
-                for (int cb = 0; cb < combos; ++cb) {
-                    const float4 cv = *reinterpret_cast<const float4 *>(&winb[cb * kCin + lane * 4]);
-                    float s = wv.x * cv.x + wv.y * cv.y + wv.z * cv.z + wv.w * cv.w;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == 0) hid[cb * kMaxHidden + j] = fmaxf(s + bj, 0.f);
                 }
             }
             epi_bar_sync();
-            for (int o = ew; o < kCout; o += 8) {
-                const float wa = (lane < g.hidden) ? __ldg(w2 + (size_t)o * g.hidden + lane) : 0.f;
-                const float wb = (lane + 32 < g.hidden) ? __ldg(w2 + (size_t)o * g.hidden + lane + 32) : 0.f;
-                const float bo = __ldg(b2 + o);
-                for (int cb = 0; cb < combos; ++cb) {
-                    float s = wa * ((lane < g.hidden) ? hid[cb * kMaxHidden + lane] : 0.f) +
-                              wb * ((lane + 32 < g.hidden) ? hid[cb * kMaxHidden + lane + 32] : 0.f);
+            // ---- hidden = relu(W1 ctx + b1): thread (j = et & 63, quarter qd = et >> 6) does 32 channels of
+            // every combo from the TRANSPOSED weights (coalesced rows of 64 floats); quarters folded in order
+            {
+                const int j = et & 63, qd = et >> 6;
+                float acc[kMaxSeg * kMaxWin > 8 ? 8 : kMaxSeg * kMaxWin];
+                float *hp = part;                            // [4][combos][64] aliases the (now dead) row-group partials
+                if (j < g.hidden) {
 #pragma unroll
-                    for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
-                    if (lane == 0) gateb[cb * kCout + o] = 1.f / (1.f + expf(-(s + bo)));
+                    for (int cb = 0; cb < 8; ++cb) acc[cb] = 0.f;
+                    for (int i = 0; i < 32; ++i) {
+                        const int ch = qd * 32 + i;
+                        const float wv = __ldg(w1t + (size_t)ch * g.hidden + j);
+#pragma unroll
+                        for (int cb = 0; cb < 8; ++cb)
+                            if (cb < combos) acc[cb] = fmaf(wv, winb[cb * kCin + ch], acc[cb]);
+                    }
+#pragma unroll
+                    for (int cb = 0; cb < 8; ++cb)
+                        if (cb < combos) hp[(qd * 8 + cb) * kMaxHidden + j] = acc[cb];
                 }
+                epi_bar_sync();
+                for (int idx = et; idx < combos * g.hidden; idx += kEpi) {
+                    const int cb = idx / g.hidden, jj = idx - cb * g.hidden;
+                    const float s = ((hp[(0 * 8 + cb) * kMaxHidden + jj] + hp[(1 * 8 + cb) * kMaxHidden + jj]) +
+                                     (hp[(2 * 8 + cb) * kMaxHidden + jj] + hp[(3 * 8 + cb) * kMaxHidden + jj])) + __ldg(b1 + jj);
+                    hid[cb * kMaxHidden + jj] = fmaxf(s, 0.f);
+                }
+                epi_bar_sync();
             }
-            epi_bar_sync();
+            // ---- gate = sigmoid(W2 hidden + b2): thread (o = et & 31, part pt = et >> 5) does 8 hidden units
+            {
+                const int o = et & 31, pt = et >> 5;
+                float *gp = part;                            // [8][combos][32]
+                float acc[8];
+#pragma unroll
+                for (int cb = 0; cb < 8; ++cb) acc[cb] = 0.f;
+                for (int i = 0; i < 8; ++i) {
+                    const int jj = pt * 8 + i;
+                    if (jj < g.hidden) {
+                        const float wv = __ldg(w2t + (size_t)jj * kCout + o);
+#pragma unroll
+                        for (int cb = 0; cb < 8; ++cb)
+                            if (cb < combos) acc[cb] = fmaf(wv, hid[cb * kMaxHidden + jj], acc[cb]);
+                    }
+                }
+#pragma unroll
+                for (int cb = 0; cb < 8; ++cb)
+                    if (cb < combos) gp[(pt * 8 + cb) * kCout + o] = acc[cb];
+                epi_bar_sync();
+                for (int idx = et; idx < combos * kCout; idx += kEpi) {
+                    const int cb = idx >> 5, oo = idx & 31;
+                    float s = __ldg(b2 + oo);
+#pragma unroll
+                    for (int q8 = 0; q8 < 8; ++q8) s += gp[(q8 * 8 + cb) * kCout + oo];
+                    gateb[cb * kCout + oo] = 1.f / (1.f + expf(-s));
+                }
+                epi_bar_sync();
+            }
             // ---- accumulator -> gate -> bf16 -> concat buffer slice
             mbar_wait(afull(buf), ph);
             tc_fence_after();
@@ -365,6 +395,7 @@ bool geometry(const ConvArgs &a, int hidden, int seg_len, CamGeom &g) {
     g.P = (g.T + 2 * g.d + 7) & ~7;
     g.G = std::min(kMaxSeg, 248 / g.P);
     if (g.G < 1 || g.nwin > kMaxWin || hidden > kMaxHidden || hidden < 1) return false;
+    while (g.G * g.nwin > 8) --g.G;             // the gate MLP keeps at most 8 (segment, window) combos in registers
     g.n_tiles = (g.G * g.P + 127) / 128;
     // rows the shifted views can touch: n_tiles*128 + 2d; planes padded to px = 1 (mod 8) rows so the
     // sixteen planes of one row fall into different banks for the cp.async stores
@@ -377,7 +408,7 @@ bool geometry(const ConvArgs &a, int hidden, int seg_len, CamGeom &g) {
     auto take = [&](uint32_t bytes) { uint32_t o = off; off += (bytes + 127u) & ~127u; return o; };
     g.off_w = take(kTaps * kPlanes * 32 * 16);
     g.off_slab = take(2 * g.slab_bytes);
-    g.off_part = take(16 * kCin * 4);
+    g.off_part = take(2 * 16 * kCin * 4);       // double-buffered row-group partials; later aliased by the MLP partials
     g.off_win = take(2 * g.G * g.nwin * kCin * 4);
     g.off_tot = take(g.G * kCin * 4);
     g.off_hid = take(g.G * g.nwin * kMaxHidden * 4);
@@ -403,7 +434,7 @@ bool cam_local_supported(const ConvArgs &a, int in_dtype, int out_dtype, int hid
     return geometry(a, hidden, seg_len, g);
 }
 
-int launch_cam_local(const ConvArgs &a, const float *w1, const float *b1, const float *w2, const float *b2, int hidden,
+int launch_cam_local(const ConvArgs &a, const float *w1t, const float *b1, const float *w2t, const float *b2, int hidden,
                      int seg_len, cudaStream_t s) {
     CamGeom g;
     if (!geometry(a, hidden, seg_len, g)) {
@@ -422,7 +453,7 @@ int launch_cam_local(const ConvArgs &a, const float *w1, const float *b1, const 
     }
     const int items = (a.B + g.G - 1) / g.G;
     const int grid = std::min(items, sm_count());
-    cam_local_kernel<<<grid, kThreads, g.smem_bytes, s>>>(a, g, w1, b1, w2, b2, items);
+    cam_local_kernel<<<grid, kThreads, g.smem_bytes, s>>>(a, g, w1t, b1, w2t, b2, items);
     return check_launch("cam_local_kernel");
 }
 

@@ -102,7 +102,8 @@ int validate(const spk_model *m, const spk_program &p) {
                 break;
             case SPK_OP_CAM_LOCAL:
                 for (int j = 0; j < 4; ++j) ok = ok && par_ok(o.aux[j], false);
-                ok = ok && par_ok(o.w, false) && o.iaux[0] > 0 && o.iaux[1] > 0 && o.gate_buf >= 0 && o.KH == 1 && o.H == 1;
+                ok = ok && par_ok(o.w, false) && o.iaux[0] > 0 && o.iaux[1] > 0 && o.gate_buf >= 0 && o.KH == 1 && o.H == 1 &&
+                     par_ok(o.iaux[2], false) && par_ok(o.iaux[3], false);
                 if (ok && m->param_n[o.w] != (int64_t)o.Cout * o.KW * o.Cin) ok = false;
                 break;
             case SPK_OP_STATS_POOL:
@@ -270,7 +271,7 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                             rc = param_bf16(m, o.w, &wb, s);
                             if (rc == SPK_OK) {
                                 f.w = wb;
-                                rc = launch_cam_local(f, param(m, o.aux[0]), param(m, o.aux[1]), param(m, o.aux[2]),
+                                rc = launch_cam_local(f, param(m, o.iaux[2]), param(m, o.aux[1]), param(m, o.iaux[3]),
                                                       param(m, o.aux[3]), hidden, seg_len, s);
                             }
                             break;

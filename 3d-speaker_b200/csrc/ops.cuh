@@ -36,7 +36,8 @@ int launch_conv_slab(const ConvArgs &a, cudaStream_t s);
 
 // fused CAM layer (cam_local.cu): dilated k=3 conv (128->32) + context gate + gating multiply
 bool cam_local_supported(const ConvArgs &a, int in_dtype, int out_dtype, int hidden, int seg_len);
-int launch_cam_local(const ConvArgs &a, const float *w1, const float *b1, const float *w2, const float *b2, int hidden,
+// w1t [C][hidden] and w2t [hidden][Cout] are the TRANSPOSED gate weights
+int launch_cam_local(const ConvArgs &a, const float *w1t, const float *b1, const float *w2t, const float *b2, int hidden,
                      int seg_len, cudaStream_t s);
 
 struct StemArgs {

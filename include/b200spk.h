@@ -90,7 +90,7 @@ enum {
     SPK_OP_STATS_POOL = 4,  /* mean / std over positions                                             */
     SPK_OP_AFF_BLEND  = 5,  /* x*g + y*(2-g), g = 1+tanh(z)  (fusion.py:22-28); z = none: x + y       */
     SPK_OP_CAM_LOCAL  = 6   /* whole CAMLayer: dilated k=3 conv x context gate (layers.py:93-99); CONV fields +
-                               aux = w1,b1,w2,b2, iaux = hidden, seg_len, gate_buf = scratch for the unfused path */
+                               aux = w1,b1,w2,b2, iaux = hidden, seg_len, id(w1^T), id(w2^T); gate_buf = scratch for the unfused path */
 };
 enum { SPK_ACT_NONE = 0, SPK_ACT_RELU = 1, SPK_ACT_CLAMP20 = 2, SPK_ACT_SILU = 3 };
 

@@ -231,7 +231,8 @@ def test_cam_local_fused_op(precision, W, B, dil):
             w=model.param(torch.eye(C).reshape(C, 1, 1, C)))
     prog.op(_lib.OP_CAM_LOCAL, in_buf=xin, in_ld=C, out_buf=ybuf, out_ld=G, H=1, W=W, Cin=C, Ho=1, Wo=W, Cout=G, KH=1, KW=3,
             pw=dil, dw=dil, w=model.param(w), gate_buf=gbuf, gate_win=seg,
-            aux=[model.param(w1), model.param(b1), model.param(w2), model.param(b2)], iaux=[hidden, seg])
+            aux=[model.param(w1), model.param(b1), model.param(w2), model.param(b2)],
+            iaux=[hidden, seg, model.param(w1.t().contiguous()), model.param(w2.t().contiguous())])
     prog.op(_lib.OP_CONV, in_buf=ybuf, in_ld=G, out_buf=1, out_ld=G, H=1, W=W, Cin=G, Ho=1, Wo=W, Cout=G,
             w=model.param(torch.eye(G).reshape(G, 1, 1, G)))
     model.set_program(1, prog)

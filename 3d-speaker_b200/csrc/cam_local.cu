@@ -11,13 +11,17 @@
 // From that one copy
 //   * the MMA warp runs the three taps as shifted no-swizzle K-major UMMA descriptors
 //     (tap k = start address + k*d rows), tcgen05.mma M=128 N=32 K=16, accumulators in TMEM;
-//   * the epilogue warps - idle until the accumulator is ready - reduce the column sums of the
-//     same staged rows (fixed order: deterministic), run the two tiny mat-vecs of the gate, and
-//     then multiply the gate into the accumulator on its way to HBM.
+//   * the same warp gets the per-window column sums from the tensor core too: the channel-plane
+//     slab read as an MN-major operand (M = channels, K = rows) times a constant 0/1 window
+//     indicator matrix gives sum_t x[t, c] per (segment, window) in fp32, in a fixed order;
+//   * four "gate" warps read those sums from TMEM (one channel per thread) and run the two tiny
+//     mat-vecs of the gate while the conv MMAs are in flight;
+//   * four epilogue warps multiply the gate into the accumulator on its way to HBM.
 // Compared with the unfused path this removes one kernel launch, the separate read of x for the
 // context and the 3x gather of x for the taps.  Slabs and TMEM accumulators are double buffered,
 // so staging, MMA and epilogue of consecutive items overlap.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "ops.cuh"
@@ -27,7 +31,7 @@ namespace {
 
 using bf16 = __nv_bfloat16;
 constexpr int kCin = 128, kCout = 32, kPlanes = kCin / 8, kTaps = 3;
-constexpr int kProd = 128, kEpi = 256, kThreads = kProd + 32 + kEpi;       // 416
+constexpr int kProd = 128, kGate = 128, kEpi = 128, kThreads = kProd + 32 + kGate + kEpi;       // 416
 constexpr int kMaxSeg = 8, kMaxWin = 4, kMaxHidden = 64;
 constexpr uint32_t kSpinLimit = 1u << 26;
 
@@ -71,6 +75,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void umma_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -91,6 +107,17 @@ __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t addr, uint32_t lbo_b
     d |= (uint64_t)1 << 46;
     return d;
 }
+// descriptor halves: lo = start address | leading byte offset, hi = stride byte offset | version
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo_bytes) { return ((addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+// sums: D[128 channels][16] = A^T-view (MN-major, bit 15) x indicator (K-major)
+constexpr uint32_t kIdescSum = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+constexpr int kSumCols = 16;
 constexpr uint32_t kIdescN32 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 __device__ __forceinline__ uint4 ldg16(const void *p) {
     uint4 v;
@@ -109,7 +136,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void gate_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&t);
@@ -119,38 +146,130 @@ __device__ __forceinline__ float2 unpack2(uint32_t v) {
     return make_float2(__low2float(t), __high2float(t));
 }
 
+// The two mat-vecs of the gate for NC (segment, window) contexts at once, on 128 threads.
+//   hidden = relu(W1 ctx + b1): thread (hidden pair jp = t & 31, K split ks = t >> 5) does 32 channels;
+//   gate   = sigmoid(W2 hidden + b2): thread (o = t & 31, K split ks) does hidden/4 units;
+// the K splits are folded in a fixed order.  Weights are the transposed copies in shared memory:
+// w1t [128][hidden], w2t [hidden][32].  `part` (>= 4*NC*64 floats) is scratch; ends with a barrier
+// after which `gateb` [NC][32] is complete and `part` is free again.
+__device__ long long g_cam_ts[16 * 12];
+#define CAM_TS(slot) do { if ((dbg & 64) && blockIdx.x == 0 && it < 16 && (threadIdx.x & 31) == 0) g_cam_ts[it * 12 + (slot)] = clock64(); } while (0)
+
+template <int NC>
+__device__ __forceinline__ void gate_mlp(const float *ctx, float *part, float *hid, float *gateb, const float *w1t,
+                                         const float *w2t, const float *b1, const float *b2, int hidden, int t) {
+    const int ks = t >> 5;
+    {
+        const int j = 2 * (t & 31);
+        float2 acc[NC];
+#pragma unroll
+        for (int cb = 0; cb < NC; ++cb) acc[cb] = make_float2(0.f, 0.f);
+        if (j < hidden) {
+#pragma unroll 2
+            for (int i = 0; i < 32; i += 4) {
+                const int ch = ks * 32 + i;
+                float2 wv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) wv[e] = *reinterpret_cast<const float2 *>(&w1t[(ch + e) * hidden + j]);
+#pragma unroll
+                for (int cb = 0; cb < NC; ++cb) {
+                    const float4 x = *reinterpret_cast<const float4 *>(&ctx[cb * kCin + ch]);
+                    acc[cb].x = fmaf(wv[0].x, x.x, acc[cb].x); acc[cb].y = fmaf(wv[0].y, x.x, acc[cb].y);
+                    acc[cb].x = fmaf(wv[1].x, x.y, acc[cb].x); acc[cb].y = fmaf(wv[1].y, x.y, acc[cb].y);
+                    acc[cb].x = fmaf(wv[2].x, x.z, acc[cb].x); acc[cb].y = fmaf(wv[2].y, x.z, acc[cb].y);
+                    acc[cb].x = fmaf(wv[3].x, x.w, acc[cb].x); acc[cb].y = fmaf(wv[3].y, x.w, acc[cb].y);
+                }
+            }
+        }
+#pragma unroll
+        for (int cb = 0; cb < NC; ++cb) *reinterpret_cast<float2 *>(&part[(ks * NC + cb) * kMaxHidden + j]) = acc[cb];
+        gate_bar_sync();
+        for (int idx = t; idx < NC * kMaxHidden; idx += kGate) {
+            const int cb = idx >> 6, jj = idx & 63;
+            const float s = ((part[cb * kMaxHidden + jj] + part[(NC + cb) * kMaxHidden + jj]) +
+                             (part[(2 * NC + cb) * kMaxHidden + jj] + part[(3 * NC + cb) * kMaxHidden + jj]));
+            hid[idx] = jj < hidden ? fmaxf(s + b1[jj], 0.f) : 0.f;
+        }
+        gate_bar_sync();
+    }
+    {
+        const int o = t & 31;
+        float acc[NC];
+#pragma unroll
+        for (int cb = 0; cb < NC; ++cb) acc[cb] = 0.f;
+#pragma unroll
+        for (int i = 0; i < kMaxHidden / 4; i += 4) {
+            const int jj = ks * (kMaxHidden / 4) + i;
+            float wv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) wv[e] = jj + e < hidden ? w2t[(jj + e) * kCout + o] : 0.f;
+#pragma unroll
+            for (int cb = 0; cb < NC; ++cb) {
+                const float4 h = *reinterpret_cast<const float4 *>(&hid[cb * kMaxHidden + jj]);
+                acc[cb] = fmaf(wv[0], h.x, acc[cb]);
+                acc[cb] = fmaf(wv[1], h.y, acc[cb]);
+                acc[cb] = fmaf(wv[2], h.z, acc[cb]);
+                acc[cb] = fmaf(wv[3], h.w, acc[cb]);
+            }
+        }
+#pragma unroll
+        for (int cb = 0; cb < NC; ++cb) part[(ks * NC + cb) * kCout + o] = acc[cb];
+        gate_bar_sync();
+        for (int idx = t; idx < NC * kCout; idx += kGate) {
+            const int cb = idx >> 5, oo = idx & 31;
+            const float s = ((part[cb * kCout + oo] + part[(NC + cb) * kCout + oo]) +
+                             (part[(2 * NC + cb) * kCout + oo] + part[(3 * NC + cb) * kCout + oo])) + b2[oo];
+            gateb[idx] = 1.f / (1.f + expf(-s));
+        }
+        gate_bar_sync();
+    }
+}
+
 struct CamGeom {
     int T, d, P, G, n_tiles, px, nwin, seg_len, hidden;
     int smem_bytes, tmem_cols;
     unsigned p_magic;        // ceil(2^32 / P)
-    uint32_t off_w, off_slab, slab_bytes, off_part, off_win, off_tot, off_hid, off_gate, off_bar;
+    uint32_t off_w, off_slab, slab_bytes, off_part, off_win, off_ind, off_hid, off_gate, off_bar, off_mlp;
+    int k16;                 // 16-row K steps of the column-sum MMAs (covers G*P rows)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1t, const float *__restrict__ b1,
-                 const float *__restrict__ w2t, const float *__restrict__ b2, int n_items) {
+                 const float *__restrict__ w2t, const float *__restrict__ b2, int n_items, int dbg) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t s0 = smem_u32(smem);
-    const uint32_t s_w = s0 + g.off_w, s_slab0 = s0 + g.off_slab, s_bar = s0 + g.off_bar;
-    float *part = reinterpret_cast<float *>(smem + g.off_part);     // [2][16][128]
-    float *win = reinterpret_cast<float *>(smem + g.off_win);       // [2][G][nwin][128]   (per slab buffer)
-    float *hid = reinterpret_cast<float *>(smem + g.off_hid);       // [G*nwin][hidden]
+    const uint32_t s_w = s0 + g.off_w, s_slab0 = s0 + g.off_slab, s_bar = s0 + g.off_bar, s_ind = s0 + g.off_ind;
+    float *part = reinterpret_cast<float *>(smem + g.off_part);     // MLP partial sums
+    float *win = reinterpret_cast<float *>(smem + g.off_win);       // [G*nwin][128]  the contexts
+    float *hid = reinterpret_cast<float *>(smem + g.off_hid);       // [G*nwin][64]
     float *gate = reinterpret_cast<float *>(smem + g.off_gate);     // [2][G][nwin][32]
-    auto sfull = [&](int i) { return s_bar + 8u * i; };
-    auto sempty = [&](int i) { return s_bar + 8u * (2 + i); };
-    auto afull = [&](int i) { return s_bar + 8u * (4 + i); };
-    auto aempty = [&](int i) { return s_bar + 8u * (6 + i); };
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + g.off_bar + 64);
+    // gate MLP parameters, staged once per CTA: with ~200 KB of the SM given to shared memory the L1 is too
+    // small to keep the 40 KB of weights, and every mat-vec step would pay an L2 round trip
+    float *s_w1t = reinterpret_cast<float *>(smem + g.off_mlp);     // [128][hidden]
+    float *s_w2t = s_w1t + kCin * g.hidden;                          // [hidden][32]
+    float *s_b1 = s_w2t + g.hidden * kCout;                          // [hidden]
+    float *s_b2 = s_b1 + g.hidden;                                   // [32]
+    auto sfull = [&](int i) { return s_bar + 8u * i; };             // slab staged           (producers -> MMA)
+    auto sempty = [&](int i) { return s_bar + 8u * (2 + i); };      // slab consumed         (MMA commit -> producers)
+    auto afull = [&](int i) { return s_bar + 8u * (4 + i); };       // conv accumulator done (MMA commit -> epilogue)
+    auto aempty = [&](int i) { return s_bar + 8u * (6 + i); };      // TMEM buffer drained   (epilogue -> MMA)
+    auto gfull = [&](int i) { return s_bar + 8u * (8 + i); };       // gate values ready     (gate -> epilogue)
+    auto gempty = [&](int i) { return s_bar + 8u * (10 + i); };     // gate values consumed  (epilogue -> gate)
+    auto cfull = [&](int i) { return s_bar + 8u * (12 + i); };      // column sums done      (MMA commit -> gate)
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + g.off_bar + 128);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t plane = (uint32_t)g.px * 16u;
-    const uint32_t acc_cols = (uint32_t)g.n_tiles * 32u;
+    const uint32_t acc_cols = (uint32_t)g.n_tiles * 32u + 2 * kSumCols;  // per TMEM buffer: conv tiles, then the two sum halves
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(sfull(i), kProd);
-            mbar_init(sempty(i), 1 + kEpi);        // MMA commit + every epilogue thread (they read the slab for the context)
+            mbar_init(sempty(i), 1);
             mbar_init(afull(i), 1);
             mbar_init(aempty(i), kEpi);
+            mbar_init(gfull(i), kGate);
+            mbar_init(gempty(i), kEpi);
+            mbar_init(cfull(i), 1);
         }
         fence_barrier_init();
     }
@@ -164,13 +283,39 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
             const int c = idx % kPlanes, t = (idx / kPlanes) % kTaps, n = idx / (kPlanes * kTaps);
             sts16(s_w + (uint32_t)(((t * kPlanes + c) * 32 + n) * 16), ldg16(w + ((long long)n * kTaps + t) * kCin + c * 8));
         }
-        const int rows = g.G * g.P, slack = g.px - rows;
-        for (int idx = threadIdx.x; idx < 2 * slack * kPlanes; idx += kThreads) {
+        // rows the copies never write: the d leading and P-T-d trailing rows of every segment band, and the
+        // slack behind the last band
+        const int rows = g.G * g.P, pad = g.P - g.T, slack = g.px - rows;
+        const int per_slab = g.G * pad + slack;
+        for (int idx = threadIdx.x; idx < 2 * per_slab * kPlanes; idx += kThreads) {
             const int c = idx % kPlanes;
             int p = idx / kPlanes;
-            const uint32_t sb = s_slab0 + (p >= slack ? g.slab_bytes : 0u);
-            if (p >= slack) p -= slack;
-            sts16(sb + c * plane + (uint32_t)(rows + p) * 16u, make_uint4(0u, 0u, 0u, 0u));
+            const uint32_t sb = s_slab0 + (p >= per_slab ? g.slab_bytes : 0u);
+            if (p >= per_slab) p -= per_slab;
+            int row;
+            if (p < g.G * pad) {
+                const int gs = p / pad, e = p - gs * pad;
+                row = gs * g.P + (e < g.d ? e : g.T + e);
+            } else {
+                row = rows + (p - g.G * pad);
+            }
+            sts16(sb + c * plane + (uint32_t)row * 16u, make_uint4(0u, 0u, 0u, 0u));
+        }
+        // window indicator, K-major no-swizzle [k8 group][n = 16][8 rows]: 1 where slab row k is a frame of
+        // (segment, window) n
+        for (int idx = threadIdx.x; idx < g.k16 * 2 * kSumCols; idx += kThreads) {
+            const int n = idx % kSumCols, k8 = idx / kSumCols;
+            uint32_t v[4] = {0u, 0u, 0u, 0u};
+            if (n < g.G * g.nwin) {
+                const int gs = n / g.nwin, w = n - gs * g.nwin;
+                const int r0 = gs * g.P + g.d + w * g.seg_len, r1 = gs * g.P + g.d + min(g.T, (w + 1) * g.seg_len);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int r = k8 * 8 + e;
+                    if (r >= r0 && r < r1) v[e >> 1] |= (e & 1) ? 0x3F800000u : 0x00003F80u;       // bf16 1.0
+                }
+            }
+            sts16(s_ind + (uint32_t)idx * 16u, make_uint4(v[0], v[1], v[2], v[3]));
         }
     }
     fence_proxy_async();
@@ -181,180 +326,177 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
 
     if (warp < 4) {
         // =========================== producers (cp.async, zero-fill for the padding rows) ===========================
-        const bf16 *x = static_cast<const bf16 *>(a.x);
-        const int pieces = g.G * g.P * kPlanes;
+        // thread = (plane c, row r mod 8); rows advance by 8 so (segment, frame) are tracked incrementally.  The
+        // copies signal the slab barrier themselves when they land: the threads never wait for their data.
+        const bf16 *x = static_cast<const bf16 *>(a.x) + a.in_choff + (threadIdx.x & 15) * 8;
+        const uint32_t c_off = (uint32_t)(threadIdx.x & 15) * plane;
+        const int r_first = threadIdx.x >> 4;                // 0..7
+        const int rows = g.G * g.P;
+        const long long seg_stride = (long long)g.T * a.in_ld;
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int b0 = item * g.G;
             const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
             mbar_wait(sempty(buf), ph ^ 1u);
-            const uint32_t sb = s_slab0 + buf * g.slab_bytes;
-            for (int idx = threadIdx.x; idx < pieces; idx += kProd) {
-                const int c = idx & (kPlanes - 1);
-                const int row = idx >> 4;
-                const int gs = (int)__umulhi((unsigned)row, g.p_magic);
-                const int u = row - gs * g.P;
-                const int t = u - g.d;
-                const bool ok = (b0 + gs < a.B) && t >= 0 && t < g.T;
-                const bf16 *src = ok ? x + ((long long)(b0 + gs) * g.T + t) * a.in_ld + a.in_choff + c * 8 : x;
-                cp_async16(sb + c * plane + (uint32_t)row * 16u, src, ok ? 16u : 0u);
+            if (threadIdx.x == 0) CAM_TS(0);
+            const uint32_t sb = s_slab0 + buf * g.slab_bytes + c_off;
+            const bf16 *seg = x + (long long)b0 * seg_stride + (long long)r_first * a.in_ld;
+            uint32_t dst0 = sb + (uint32_t)(g.d + r_first) * 16u;
+            for (int gs = 0; gs < g.G; ++gs, seg += seg_stride, dst0 += (uint32_t)g.P * 16u) {
+                if (b0 + gs < a.B) {
+                    const bf16 *src = seg;
+                    uint32_t dst = dst0;
+                    for (int t = r_first; t < g.T; t += 8, src += 8 * (long long)a.in_ld, dst += 128u)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                } else {
+                    // ragged last item: rows of missing segments are zeros (their outputs are dropped, but they
+                    // must be finite for the column-sum MMAs, which run over all rows of the slab)
+                    for (int t = r_first; t < g.T; t += 8) sts16(dst0 + (uint32_t)(t - r_first) * 16u, make_uint4(0u, 0u, 0u, 0u));
+                    fence_proxy_async();
+                }
             }
-            cp_async_wait_all();
-            fence_proxy_async();
-            mbar_arrive(sfull(buf));
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sfull(buf)) : "memory");
+            if (threadIdx.x == 0) CAM_TS(1);
         }
+        cp_async_wait_all();
     } else if (warp == 4) {
         // =========================== MMA issuer ===========================
+        const uint32_t hi_a = desc_hi(128u), hi_b = desc_hi(128u);        // conv: K-major, 8-row groups 128 B apart
+        const uint32_t hi_at = desc_hi(plane);                             // sums: MN-major A, channel groups one plane apart
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
             mbar_wait(aempty(buf), ph ^ 1u);
             mbar_wait(sfull(buf), ph);
+            fence_proxy_async();                             // cp.async (generic proxy) writes -> tensor-core reads
             tc_fence_after();
-            if (lane == 0) {
+            CAM_TS(3);
+            if (elect_one()) {
                 const uint32_t sb = s_slab0 + buf * g.slab_bytes;
+                const uint32_t tb = tmem_base + buf * acc_cols;
+                {   // column sums first: the gate warps start while the conv MMAs run.  Even and odd K steps go
+                    // to two accumulators; the gate threads add them.
+                    uint32_t lo_a = desc_lo(sb, 128u), lo_b = desc_lo(s_ind, 256u);
+                    const uint32_t dsum = tb + (uint32_t)g.n_tiles * 32u;
+                    umma_bf16(dsum, desc64(lo_a, hi_at), desc64(lo_b, hi_b), kIdescSum, 0u);
+                    if (g.k16 > 1) umma_bf16(dsum + kSumCols, desc64(lo_a + (256u >> 4), hi_at), desc64(lo_b + (512u >> 4), hi_b), kIdescSum, 0u);
+                    for (int k = 2; k < g.k16; ++k) {
+                        lo_a += 256u >> 4;                   // 16 rows of 16 B
+                        lo_b += 512u >> 4;                   // two k8 groups of 16 x 16 B
+                        umma_bf16(dsum + (uint32_t)(k & 1) * kSumCols, desc64(lo_a + (256u >> 4), hi_at), desc64(lo_b + (512u >> 4), hi_b), kIdescSum, 1u);
+                    }
+                    umma_commit(cfull(buf));
+                }
+                // conv: per 128-row tile, 3 taps x 8 K steps, fully unrolled (the issue rate of this thread is
+                // what bounds small-N MMAs, so the loop body is one add per operand)
+                const uint32_t step_a = (2u * plane) >> 4;
                 for (int t = 0; t < g.n_tiles; ++t) {
-                    const uint32_t dcol = tmem_base + buf * acc_cols + (uint32_t)t * 32u;
+                    const uint32_t dcol = tb + (uint32_t)t * 32u;
 #pragma unroll
                     for (int k = 0; k < kTaps; ++k) {
-                        const uint32_t a_row = sb + (uint32_t)(t * 128 + k * g.d) * 16u;
-                        const uint32_t b_tap = s_w + (uint32_t)(k * kPlanes * 32 * 16);
+                        uint32_t lo_a = desc_lo(sb + (uint32_t)(t * 128 + k * g.d) * 16u, plane);
+                        const uint32_t lo_b = desc_lo(s_w + (uint32_t)(k * kPlanes * 32 * 16), 512u);
 #pragma unroll
-                        for (int j = 0; j < kCin / 16; ++j)
-                            umma_bf16(dcol, make_desc_nosw(a_row + 2u * j * plane, plane, 128u),
-                                      make_desc_nosw(b_tap + 2u * j * 512u, 512u, 128u), kIdescN32, (k | j) ? 1u : 0u);
+                        for (int j = 0; j < kCin / 16; ++j) {
+                            if (k == 0 && j == 0) umma_bf16(dcol, desc64(lo_a, hi_a), desc64(lo_b, hi_b), kIdescN32, 0u);
+                            else umma_acc(dcol, desc64(lo_a, hi_a), desc64(lo_b + (uint32_t)j * ((2u * 512u) >> 4), hi_b), kIdescN32);
+                            lo_a += step_a;
+                        }
                     }
                 }
                 umma_commit(sempty(buf));
                 umma_commit(afull(buf));
             }
             __syncwarp();
+            CAM_TS(4);
+        }
+    } else if (warp < 9) {
+        // =========================== context gate (warps 5-8, 128 threads) ===========================
+        // thread = one input channel: TMEM lane (warp & 3) * 32 + lane of the column-sum accumulator
+        const int gt = threadIdx.x - (kProd + 32);          // 0..127, the MLP work index
+        const int q = warp & 3, ch = q * 32 + lane;
+        {   // gate MLP parameters -> smem (overlaps the producers' first item)
+            const int n16 = (kCin * g.hidden + g.hidden * kCout + g.hidden + kCout) / 4;     // laid out back to back
+            const uint32_t dst = smem_u32(s_w1t);
+            for (int idx = gt; idx < n16; idx += kGate) {
+                const int e = idx * 4;
+                const float *src = e < kCin * g.hidden ? w1t + e
+                                 : e < kCin * g.hidden + g.hidden * kCout ? w2t + (e - kCin * g.hidden)
+                                 : e < kCin * g.hidden + g.hidden * kCout + g.hidden ? b1 + (e - kCin * g.hidden - g.hidden * kCout)
+                                 : b2 + (e - kCin * g.hidden - g.hidden * kCout - g.hidden);
+                cp_async16(dst + (uint32_t)e * 4u, src, 16u);
+            }
+            cp_async_wait_all();
+            gate_bar_sync();
+        }
+        const int nc = g.G * g.nwin;                        // (segment, window) combos of a full item
+        const float inv_T = 1.f / (float)g.T;
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+            float *gateb = gate + (size_t)buf * g.G * g.nwin * kCout;
+            mbar_wait(cfull(buf), ph);
+            tc_fence_after();
+            if (gt == 0) CAM_TS(5);
+            {   // ---- ctx = mean over the segment + mean over the window, for this thread's channel
+                uint32_t rr[16], ro[16];
+                const uint32_t ts = tmem_base + buf * acc_cols + (uint32_t)g.n_tiles * 32u + ((uint32_t)(q * 32) << 16);
+                tmem_ld16(ts, rr);
+                tmem_ld16(ts + kSumCols, ro);
+                tmem_ld_wait();
+                tc_fence_before();
+                float sums[kSumCols];
+#pragma unroll
+                for (int e = 0; e < kSumCols; ++e) sums[e] = __uint_as_float(rr[e]) + (g.k16 > 1 ? __uint_as_float(ro[e]) : 0.f);
+                int cb = 0;
+                for (int gs = 0; gs < g.G; ++gs) {
+                    float tot = 0.f;
+#pragma unroll
+                    for (int e = 0; e < kSumCols; ++e)
+                        if (e >= cb && e < cb + g.nwin) tot += sums[e];
+                    tot *= inv_T;
+                    for (int w = 0; w < g.nwin; ++w, ++cb) {
+                        const int len = min(g.T, (w + 1) * g.seg_len) - w * g.seg_len;
+                        float sv = 0.f;
+#pragma unroll
+                        for (int e = 0; e < kSumCols; ++e)
+                            if (e == cb) sv = sums[e];
+                        win[cb * kCin + ch] = tot + sv / (float)len;
+                    }
+                }
+            }
+            if (gt == 0) CAM_TS(6);
+            mbar_wait(gempty(buf), ph ^ 1u);                // the epilogue of item i-2 has read this gate buffer
+            gate_bar_sync();
+            if (gt == 0) CAM_TS(7);
+            switch (nc) {
+                case 1: gate_mlp<1>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 2: gate_mlp<2>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 3: gate_mlp<3>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 4: gate_mlp<4>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 5: gate_mlp<5>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 6: gate_mlp<6>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 7: gate_mlp<7>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                default: gate_mlp<8>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+            }
+            mbar_arrive(gfull(buf));
+            if (gt == 0) CAM_TS(8);
         }
     } else {
-        // =========================== context gate + epilogue (256 threads) ===========================
-        const int et = threadIdx.x - (kProd + 32);          // 0..255
-        const int ew = et >> 5;                              // 0..7
-        const int q = warp & 3, tsel = ew >> 2;
+        // =========================== epilogue (warps 9-12, 128 threads) ===========================
+        const int q = warp & 3;                              // warps 9..12 -> TMEM lane quarters 1,2,3,0
         bf16 *y = static_cast<bf16 *>(a.y);
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int b0 = item * g.G;
             const int g_valid = min(g.G, a.B - b0);
             const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
-            const uint32_t sb = s_slab0 + buf * g.slab_bytes;
-            float *winb = win + (size_t)buf * g.G * g.nwin * kCin;
-            float *gateb = gate + (size_t)buf * g.G * g.nwin * kCout;
-            mbar_wait(sfull(buf), ph);
-            const int combos = g_valid * g.nwin;
-            // ---- column sums of the staged rows: thread (plane c = et & 15, row group rg = et >> 4) sums its
-            // rows of one (segment, window), the 16 row groups are folded in a fixed order (deterministic).
-            // `part` is double buffered so each round needs one barrier only.
-            {
-                const int c = et & 15, rg = et >> 4;
-                for (int cb = 0; cb < combos; ++cb) {
-                    const int gs = cb / g.nwin, w = cb - gs * g.nwin;
-                    const int t0 = w * g.seg_len, t1 = min(g.T, t0 + g.seg_len);
-                    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    for (int t = t0 + rg; t < t1; t += 16) {
-                        const uint4 v = lds16(sb + c * plane + (uint32_t)(gs * g.P + g.d + t) * 16u);
-                        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            const float2 f = unpack2(vv[h]);
-                            acc[2 * h] += f.x;
-                            acc[2 * h + 1] += f.y;
-                        }
-                    }
-                    float *pp = part + (cb & 1) * 16 * kCin;
-                    *reinterpret_cast<float4 *>(&pp[rg * kCin + c * 8]) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                    *reinterpret_cast<float4 *>(&pp[rg * kCin + c * 8 + 4]) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-                    epi_bar_sync();
-                    if (et < kCin) {
-                        float s = 0.f;
-#pragma unroll
-                        for (int r = 0; r < 16; ++r) s += pp[r * kCin + et];
-                        winb[cb * kCin + et] = s;
-                    }
-                }
-            }
-            // the slab is no longer needed by these threads
-            mbar_arrive(sempty(buf));
-            // ---- ctx = tot/T + win/len, in place (thread et owns channel et of every combo: no barrier needed)
-            if (et < kCin) {
-                for (int gs = 0; gs < g_valid; ++gs) {
-                    float t = 0.f;
-                    for (int w = 0; w < g.nwin; ++w) t += winb[(gs * g.nwin + w) * kCin + et];
-                    t /= (float)g.T;
-                    for (int w = 0; w < g.nwin; ++w) {
-                        const int len = min(g.T, (w + 1) * g.seg_len) - w * g.seg_len;
-                        float *p = &winb[(gs * g.nwin + w) * kCin + et];
-                        *p = t + *p / (float)len;
-                    }
-                }
-            }
-            epi_bar_sync();
-            // ---- hidden = relu(W1 ctx + b1): thread (j = et & 63, quarter qd = et >> 6) does 32 channels of
-            // every combo from the TRANSPOSED weights (coalesced rows of 64 floats); quarters folded in order
-            {
-                const int j = et & 63, qd = et >> 6;
-                float acc[kMaxSeg * kMaxWin > 8 ? 8 : kMaxSeg * kMaxWin];
-                float *hp = part;                            // [4][combos][64] aliases the (now dead) row-group partials
-                if (j < g.hidden) {
-#pragma unroll
-                    for (int cb = 0; cb < 8; ++cb) acc[cb] = 0.f;
-                    for (int i = 0; i < 32; ++i) {
-                        const int ch = qd * 32 + i;
-                        const float wv = __ldg(w1t + (size_t)ch * g.hidden + j);
-#pragma unroll
-                        for (int cb = 0; cb < 8; ++cb)
-                            if (cb < combos) acc[cb] = fmaf(wv, winb[cb * kCin + ch], acc[cb]);
-                    }
-#pragma unroll
-                    for (int cb = 0; cb < 8; ++cb)
-                        if (cb < combos) hp[(qd * 8 + cb) * kMaxHidden + j] = acc[cb];
-                }
-                epi_bar_sync();
-                for (int idx = et; idx < combos * g.hidden; idx += kEpi) {
-                    const int cb = idx / g.hidden, jj = idx - cb * g.hidden;
-                    const float s = ((hp[(0 * 8 + cb) * kMaxHidden + jj] + hp[(1 * 8 + cb) * kMaxHidden + jj]) +
-                                     (hp[(2 * 8 + cb) * kMaxHidden + jj] + hp[(3 * 8 + cb) * kMaxHidden + jj])) + __ldg(b1 + jj);
-                    hid[cb * kMaxHidden + jj] = fmaxf(s, 0.f);
-                }
-                epi_bar_sync();
-            }
-            // ---- gate = sigmoid(W2 hidden + b2): thread (o = et & 31, part pt = et >> 5) does 8 hidden units
-            {
-                const int o = et & 31, pt = et >> 5;
-                float *gp = part;                            // [8][combos][32]
-                float acc[8];
-#pragma unroll
-                for (int cb = 0; cb < 8; ++cb) acc[cb] = 0.f;
-                for (int i = 0; i < 8; ++i) {
-                    const int jj = pt * 8 + i;
-                    if (jj < g.hidden) {
-                        const float wv = __ldg(w2t + (size_t)jj * kCout + o);
-#pragma unroll
-                        for (int cb = 0; cb < 8; ++cb)
-                            if (cb < combos) acc[cb] = fmaf(wv, hid[cb * kMaxHidden + jj], acc[cb]);
-                    }
-                }
-#pragma unroll
-                for (int cb = 0; cb < 8; ++cb)
-                    if (cb < combos) gp[(pt * 8 + cb) * kCout + o] = acc[cb];
-                epi_bar_sync();
-                for (int idx = et; idx < combos * kCout; idx += kEpi) {
-                    const int cb = idx >> 5, oo = idx & 31;
-                    float s = __ldg(b2 + oo);
-#pragma unroll
-                    for (int q8 = 0; q8 < 8; ++q8) s += gp[(q8 * 8 + cb) * kCout + oo];
-                    gateb[cb * kCout + oo] = 1.f / (1.f + expf(-s));
-                }
-                epi_bar_sync();
-            }
-            // ---- accumulator -> gate -> bf16 -> concat buffer slice
+            const float *gateb = gate + (size_t)buf * g.G * g.nwin * kCout;
+            mbar_wait(gfull(buf), ph);
             mbar_wait(afull(buf), ph);
             tc_fence_after();
-            for (int t = tsel; t < g.n_tiles; t += 2) {
+            if (warp == 9) CAM_TS(9);
+            for (int t = 0; t < g.n_tiles; ++t) {
                 const int r = t * 128 + q * 32 + lane;
                 const int gs = (int)__umulhi((unsigned)r, g.p_magic);
                 const int u = r - gs * g.P;
@@ -382,6 +524,8 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
             }
             tc_fence_before();
             mbar_arrive(aempty(buf));
+            mbar_arrive(gempty(buf));
+            if (warp == 9) CAM_TS(10);
         }
     }
     tc_fence_before();
@@ -394,12 +538,12 @@ bool geometry(const ConvArgs &a, int hidden, int seg_len, CamGeom &g) {
     g.nwin = (g.T + seg_len - 1) / seg_len;
     g.P = (g.T + 2 * g.d + 7) & ~7;
     g.G = std::min(kMaxSeg, 248 / g.P);
-    if (g.G < 1 || g.nwin > kMaxWin || hidden > kMaxHidden || hidden < 1) return false;
+    if (g.G < 1 || g.nwin > kMaxWin || hidden > kMaxHidden || hidden < 4 || hidden % 4) return false;
     while (g.G * g.nwin > 8) --g.G;             // the gate MLP keeps at most 8 (segment, window) combos in registers
     g.n_tiles = (g.G * g.P + 127) / 128;
     // rows the shifted views can touch: n_tiles*128 + 2d; planes padded to px = 1 (mod 8) rows so the
     // sixteen planes of one row fall into different banks for the cp.async stores
-    int px = std::max(g.G * g.P, g.n_tiles * 128) + 2 * g.d + 8;
+    int px = std::max(g.G * g.P, g.n_tiles * 128) + 2 * g.d;
     px = ((px + 7) & ~7) + 1;
     g.px = px;
     g.p_magic = (unsigned)(((1ull << 32) + g.P - 1) / g.P);
@@ -408,16 +552,18 @@ bool geometry(const ConvArgs &a, int hidden, int seg_len, CamGeom &g) {
     auto take = [&](uint32_t bytes) { uint32_t o = off; off += (bytes + 127u) & ~127u; return o; };
     g.off_w = take(kTaps * kPlanes * 32 * 16);
     g.off_slab = take(2 * g.slab_bytes);
-    g.off_part = take(2 * 16 * kCin * 4);       // double-buffered row-group partials; later aliased by the MLP partials
-    g.off_win = take(2 * g.G * g.nwin * kCin * 4);
-    g.off_tot = take(g.G * kCin * 4);
-    g.off_hid = take(g.G * g.nwin * kMaxHidden * 4);
+    g.off_part = take(4 * 8 * kMaxHidden * 4);  // K-split partials of the gate MLP
+    g.off_win = take(g.G * g.nwin * kCin * 4);
+    g.k16 = (g.G * g.P + 15) / 16;
+    g.off_ind = take(g.k16 * 2 * kSumCols * 16);
+    g.off_hid = take(8 * kMaxHidden * 4);
     g.off_gate = take(2 * g.G * g.nwin * kCout * 4);
-    g.off_bar = take(128);
+    g.off_bar = take(256);
+    g.off_mlp = take((kCin * hidden + hidden * kCout + hidden + kCout) * 4);
     g.smem_bytes = (int)off;
-    const int cols = 2 * g.n_tiles * 32;
+    const int cols = 2 * (g.n_tiles * 32 + 2 * kSumCols);
     g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-    return g.smem_bytes <= 220 * 1024 && cols <= 512;
+    return g.smem_bytes <= 227 * 1024 && cols <= 512;
 }
 
 }  // namespace
@@ -445,7 +591,7 @@ int launch_cam_local(const ConvArgs &a, const float *w1t, const float *b1, const
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] {
-        attr_err = cudaFuncSetAttribute(cam_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        attr_err = cudaFuncSetAttribute(cam_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     });
     if (attr_err != cudaSuccess) {
         set_error("cudaFuncSetAttribute(cam_local) failed: %s", cudaGetErrorString(attr_err));
@@ -453,8 +599,14 @@ int launch_cam_local(const ConvArgs &a, const float *w1t, const float *b1, const
     }
     const int items = (a.B + g.G - 1) / g.G;
     const int grid = std::min(items, sm_count());
-    cam_local_kernel<<<grid, kThreads, g.smem_bytes, s>>>(a, g, w1t, b1, w2t, b2, items);
+    static const int dbg = getenv("SPK_CAM_DBG") ? atoi(getenv("SPK_CAM_DBG")) : 0;
+    cam_local_kernel<<<grid, kThreads, g.smem_bytes, s>>>(a, g, w1t, b1, w2t, b2, items, dbg);
     return check_launch("cam_local_kernel");
 }
 
 }  // namespace spk
+
+// debug aid (not part of the ABI): per-item role timestamps of CTA 0 of the last launch with SPK_CAM_DBG & 64
+extern "C" int spk_debug_cam_timeline(long long *dst) {
+    return cudaMemcpyFromSymbol(dst, spk::g_cam_ts, sizeof(long long) * 16 * 12) == cudaSuccess ? 0 : -1;
+}

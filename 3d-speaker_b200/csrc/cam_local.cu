@@ -6,32 +6,40 @@
 //   m   = sigmoid(W2 relu(W1 ctx + b1) + b2)      1x1 convs with bias, evaluated once per window
 //   out = y * m                                   written into the block's concat buffer slice
 //
-// A CTA item is a group of whole segments: their rows (zero padded by d on both sides, pitch P)
-// are staged ONCE in shared memory as sixteen 16-byte channel planes by cp.async producer warps.
-// From that one copy
-//   * the MMA warp runs the three taps as shifted no-swizzle K-major UMMA descriptors
-//     (tap k = start address + k*d rows), tcgen05.mma M=128 N=32 K=16, accumulators in TMEM;
-//   * the same warp gets the per-window column sums from the tensor core too: the channel-plane
-//     slab read as an MN-major operand (M = channels, K = rows) times a constant 0/1 window
-//     indicator matrix gives sum_t x[t, c] per (segment, window) in fp32, in a fixed order;
+// A CTA item is a group of whole segments.  Their rows (zero padded by d on both sides, pitch P)
+// are staged ONCE in shared memory by TMA: one 3-D box {64 channels, P frames, 1 segment} per
+// segment and channel half, starting at frame -d, so the padding rows - and the rows of segments past
+// the end of the batch - are the TMA unit's out-of-bounds zero fill.  The slab is two K-major
+// 128-byte-swizzled halves (channels 0-63 and 64-127).  From that one copy
+//   * the MMA warp runs the three taps as row-shifted UMMA descriptors (tap k = start address +
+//     k*d rows; the swizzle is a function of the absolute shared-memory address, so any row shift
+//     keeps the pattern), tcgen05.mma M=128 N=32 K=16, accumulators in TMEM;
+//   * the same warp gets the per-window column sums from the tensor core too: the slab read as an
+//     MN-major operand (M = channels, K = rows) times a constant 0/1 window indicator matrix gives
+//     sum_t x[t, c] per (segment, window) in fp32, in a fixed order;
 //   * four "gate" warps read those sums from TMEM (one channel per thread) and run the two tiny
 //     mat-vecs of the gate while the conv MMAs are in flight;
 //   * four epilogue warps multiply the gate into the accumulator on its way to HBM.
 // Compared with the unfused path this removes one kernel launch, the separate read of x for the
 // context and the 3x gather of x for the taps.  Slabs and TMEM accumulators are double buffered,
-// so staging, MMA and epilogue of consecutive items overlap.
+// so staging, MMA and epilogue of consecutive items overlap.  Small-N MMAs are bound by the
+// shared-memory read of A (4 KB per MMA, ~40 cycles) and by the issue rate of the one issuing
+// thread, hence the fully unrolled issue loops.
 #include <algorithm>
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <tuple>
 
 #include "ops.cuh"
+#include "tmap.cuh"
 
 namespace spk {
 namespace {
 
 using bf16 = __nv_bfloat16;
 constexpr int kCin = 128, kCout = 32, kPlanes = kCin / 8, kTaps = 3;
-constexpr int kProd = 128, kGate = 128, kEpi = 128, kThreads = kProd + 32 + kGate + kEpi;       // 416
+constexpr int kGate = 128, kEpi = 128, kThreads = 32 + 32 + kGate + kEpi;       // 320: TMA warp, MMA warp, gate, epilogue
 constexpr int kMaxSeg = 8, kMaxWin = 4, kMaxHidden = 64;
 constexpr uint32_t kSpinLimit = 1u << 26;
 
@@ -41,6 +49,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -110,6 +121,7 @@ __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t addr, uint32_t lbo_b
 // descriptor halves: lo = start address | leading byte offset, hi = stride byte offset | version
 __device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo_bytes) { return ((addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint32_t desc_hi_sw128(uint32_t sbo_bytes) { return desc_hi(sbo_bytes) | (2u << 29); }
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
     uint64_t d;
     asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
@@ -146,66 +158,74 @@ __device__ __forceinline__ float2 unpack2(uint32_t v) {
     return make_float2(__low2float(t), __high2float(t));
 }
 
-// The two mat-vecs of the gate for NC (segment, window) contexts at once, on 128 threads.
-//   hidden = relu(W1 ctx + b1): thread (hidden pair jp = t & 31, K split ks = t >> 5) does 32 channels;
-//   gate   = sigmoid(W2 hidden + b2): thread (o = t & 31, K split ks) does hidden/4 units;
-// the K splits are folded in a fixed order.  Weights are the transposed copies in shared memory:
-// w1t [128][hidden], w2t [hidden][32].  `part` (>= 4*NC*64 floats) is scratch; ends with a barrier
-// after which `gateb` [NC][32] is complete and `part` is free again.
+// debug aid: per-item role timestamps of CTA 0 (SPK_CAM_DBG & 64), read back by spk_debug_cam_timeline
 __device__ long long g_cam_ts[16 * 12];
 #define CAM_TS(slot) do { if ((dbg & 64) && blockIdx.x == 0 && it < 16 && (threadIdx.x & 31) == 0) g_cam_ts[it * 12 + (slot)] = clock64(); } while (0)
 
+// The two mat-vecs of the gate for NC (segment, window) contexts at once, on 4 warps, with one block barrier.
+// Both layers split the outputs across warps and the reduction dimension across the four lane groups
+// ks = lane >> 3 of a warp, so partial sums are folded with two shuffles (fixed order) instead of shared memory:
+//   hidden = relu(W1 ctx + b1): warp w owns hidden units 16w..16w+15, lane = (pair jq = lane & 7, ks);
+//                               lane group ks covers channels ch = 4i + ks
+//   gate   = sigmoid(W2 hidden + b2): warp w owns outputs 8w..8w+7, lane = (o = lane & 7, ks);
+//                               lane group ks covers hidden units 4i + ks
+// ctx and hid are stored permuted ([cb][ks][i]) so a lane reads its operands as float4; the transposed weights
+// have padded pitches (kW1Pitch, kW2Pitch) that put the four lane groups of a load in different banks.
+constexpr int kW1Pitch = 80, kW2Pitch = 40;
 template <int NC>
-__device__ __forceinline__ void gate_mlp(const float *ctx, float *part, float *hid, float *gateb, const float *w1t,
-                                         const float *w2t, const float *b1, const float *b2, int hidden, int t) {
-    const int ks = t >> 5;
+__device__ __forceinline__ void gate_mlp(const float *ctx, float *hid, float *gateb, const float *w1t, const float *w2t,
+                                         const float *b1, const float *b2, int hidden, int t) {
+    const int w = t >> 5, lane = t & 31, ks = lane >> 3;
     {
-        const int j = 2 * (t & 31);
+        const int j = 16 * w + 2 * (lane & 7);
         float2 acc[NC];
 #pragma unroll
         for (int cb = 0; cb < NC; ++cb) acc[cb] = make_float2(0.f, 0.f);
-        if (j < hidden) {
 #pragma unroll 2
-            for (int i = 0; i < 32; i += 4) {
-                const int ch = ks * 32 + i;
-                float2 wv[4];
+        for (int i = 0; i < 32; i += 4) {
+            float2 wv[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) wv[e] = *reinterpret_cast<const float2 *>(&w1t[(ch + e) * hidden + j]);
+            for (int e = 0; e < 4; ++e) wv[e] = *reinterpret_cast<const float2 *>(&w1t[(4 * (i + e) + ks) * kW1Pitch + j]);
 #pragma unroll
-                for (int cb = 0; cb < NC; ++cb) {
-                    const float4 x = *reinterpret_cast<const float4 *>(&ctx[cb * kCin + ch]);
-                    acc[cb].x = fmaf(wv[0].x, x.x, acc[cb].x); acc[cb].y = fmaf(wv[0].y, x.x, acc[cb].y);
-                    acc[cb].x = fmaf(wv[1].x, x.y, acc[cb].x); acc[cb].y = fmaf(wv[1].y, x.y, acc[cb].y);
-                    acc[cb].x = fmaf(wv[2].x, x.z, acc[cb].x); acc[cb].y = fmaf(wv[2].y, x.z, acc[cb].y);
-                    acc[cb].x = fmaf(wv[3].x, x.w, acc[cb].x); acc[cb].y = fmaf(wv[3].y, x.w, acc[cb].y);
-                }
+            for (int cb = 0; cb < NC; ++cb) {
+                const float4 x = *reinterpret_cast<const float4 *>(&ctx[cb * kCin + ks * 32 + i]);
+                acc[cb].x = fmaf(wv[0].x, x.x, acc[cb].x); acc[cb].y = fmaf(wv[0].y, x.x, acc[cb].y);
+                acc[cb].x = fmaf(wv[1].x, x.y, acc[cb].x); acc[cb].y = fmaf(wv[1].y, x.y, acc[cb].y);
+                acc[cb].x = fmaf(wv[2].x, x.z, acc[cb].x); acc[cb].y = fmaf(wv[2].y, x.z, acc[cb].y);
+                acc[cb].x = fmaf(wv[3].x, x.w, acc[cb].x); acc[cb].y = fmaf(wv[3].y, x.w, acc[cb].y);
             }
         }
 #pragma unroll
-        for (int cb = 0; cb < NC; ++cb) *reinterpret_cast<float2 *>(&part[(ks * NC + cb) * kMaxHidden + j]) = acc[cb];
-        gate_bar_sync();
-        for (int idx = t; idx < NC * kMaxHidden; idx += kGate) {
-            const int cb = idx >> 6, jj = idx & 63;
-            const float s = ((part[cb * kMaxHidden + jj] + part[(NC + cb) * kMaxHidden + jj]) +
-                             (part[(2 * NC + cb) * kMaxHidden + jj] + part[(3 * NC + cb) * kMaxHidden + jj]));
-            hid[idx] = jj < hidden ? fmaxf(s + b1[jj], 0.f) : 0.f;
+        for (int cb = 0; cb < NC; ++cb) {
+            acc[cb].x += __shfl_xor_sync(0xffffffffu, acc[cb].x, 8);
+            acc[cb].y += __shfl_xor_sync(0xffffffffu, acc[cb].y, 8);
+            acc[cb].x += __shfl_xor_sync(0xffffffffu, acc[cb].x, 16);
+            acc[cb].y += __shfl_xor_sync(0xffffffffu, acc[cb].y, 16);
         }
-        gate_bar_sync();
+        if (ks == 0) {
+            const float bx = j < hidden ? b1[j] : 0.f, by = j + 1 < hidden ? b1[j + 1] : 0.f;
+#pragma unroll
+            for (int cb = 0; cb < NC; ++cb) {
+                // unit j lives at [cb][j & 3][j >> 2]
+                hid[cb * kMaxHidden + (j & 3) * 16 + (j >> 2)] = j < hidden ? fmaxf(acc[cb].x + bx, 0.f) : 0.f;
+                hid[cb * kMaxHidden + ((j + 1) & 3) * 16 + ((j + 1) >> 2)] = j + 1 < hidden ? fmaxf(acc[cb].y + by, 0.f) : 0.f;
+            }
+        }
     }
+    gate_bar_sync();
     {
-        const int o = t & 31;
+        const int o = 8 * w + (lane & 7);
         float acc[NC];
 #pragma unroll
         for (int cb = 0; cb < NC; ++cb) acc[cb] = 0.f;
 #pragma unroll
-        for (int i = 0; i < kMaxHidden / 4; i += 4) {
-            const int jj = ks * (kMaxHidden / 4) + i;
+        for (int i = 0; i < 16; i += 4) {
             float wv[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) wv[e] = jj + e < hidden ? w2t[(jj + e) * kCout + o] : 0.f;
+            for (int e = 0; e < 4; ++e) wv[e] = w2t[(4 * (i + e) + ks) * kW2Pitch + o];
 #pragma unroll
             for (int cb = 0; cb < NC; ++cb) {
-                const float4 h = *reinterpret_cast<const float4 *>(&hid[cb * kMaxHidden + jj]);
+                const float4 h = *reinterpret_cast<const float4 *>(&hid[cb * kMaxHidden + ks * 16 + i]);
                 acc[cb] = fmaf(wv[0], h.x, acc[cb]);
                 acc[cb] = fmaf(wv[1], h.y, acc[cb]);
                 acc[cb] = fmaf(wv[2], h.z, acc[cb]);
@@ -213,15 +233,35 @@ __device__ __forceinline__ void gate_mlp(const float *ctx, float *part, float *h
             }
         }
 #pragma unroll
-        for (int cb = 0; cb < NC; ++cb) part[(ks * NC + cb) * kCout + o] = acc[cb];
-        gate_bar_sync();
-        for (int idx = t; idx < NC * kCout; idx += kGate) {
-            const int cb = idx >> 5, oo = idx & 31;
-            const float s = ((part[cb * kCout + oo] + part[(NC + cb) * kCout + oo]) +
-                             (part[(2 * NC + cb) * kCout + oo] + part[(3 * NC + cb) * kCout + oo])) + b2[oo];
-            gateb[idx] = 1.f / (1.f + expf(-s));
+        for (int cb = 0; cb < NC; ++cb) {
+            acc[cb] += __shfl_xor_sync(0xffffffffu, acc[cb], 8);
+            acc[cb] += __shfl_xor_sync(0xffffffffu, acc[cb], 16);
         }
-        gate_bar_sync();
+        if (ks == 0) {
+            const float bo = b2[o];
+#pragma unroll
+            for (int cb = 0; cb < NC; ++cb) gateb[cb * kCout + o] = 1.f / (1.f + expf(-(acc[cb] + bo)));
+        }
+    }
+}
+
+// ctx = mean over the segment + mean over the window for one channel, from the raw window sums (registers only).
+// Written permuted: channel ch of combo cb lives at ctx[cb][ch & 3][ch >> 2].
+template <int NWIN>
+__device__ __forceinline__ void ctx_from_sums(const float (&sums)[8], float *ctx, int G, int ch, float inv_T, float inv_seg,
+                                              float inv_last) {
+    const int pos = (ch & 3) * 32 + (ch >> 2);
+#pragma unroll
+    for (int gs = 0; gs < 8 / NWIN; ++gs) {
+        if (gs < G) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < NWIN; ++w) tot += sums[gs * NWIN + w];
+            tot *= inv_T;
+#pragma unroll
+            for (int w = 0; w < NWIN; ++w)
+                ctx[(gs * NWIN + w) * kCin + pos] = fmaf(sums[gs * NWIN + w], w == NWIN - 1 ? inv_last : inv_seg, tot);
+        }
     }
 }
 
@@ -229,28 +269,28 @@ struct CamGeom {
     int T, d, P, G, n_tiles, px, nwin, seg_len, hidden;
     int smem_bytes, tmem_cols;
     unsigned p_magic;        // ceil(2^32 / P)
-    uint32_t off_w, off_slab, slab_bytes, off_part, off_win, off_ind, off_hid, off_gate, off_bar, off_mlp;
+    uint32_t off_w, off_slab, slab_bytes, half_bytes, off_part, off_win, off_ind, off_hid, off_gate, off_bar, off_mlp;
     int k16;                 // 16-row K steps of the column-sum MMAs (covers G*P rows)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1t, const float *__restrict__ b1,
-                 const float *__restrict__ w2t, const float *__restrict__ b2, int n_items, int dbg) {
-    extern __shared__ __align__(128) uint8_t smem[];
+                 const float *__restrict__ w2t, const float *__restrict__ b2, int n_items, int dbg,
+                 const __grid_constant__ CUtensorMap xmap) {
+    extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t s0 = smem_u32(smem);
     const uint32_t s_w = s0 + g.off_w, s_slab0 = s0 + g.off_slab, s_bar = s0 + g.off_bar, s_ind = s0 + g.off_ind;
-    float *part = reinterpret_cast<float *>(smem + g.off_part);     // MLP partial sums
     float *win = reinterpret_cast<float *>(smem + g.off_win);       // [G*nwin][128]  the contexts
     float *hid = reinterpret_cast<float *>(smem + g.off_hid);       // [G*nwin][64]
     float *gate = reinterpret_cast<float *>(smem + g.off_gate);     // [2][G][nwin][32]
-    // gate MLP parameters, staged once per CTA: with ~200 KB of the SM given to shared memory the L1 is too
+    // gate MLP parameters, staged once per CTA: with ~220 KB of the SM given to shared memory the L1 is too
     // small to keep the 40 KB of weights, and every mat-vec step would pay an L2 round trip
-    float *s_w1t = reinterpret_cast<float *>(smem + g.off_mlp);     // [128][hidden]
-    float *s_w2t = s_w1t + kCin * g.hidden;                          // [hidden][32]
-    float *s_b1 = s_w2t + g.hidden * kCout;                          // [hidden]
-    float *s_b2 = s_b1 + g.hidden;                                   // [32]
-    auto sfull = [&](int i) { return s_bar + 8u * i; };             // slab staged           (producers -> MMA)
-    auto sempty = [&](int i) { return s_bar + 8u * (2 + i); };      // slab consumed         (MMA commit -> producers)
+    float *s_w1t = reinterpret_cast<float *>(smem + g.off_mlp);     // [128][kW1Pitch]  (W1 transposed, 64 used columns)
+    float *s_w2t = s_w1t + kCin * kW1Pitch;                          // [64][kW2Pitch]   (W2 transposed, 32 used columns)
+    float *s_b1 = s_w2t + kMaxHidden * kW2Pitch;                     // [64]
+    float *s_b2 = s_b1 + kMaxHidden;                                 // [32]
+    auto sfull = [&](int i) { return s_bar + 8u * i; };             // slab staged           (TMA tx -> MMA)
+    auto sempty = [&](int i) { return s_bar + 8u * (2 + i); };      // slab consumed         (MMA commit -> TMA warp)
     auto afull = [&](int i) { return s_bar + 8u * (4 + i); };       // conv accumulator done (MMA commit -> epilogue)
     auto aempty = [&](int i) { return s_bar + 8u * (6 + i); };      // TMEM buffer drained   (epilogue -> MMA)
     auto gfull = [&](int i) { return s_bar + 8u * (8 + i); };       // gate values ready     (gate -> epilogue)
@@ -258,12 +298,12 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
     auto cfull = [&](int i) { return s_bar + 8u * (12 + i); };      // column sums done      (MMA commit -> gate)
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + g.off_bar + 128);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t plane = (uint32_t)g.px * 16u;
     const uint32_t acc_cols = (uint32_t)g.n_tiles * 32u + 2 * kSumCols;  // per TMEM buffer: conv tiles, then the two sum halves
 
     if (threadIdx.x == 0) {
+        tmap_prefetch(&xmap);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(sfull(i), kProd);
+            mbar_init(sfull(i), 1);
             mbar_init(sempty(i), 1);
             mbar_init(afull(i), 1);
             mbar_init(aempty(i), kEpi);
@@ -273,33 +313,22 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
         }
         fence_barrier_init();
     }
-    if (warp == 4) {
+    if (warp == 1) {
         __syncwarp();
         tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), g.tmem_cols);
     }
-    {   // weights -> smem as [tap][chunk c][n] x 16 B; zero the slack rows of both slabs once
+    {   // conv weights -> smem, per (tap, channel half) a K-major 128B-swizzled [32][64] block
         const bf16 *w = static_cast<const bf16 *>(a.w);          // [32][3][128]
         for (int idx = threadIdx.x; idx < kCout * kTaps * kPlanes; idx += kThreads) {
             const int c = idx % kPlanes, t = (idx / kPlanes) % kTaps, n = idx / (kPlanes * kTaps);
-            sts16(s_w + (uint32_t)(((t * kPlanes + c) * 32 + n) * 16), ldg16(w + ((long long)n * kTaps + t) * kCin + c * 8));
+            const int h = c >> 3, cc = c & 7;
+            sts16(s_w + (uint32_t)((t * 2 + h) * 4096 + n * 128 + ((cc ^ (n & 7)) << 4)), ldg16(w + ((long long)n * kTaps + t) * kCin + c * 8));
         }
-        // rows the copies never write: the d leading and P-T-d trailing rows of every segment band, and the
-        // slack behind the last band
-        const int rows = g.G * g.P, pad = g.P - g.T, slack = g.px - rows;
-        const int per_slab = g.G * pad + slack;
-        for (int idx = threadIdx.x; idx < 2 * per_slab * kPlanes; idx += kThreads) {
-            const int c = idx % kPlanes;
-            int p = idx / kPlanes;
-            const uint32_t sb = s_slab0 + (p >= per_slab ? g.slab_bytes : 0u);
-            if (p >= per_slab) p -= per_slab;
-            int row;
-            if (p < g.G * pad) {
-                const int gs = p / pad, e = p - gs * pad;
-                row = gs * g.P + (e < g.d ? e : g.T + e);
-            } else {
-                row = rows + (p - g.G * pad);
-            }
-            sts16(sb + c * plane + (uint32_t)row * 16u, make_uint4(0u, 0u, 0u, 0u));
+        // rows behind the last segment band are never written by TMA: zero them once (both buffers, both halves)
+        const int rows = g.G * g.P, slack = g.px - rows;
+        for (int idx = threadIdx.x; idx < 4 * slack * 8; idx += kThreads) {
+            const int c = idx & 7, p = (idx >> 3) % slack, hb = (idx >> 3) / slack;
+            sts16(s_slab0 + (uint32_t)hb * g.half_bytes + (uint32_t)(rows + p) * 128u + (uint32_t)c * 16u, make_uint4(0u, 0u, 0u, 0u));
         }
         // window indicator, K-major no-swizzle [k8 group][n = 16][8 rows]: 1 where slab row k is a frame of
         // (segment, window) n
@@ -324,83 +353,67 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
-        // =========================== producers (cp.async, zero-fill for the padding rows) ===========================
-        // thread = (plane c, row r mod 8); rows advance by 8 so (segment, frame) are tracked incrementally.  The
-        // copies signal the slab barrier themselves when they land: the threads never wait for their data.
-        const bf16 *x = static_cast<const bf16 *>(a.x) + a.in_choff + (threadIdx.x & 15) * 8;
-        const uint32_t c_off = (uint32_t)(threadIdx.x & 15) * plane;
-        const int r_first = threadIdx.x >> 4;                // 0..7
-        const int rows = g.G * g.P;
-        const long long seg_stride = (long long)g.T * a.in_ld;
-        uint32_t it = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            const int b0 = item * g.G;
-            const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
-            mbar_wait(sempty(buf), ph ^ 1u);
-            if (threadIdx.x == 0) CAM_TS(0);
-            const uint32_t sb = s_slab0 + buf * g.slab_bytes + c_off;
-            const bf16 *seg = x + (long long)b0 * seg_stride + (long long)r_first * a.in_ld;
-            uint32_t dst0 = sb + (uint32_t)(g.d + r_first) * 16u;
-            for (int gs = 0; gs < g.G; ++gs, seg += seg_stride, dst0 += (uint32_t)g.P * 16u) {
-                if (b0 + gs < a.B) {
-                    const bf16 *src = seg;
-                    uint32_t dst = dst0;
-                    for (int t = r_first; t < g.T; t += 8, src += 8 * (long long)a.in_ld, dst += 128u)
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-                } else {
-                    // ragged last item: rows of missing segments are zeros (their outputs are dropped, but they
-                    // must be finite for the column-sum MMAs, which run over all rows of the slab)
-                    for (int t = r_first; t < g.T; t += 8) sts16(dst0 + (uint32_t)(t - r_first) * 16u, make_uint4(0u, 0u, 0u, 0u));
-                    fence_proxy_async();
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (elect_one()) {
+            const uint32_t band_bytes = (uint32_t)g.P * 128u;
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const int b0 = item * g.G;
+                const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
+                mbar_wait(sempty(buf), ph ^ 1u);
+                CAM_TS(0);
+                mbar_arrive_expect_tx(sfull(buf), 2u * (uint32_t)g.G * band_bytes);
+                const uint32_t sb = s_slab0 + buf * g.slab_bytes;
+                for (int gs = 0; gs < g.G; ++gs) {
+                    tmap_load_3d(sb + (uint32_t)gs * band_bytes, &xmap, a.in_choff, -g.d, b0 + gs, sfull(buf));
+                    tmap_load_3d(sb + g.half_bytes + (uint32_t)gs * band_bytes, &xmap, a.in_choff + 64, -g.d, b0 + gs, sfull(buf));
                 }
+                CAM_TS(1);
             }
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(sfull(buf)) : "memory");
-            if (threadIdx.x == 0) CAM_TS(1);
         }
-        cp_async_wait_all();
-    } else if (warp == 4) {
+    } else if (warp == 1) {
         // =========================== MMA issuer ===========================
-        const uint32_t hi_a = desc_hi(128u), hi_b = desc_hi(128u);        // conv: K-major, 8-row groups 128 B apart
-        const uint32_t hi_at = desc_hi(plane);                             // sums: MN-major A, channel groups one plane apart
+        const uint32_t hi_sw = desc_hi_sw128(1024u);         // conv A and B: K-major SW128, 8-row groups 1024 B apart
+        const uint32_t hi_ind = desc_hi(128u);               // indicator: K-major no swizzle
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
             mbar_wait(aempty(buf), ph ^ 1u);
             mbar_wait(sfull(buf), ph);
-            fence_proxy_async();                             // cp.async (generic proxy) writes -> tensor-core reads
             tc_fence_after();
             CAM_TS(3);
             if (elect_one()) {
                 const uint32_t sb = s_slab0 + buf * g.slab_bytes;
                 const uint32_t tb = tmem_base + buf * acc_cols;
-                {   // column sums first: the gate warps start while the conv MMAs run.  Even and odd K steps go
-                    // to two accumulators; the gate threads add them.
-                    uint32_t lo_a = desc_lo(sb, 128u), lo_b = desc_lo(s_ind, 256u);
+                {   // column sums first: the gate warps start while the conv MMAs run.  A = the slab read MN-major
+                    // (64-channel groups one half apart, 8-row K groups 1024 B apart).  Even and odd K steps go to
+                    // two accumulators; the gate threads add them.
+                    uint32_t lo_a = desc_lo(sb, g.half_bytes), lo_b = desc_lo(s_ind, 256u);
                     const uint32_t dsum = tb + (uint32_t)g.n_tiles * 32u;
-                    umma_bf16(dsum, desc64(lo_a, hi_at), desc64(lo_b, hi_b), kIdescSum, 0u);
-                    if (g.k16 > 1) umma_bf16(dsum + kSumCols, desc64(lo_a + (256u >> 4), hi_at), desc64(lo_b + (512u >> 4), hi_b), kIdescSum, 0u);
+                    umma_bf16(dsum, desc64(lo_a, hi_sw), desc64(lo_b, hi_ind), kIdescSum, 0u);
+                    if (g.k16 > 1) umma_bf16(dsum + kSumCols, desc64(lo_a + (2048u >> 4), hi_sw), desc64(lo_b + (512u >> 4), hi_ind), kIdescSum, 0u);
                     for (int k = 2; k < g.k16; ++k) {
-                        lo_a += 256u >> 4;                   // 16 rows of 16 B
+                        lo_a += 2048u >> 4;                  // 16 rows of 128 B
                         lo_b += 512u >> 4;                   // two k8 groups of 16 x 16 B
-                        umma_bf16(dsum + (uint32_t)(k & 1) * kSumCols, desc64(lo_a + (256u >> 4), hi_at), desc64(lo_b + (512u >> 4), hi_b), kIdescSum, 1u);
+                        umma_bf16(dsum + (uint32_t)(k & 1) * kSumCols, desc64(lo_a + (2048u >> 4), hi_sw), desc64(lo_b + (512u >> 4), hi_ind), kIdescSum, 1u);
                     }
                     umma_commit(cfull(buf));
                 }
-                // conv: per 128-row tile, 3 taps x 8 K steps, fully unrolled (the issue rate of this thread is
-                // what bounds small-N MMAs, so the loop body is one add per operand)
-                const uint32_t step_a = (2u * plane) >> 4;
+                // conv: per 128-row tile, 3 taps x 2 halves x 4 K steps, fully unrolled
                 for (int t = 0; t < g.n_tiles; ++t) {
                     const uint32_t dcol = tb + (uint32_t)t * 32u;
 #pragma unroll
                     for (int k = 0; k < kTaps; ++k) {
-                        uint32_t lo_a = desc_lo(sb + (uint32_t)(t * 128 + k * g.d) * 16u, plane);
-                        const uint32_t lo_b = desc_lo(s_w + (uint32_t)(k * kPlanes * 32 * 16), 512u);
 #pragma unroll
-                        for (int j = 0; j < kCin / 16; ++j) {
-                            if (k == 0 && j == 0) umma_bf16(dcol, desc64(lo_a, hi_a), desc64(lo_b, hi_b), kIdescN32, 0u);
-                            else umma_acc(dcol, desc64(lo_a, hi_a), desc64(lo_b + (uint32_t)j * ((2u * 512u) >> 4), hi_b), kIdescN32);
-                            lo_a += step_a;
+                        for (int h = 0; h < 2; ++h) {
+                            const uint32_t lo_a = desc_lo(sb + (uint32_t)h * g.half_bytes + (uint32_t)(t * 128 + k * g.d) * 128u, 16u);
+                            const uint32_t lo_b = desc_lo(s_w + (uint32_t)((k * 2 + h) * 4096), 16u);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (k == 0 && h == 0 && j == 0) umma_bf16(dcol, desc64(lo_a, hi_sw), desc64(lo_b, hi_sw), kIdescN32, 0u);
+                                else umma_acc(dcol, desc64(lo_a + (uint32_t)j * 2u, hi_sw), desc64(lo_b + (uint32_t)j * 2u, hi_sw), kIdescN32);
+                            }
                         }
                     }
                 }
@@ -410,27 +423,38 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
             __syncwarp();
             CAM_TS(4);
         }
-    } else if (warp < 9) {
-        // =========================== context gate (warps 5-8, 128 threads) ===========================
+    } else if (warp < 6) {
+        // =========================== context gate (warps 2-5, 128 threads) ===========================
         // thread = one input channel: TMEM lane (warp & 3) * 32 + lane of the column-sum accumulator
-        const int gt = threadIdx.x - (kProd + 32);          // 0..127, the MLP work index
+        const int gt = threadIdx.x - 64;                    // 0..127, the MLP work index
         const int q = warp & 3, ch = q * 32 + lane;
-        {   // gate MLP parameters -> smem (overlaps the producers' first item)
-            const int n16 = (kCin * g.hidden + g.hidden * kCout + g.hidden + kCout) / 4;     // laid out back to back
-            const uint32_t dst = smem_u32(s_w1t);
-            for (int idx = gt; idx < n16; idx += kGate) {
-                const int e = idx * 4;
-                const float *src = e < kCin * g.hidden ? w1t + e
-                                 : e < kCin * g.hidden + g.hidden * kCout ? w2t + (e - kCin * g.hidden)
-                                 : e < kCin * g.hidden + g.hidden * kCout + g.hidden ? b1 + (e - kCin * g.hidden - g.hidden * kCout)
-                                 : b2 + (e - kCin * g.hidden - g.hidden * kCout - g.hidden);
-                cp_async16(dst + (uint32_t)e * 4u, src, 16u);
+        {   // gate MLP parameters -> smem with padded pitches (overlaps the first TMA loads)
+            const uint32_t d1 = smem_u32(s_w1t), d2 = smem_u32(s_w2t), d3 = smem_u32(s_b1), d4 = smem_u32(s_b2);
+            for (int idx = gt; idx < kCin * (g.hidden / 4); idx += kGate) {
+                const int row = idx / (g.hidden / 4), c = idx - row * (g.hidden / 4);
+                cp_async16(d1 + (uint32_t)(row * kW1Pitch + c * 4) * 4u, w1t + row * g.hidden + c * 4, 16u);
+            }
+            for (int idx = gt; idx < g.hidden * (kCout / 4); idx += kGate) {
+                const int row = idx / (kCout / 4), c = idx - row * (kCout / 4);
+                cp_async16(d2 + (uint32_t)(row * kW2Pitch + c * 4) * 4u, w2t + row * kCout + c * 4, 16u);
+            }
+            for (int idx = gt; idx < g.hidden / 4; idx += kGate) cp_async16(d3 + (uint32_t)idx * 16u, b1 + idx * 4, 16u);
+            for (int idx = gt; idx < kCout / 4; idx += kGate) cp_async16(d4 + (uint32_t)idx * 16u, b2 + idx * 4, 16u);
+            // rows of W1^T beyond `hidden` columns and rows of W2^T beyond `hidden` must read as zeros
+            if (g.hidden < kMaxHidden) {
+                for (int idx = gt; idx < kCin * (kMaxHidden - g.hidden); idx += kGate) {
+                    const int row = idx / (kMaxHidden - g.hidden), c = g.hidden + idx % (kMaxHidden - g.hidden);
+                    s_w1t[row * kW1Pitch + c] = 0.f;
+                }
+                for (int idx = gt; idx < (kMaxHidden - g.hidden) * kCout; idx += kGate)
+                    s_w2t[(g.hidden + idx / kCout) * kW2Pitch + (idx % kCout)] = 0.f;
             }
             cp_async_wait_all();
             gate_bar_sync();
         }
         const int nc = g.G * g.nwin;                        // (segment, window) combos of a full item
-        const float inv_T = 1.f / (float)g.T;
+        const float inv_T = 1.f / (float)g.T, inv_seg = 1.f / (float)g.seg_len;
+        const float inv_last = 1.f / (float)(g.T - (g.nwin - 1) * g.seg_len);
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
@@ -438,31 +462,22 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
             mbar_wait(cfull(buf), ph);
             tc_fence_after();
             if (gt == 0) CAM_TS(5);
-            {   // ---- ctx = mean over the segment + mean over the window, for this thread's channel
+            {   // ---- this thread's channel: window sums from TMEM -> contexts
                 uint32_t rr[16], ro[16];
                 const uint32_t ts = tmem_base + buf * acc_cols + (uint32_t)g.n_tiles * 32u + ((uint32_t)(q * 32) << 16);
                 tmem_ld16(ts, rr);
                 tmem_ld16(ts + kSumCols, ro);
                 tmem_ld_wait();
                 tc_fence_before();
-                float sums[kSumCols];
+                if (gt == 0) CAM_TS(2);
+                float sums[8];
 #pragma unroll
-                for (int e = 0; e < kSumCols; ++e) sums[e] = __uint_as_float(rr[e]) + (g.k16 > 1 ? __uint_as_float(ro[e]) : 0.f);
-                int cb = 0;
-                for (int gs = 0; gs < g.G; ++gs) {
-                    float tot = 0.f;
-#pragma unroll
-                    for (int e = 0; e < kSumCols; ++e)
-                        if (e >= cb && e < cb + g.nwin) tot += sums[e];
-                    tot *= inv_T;
-                    for (int w = 0; w < g.nwin; ++w, ++cb) {
-                        const int len = min(g.T, (w + 1) * g.seg_len) - w * g.seg_len;
-                        float sv = 0.f;
-#pragma unroll
-                        for (int e = 0; e < kSumCols; ++e)
-                            if (e == cb) sv = sums[e];
-                        win[cb * kCin + ch] = tot + sv / (float)len;
-                    }
+                for (int e = 0; e < 8; ++e) sums[e] = __uint_as_float(rr[e]) + (g.k16 > 1 ? __uint_as_float(ro[e]) : 0.f);
+                switch (g.nwin) {
+                    case 1: ctx_from_sums<1>(sums, win, g.G, ch, inv_T, inv_seg, inv_last); break;
+                    case 2: ctx_from_sums<2>(sums, win, g.G, ch, inv_T, inv_seg, inv_last); break;
+                    case 3: ctx_from_sums<3>(sums, win, g.G, ch, inv_T, inv_seg, inv_last); break;
+                    default: ctx_from_sums<4>(sums, win, g.G, ch, inv_T, inv_seg, inv_last); break;
                 }
             }
             if (gt == 0) CAM_TS(6);
@@ -470,21 +485,21 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
             gate_bar_sync();
             if (gt == 0) CAM_TS(7);
             switch (nc) {
-                case 1: gate_mlp<1>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                case 2: gate_mlp<2>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                case 3: gate_mlp<3>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                case 4: gate_mlp<4>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                case 5: gate_mlp<5>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                case 6: gate_mlp<6>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                case 7: gate_mlp<7>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                default: gate_mlp<8>(win, part, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 1: gate_mlp<1>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 2: gate_mlp<2>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 3: gate_mlp<3>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 4: gate_mlp<4>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 5: gate_mlp<5>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 6: gate_mlp<6>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 7: gate_mlp<7>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                default: gate_mlp<8>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
             }
             mbar_arrive(gfull(buf));
             if (gt == 0) CAM_TS(8);
         }
     } else {
-        // =========================== epilogue (warps 9-12, 128 threads) ===========================
-        const int q = warp & 3;                              // warps 9..12 -> TMEM lane quarters 1,2,3,0
+        // =========================== epilogue (warps 6-9, 128 threads) ===========================
+        const int q = warp & 3;                              // warps 6..9 -> TMEM lane quarters 2,3,0,1
         bf16 *y = static_cast<bf16 *>(a.y);
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -495,7 +510,7 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
             mbar_wait(gfull(buf), ph);
             mbar_wait(afull(buf), ph);
             tc_fence_after();
-            if (warp == 9) CAM_TS(9);
+            if (warp == 6) CAM_TS(9);
             for (int t = 0; t < g.n_tiles; ++t) {
                 const int r = t * 128 + q * 32 + lane;
                 const int gs = (int)__umulhi((unsigned)r, g.p_magic);
@@ -525,45 +540,67 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
             tc_fence_before();
             mbar_arrive(aempty(buf));
             mbar_arrive(gempty(buf));
-            if (warp == 9) CAM_TS(10);
+            if (warp == 6) CAM_TS(10);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, g.tmem_cols);
+    if (warp == 1) tmem_dealloc(tmem_base, g.tmem_cols);
 }
 
 bool geometry(const ConvArgs &a, int hidden, int seg_len, CamGeom &g) {
     g.T = a.W; g.d = a.dw; g.seg_len = seg_len; g.hidden = hidden;
     g.nwin = (g.T + seg_len - 1) / seg_len;
-    g.P = (g.T + 2 * g.d + 7) & ~7;
+    g.P = (g.T + 2 * g.d + 7) & ~7;             // band pitch: a multiple of the 8-row swizzle atom
+    if (g.P > 256) return false;                // one TMA box per segment and channel half
     g.G = std::min(kMaxSeg, 248 / g.P);
     if (g.G < 1 || g.nwin > kMaxWin || hidden > kMaxHidden || hidden < 4 || hidden % 4) return false;
     while (g.G * g.nwin > 8) --g.G;             // the gate MLP keeps at most 8 (segment, window) combos in registers
     g.n_tiles = (g.G * g.P + 127) / 128;
-    // rows the shifted views can touch: n_tiles*128 + 2d; planes padded to px = 1 (mod 8) rows so the
-    // sixteen planes of one row fall into different banks for the cp.async stores
-    int px = std::max(g.G * g.P, g.n_tiles * 128) + 2 * g.d;
-    px = ((px + 7) & ~7) + 1;
-    g.px = px;
+    // rows the shifted views can touch: n_tiles*128 + 2d, rounded to whole swizzle atoms
+    g.px = (std::max(g.G * g.P, g.n_tiles * 128) + 2 * g.d + 7) & ~7;
     g.p_magic = (unsigned)(((1ull << 32) + g.P - 1) / g.P);
-    g.slab_bytes = (uint32_t)px * 16u * kPlanes;
-    uint32_t off = 0;
-    auto take = [&](uint32_t bytes) { uint32_t o = off; off += (bytes + 127u) & ~127u; return o; };
-    g.off_w = take(kTaps * kPlanes * 32 * 16);
-    g.off_slab = take(2 * g.slab_bytes);
-    g.off_part = take(4 * 8 * kMaxHidden * 4);  // K-split partials of the gate MLP
-    g.off_win = take(g.G * g.nwin * kCin * 4);
+    g.half_bytes = (uint32_t)g.px * 128u;
+    g.slab_bytes = 2u * g.half_bytes;
     g.k16 = (g.G * g.P + 15) / 16;
+    uint32_t off = 0;
+    auto take = [&](uint32_t bytes) { uint32_t o = off; off += (bytes + 1023u) & ~1023u; return o; };
+    g.off_w = take(kTaps * 2 * 4096);
+    g.off_slab = take(2 * g.slab_bytes);
     g.off_ind = take(g.k16 * 2 * kSumCols * 16);
-    g.off_hid = take(8 * kMaxHidden * 4);
-    g.off_gate = take(2 * g.G * g.nwin * kCout * 4);
-    g.off_bar = take(256);
-    g.off_mlp = take((kCin * hidden + hidden * kCout + hidden + kCout) * 4);
+    g.off_mlp = take((kCin * kW1Pitch + kMaxHidden * kW2Pitch + kMaxHidden + kCout) * 4);
+    g.off_part = 0;
+    g.off_win = off; off += g.G * g.nwin * kCin * 4;
+    g.off_hid = off; off += 8 * kMaxHidden * 4;
+    g.off_gate = off; off += 2 * g.G * g.nwin * kCout * 4;
+    off = (off + 127u) & ~127u;
+    g.off_bar = off; off += 256;
     g.smem_bytes = (int)off;
     const int cols = 2 * (g.n_tiles * 32 + 2 * kSumCols);
     g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
     return g.smem_bytes <= 227 * 1024 && cols <= 512;
+}
+
+// {64 channels, P frames, 1 segment} boxes over the [B][T][ld] activation buffer, 128B swizzle
+int input_map(const ConvArgs &a, const CamGeom &g, CUtensorMap *out) {
+    typedef std::tuple<const void *, int, int, int, int> Key;
+    static std::mutex mu;
+    static std::map<Key, CUtensorMap> cache;
+    const Key key(a.x, a.in_ld, g.T, a.B, g.P);
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return SPK_OK;
+    }
+    const uint64_t dims[3] = {(uint64_t)a.in_ld, (uint64_t)g.T, (uint64_t)a.B};
+    const uint64_t strides[2] = {(uint64_t)a.in_ld * 2, (uint64_t)g.T * a.in_ld * 2};
+    const uint32_t box[3] = {64u, (uint32_t)g.P, 1u};
+    const int rc = tmap_encode_bf16(a.x, 3, dims, strides, box, 128, out);
+    if (rc != SPK_OK) return rc;
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = *out;
+    return SPK_OK;
 }
 
 }  // namespace
@@ -597,10 +634,13 @@ int launch_cam_local(const ConvArgs &a, const float *w1t, const float *b1, const
         set_error("cudaFuncSetAttribute(cam_local) failed: %s", cudaGetErrorString(attr_err));
         return SPK_ERR_CUDA;
     }
+    CUtensorMap xmap;
+    const int rc = input_map(a, g, &xmap);
+    if (rc != SPK_OK) return rc;
     const int items = (a.B + g.G - 1) / g.G;
     const int grid = std::min(items, sm_count());
     static const int dbg = getenv("SPK_CAM_DBG") ? atoi(getenv("SPK_CAM_DBG")) : 0;
-    cam_local_kernel<<<grid, kThreads, g.smem_bytes, s>>>(a, g, w1t, b1, w2t, b2, items, dbg);
+    cam_local_kernel<<<grid, kThreads, g.smem_bytes, s>>>(a, g, w1t, b1, w2t, b2, items, dbg, xmap);
     return check_launch("cam_local_kernel");
 }
 

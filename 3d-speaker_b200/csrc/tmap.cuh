@@ -1,0 +1,72 @@
+// Tensor-map (TMA descriptor) helpers shared by the slab kernels: host-side encode through the driver entry
+// point (no link-time libcuda dependency) and the device-side bulk tensor loads.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace spk {
+
+typedef CUresult (*TmapEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline TmapEncodeTiledFn tmap_encode_fn() {
+    static TmapEncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<TmapEncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// bf16 tensor of `rank` dims (innermost first; strides[i] = byte pitch of dim i+1), box in elements, zero fill
+// outside the tensor.  swizzle_bytes: 0, 32, 64 or 128.
+inline int tmap_encode_bf16(const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides, const uint32_t *box,
+                            int swizzle_bytes, CUtensorMap *out) {
+    TmapEncodeTiledFn fn = tmap_encode_fn();
+    if (fn == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return SPK_ERR_CUDA;
+    }
+    cuuint64_t d[5], st[4];
+    cuuint32_t b[5], es[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) st[i] = strides[i];
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(ptr), d, st, b, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank=%d dims=%llu,%llu,%llu box=%u,%u,%u", (int)r, rank,
+                  (unsigned long long)d[0], (unsigned long long)d[1], (unsigned long long)(rank > 2 ? d[2] : 0), b[0], b[1],
+                  rank > 2 ? b[2] : 0u);
+        return SPK_ERR_CUDA;
+    }
+    return SPK_OK;
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void tmap_prefetch(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tmap_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmap_load_4d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+#endif
+
+}  // namespace spk

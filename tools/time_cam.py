@@ -48,7 +48,7 @@ def main():
         _lib.lib().spk_debug_cam_timeline(ctypes.c_void_p(ts.ctypes.data))
         ts = ts.reshape(16, 12)
         t0 = ts[0, 0]
-        names = ["P.start", "P.issued", "P.landed", "M.start", "M.issued", "G.start", "G.sums", "G.mlp0", "G.done", "E.start", "E.done"]
+        names = ["P.start", "P.issued", "G.tmemld", "M.start", "M.issued", "G.start", "G.sums", "G.mlp0", "G.done", "E.start", "E.done"]
         print("item " + " ".join("%9s" % n for n in names) + "   (cycles since first producer start)")
         for i in range(6):
             print("%4d " % i + " ".join("%9d" % (ts[i, j] - t0) for j in range(11)))

@@ -7,6 +7,7 @@
 // workspace, sized for a sub-batch ('chunk') of segments so that producer->consumer traffic
 // between consecutive ops stays inside the 126 MB L2; the batch is walked chunk by chunk on the
 // caller's stream.  Nothing here allocates or synchronises at forward time.
+#include <cstdlib>
 #include <map>
 #include <vector>
 
@@ -287,7 +288,16 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                         rc = launch_cam_gate(cg, dt(o.in_buf), s);
                         if (rc != SPK_OK) break;
                     }
-                    if (m->precision == SPK_PREC_BF16 &&
+                    static const bool slab_v2 = [] { const char *e = getenv("SPK_SLAB_V2"); return e && e[0] == '1'; }();
+                    if (m->precision == SPK_PREC_BF16 && !slab_v2 &&
+                        conv_slab3_supported(a, dt(o.in_buf), dt(o.out_buf), dt(o.res_buf))) {
+                        const __nv_bfloat16 *wb = nullptr;
+                        rc = param_bf16(m, o.w, &wb, s);
+                        if (rc == SPK_OK) {
+                            a.w = wb;
+                            rc = launch_conv_slab3(a, s);
+                        }
+                    } else if (m->precision == SPK_PREC_BF16 &&
                         conv_slab_supported(a, dt(o.in_buf), dt(o.out_buf), dt(o.res_buf))) {
                         const __nv_bfloat16 *wb = nullptr;
                         rc = param_bf16(m, o.w, &wb, s);

@@ -33,6 +33,9 @@ int launch_conv_gemm(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream
 // slab kernel for the Cin=Cout=32 2-D convs of the CAM++ head (conv_slab.cu)
 bool conv_slab_supported(const ConvArgs &a, int in_dtype, int out_dtype, int res_dtype);
 int launch_conv_slab(const ConvArgs &a, cudaStream_t s);
+// third generation of the same (conv_slab3.cu): TMA-staged 64B-swizzled slabs, lean MMA issue
+bool conv_slab3_supported(const ConvArgs &a, int in_dtype, int out_dtype, int res_dtype);
+int launch_conv_slab3(const ConvArgs &a, cudaStream_t s);
 
 // fused CAM layer (cam_local.cu): dilated k=3 conv (128->32) + context gate + gating multiply
 bool cam_local_supported(const ConvArgs &a, int in_dtype, int out_dtype, int hidden, int seg_len);

@@ -17,6 +17,7 @@
 // Warp roles (320 threads, one persistent CTA per SM): 0 TMA producer, 1 TMEM alloc + MMA issue,
 // 2-5 transform, 6-9 epilogue (folded BN, residual, activation, CAM gate; double-buffered TMEM
 // accumulator so the epilogue of tile i overlaps the mainloop of tile i+1).
+#include <cstdlib>
 #include <cuda.h>
 
 #include <algorithm>
@@ -137,6 +138,10 @@ __device__ __forceinline__ uint32_t bnrelu2(uint32_t x, uint32_t s, uint32_t b, 
     return *reinterpret_cast<uint32_t *>(&r);
 }
 
+// debug aid: per-stage role timestamps of CTA 0 (SPK_GEMM_DBG=1), read back by spk_debug_gemm_timeline
+__device__ long long g_gemm_ts[256 * 8];
+#define GEMM_TS(idx, slot) do { if (dbg && blockIdx.x == 0 && (idx) < 256 && (threadIdx.x & 31) == 0) g_gemm_ts[(idx) * 8 + (slot)] = clock64(); } while (0)
+
 template <int BLOCK_N> struct Cfg {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
@@ -150,7 +155,7 @@ template <int BLOCK_N, typename TOut, typename TRes>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const bf16 *__restrict__ pro_shift_bf,
                  int n_tiles_n, long long n_tiles, const __grid_constant__ CUtensorMap amap,
-                 const __grid_constant__ CUtensorMap wmap) {
+                 const __grid_constant__ CUtensorMap wmap, int dbg) {
     using C = Cfg<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -192,13 +197,14 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
     if (warp == 0) {
         // =========================== TMA producer ===========================
         if (lane == 0) {
-            int stage = 0;
+            int stage = 0, sidx = 0;
             uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const long long mt = tile / n_tiles_n;
                 const int nt = (int)(tile - mt * n_tiles_n);
-                for (int kc = 0; kc < nk; ++kc) {
+                for (int kc = 0; kc < nk; ++kc, ++sidx) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
+                    GEMM_TS(sidx, 0);
                     const uint32_t sa = base + stage * C::kStageBytes;
                     mbar_arrive_expect_tx(land_bar(stage), C::kStageBytes);
                     tma_load_2d(sa, &amap, kc * BLOCK_K, (int)(mt * BLOCK_M), land_bar(stage));
@@ -210,16 +216,18 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         constexpr uint32_t idesc = make_idesc(BLOCK_N);
-        int stage = 0;
+        int stage = 0, sidx = 0;
         uint32_t phase = 0, it = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const uint32_t buf = it & 1u, acc_phase = (it >> 1) & 1u;
             mbar_wait(acce_bar(buf), acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
-            for (int kc = 0; kc < nk; ++kc) {
+            for (int kc = 0; kc < nk; ++kc, ++sidx) {
+                GEMM_TS(sidx, 3);
                 mbar_wait(has_pro ? ready_bar(stage) : land_bar(stage), phase);
                 tc_fence_after();
+                GEMM_TS(sidx, 4);
                 if (lane == 0) {
                     const uint32_t sa = base + stage * C::kStageBytes;
                     const uint64_t ad = make_desc_sw128(sa), bd = make_desc_sw128(sa + C::kABytes);
@@ -230,6 +238,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                     if (kc == nk - 1) umma_commit(accf_bar(buf));
                 }
                 __syncwarp();
+                GEMM_TS(sidx, 5);
                 if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -240,10 +249,10 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
             const int j = t & 7, r0 = t >> 3;          // 16-byte column j, rows r0 + 16*i
             const uint32_t sw_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((j ^ (r0 & 7)) << 4));
             const bool relu = a.pro_relu != 0;
-            int stage = 0;
+            int stage = 0, sidx = 0;
             uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int kc = 0; kc < nk; ++kc) {
+                for (int kc = 0; kc < nk; ++kc, ++sidx) {
                     // scale/shift of this thread's 8 channels (zero beyond K: relu(0*x+0) = 0)
                     const int c = kc * BLOCK_K + j * 8;
                     uint4 s4 = make_uint4(0u, 0u, 0u, 0u), h4 = s4;
@@ -252,6 +261,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                         h4 = ldg16(pro_shift_bf + c);
                     }
                     mbar_wait(land_bar(stage), phase);
+                    if (t == 0) GEMM_TS(sidx, 1);
                     const uint32_t sa = base + stage * C::kStageBytes + sw_off;
                     uint4 v[8];
 #pragma unroll
@@ -266,6 +276,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                     }
                     fence_proxy_async();
                     mbar_arrive(ready_bar(stage));
+                    if (t == 0) GEMM_TS(sidx, 2);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -292,6 +303,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
             }
             mbar_wait(accf_bar(buf), acc_phase);
             tc_fence_after();
+            if (warp == 6) GEMM_TS(it, 6);
             const uint32_t taddr = tmem_base + buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
             for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
@@ -340,6 +352,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
             }
             tc_fence_before();
             mbar_arrive(acce_bar(buf));
+            if (warp == 6) GEMM_TS(it, 7);
         }
     }
 
@@ -429,7 +442,8 @@ int launch_one(const ConvArgs &a, cudaStream_t s) {
     const int ntn = (a.Cout + BLOCK_N - 1) / BLOCK_N;
     const long long tiles = mt * ntn;
     const long long grid = std::min<long long>(tiles, sm_count());
-    kern<<<(unsigned)grid, kThreads, C::kSmemBytes, s>>>(a, ps, ph, ntn, tiles, amap, wmap);
+    static const int dbg = getenv("SPK_GEMM_DBG") ? atoi(getenv("SPK_GEMM_DBG")) : 0;
+    kern<<<(unsigned)grid, kThreads, C::kSmemBytes, s>>>(a, ps, ph, ntn, tiles, amap, wmap, dbg);
     return check_launch("conv_gemm_kernel");
 }
 
@@ -465,3 +479,8 @@ int launch_conv_gemm(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream
 }
 
 }  // namespace spk
+
+// debug aid (not part of the ABI)
+extern "C" int spk_debug_gemm_timeline(long long *dst) {
+    return cudaMemcpyFromSymbol(dst, spk::g_gemm_ts, sizeof(long long) * 256 * 8) == cudaSuccess ? 0 : -1;
+}

@@ -216,6 +216,67 @@ stem_kernel(const StemArgs a) {
     }
 }
 
+// Register-tiled stem for Cout = 8*CG (CG = 4 or 8).  A CTA is one segment x 16 frequency rows (2 per warp); the
+// 18 input rows are staged once in shared memory (10-18 adjacent floats of every frame: the [T,F] -> [F,T]
+// transpose happens here).  A thread owns 8 output channels - their 72 weights and the folded BN live in
+// registers - and walks along time: lane = (channel group, pixel), so one warp step writes 32/CG consecutive
+// pixels x Cout channels = 512 contiguous bytes (bf16).  Per (pixel, 8 channels): 9 broadcast LDS + 80 FMA.
+constexpr int kStemRows = 16;
+template <typename TOut, int CG>
+__global__ void __launch_bounds__(256)
+stem_tiled_kernel(const StemArgs a) {
+    extern __shared__ float rows[];          // [kStemRows + 2][Tp]  zero padded
+    const int Tp = a.T + 2;
+    const int fblocks = (a.F + kStemRows - 1) / kStemRows;
+    const int fb = blockIdx.x % fblocks, b = blockIdx.x / fblocks;
+    const int f0 = fb * kStemRows;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cg = lane % CG, p = lane / CG;
+    constexpr int PIX = 32 / CG;             // pixels per warp step
+    const int c0 = cg * 8;
+    float w[9][8], sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k][j] = __ldg(a.w + (c0 + j) * 9 + k);
+        sc[j] = a.scale ? __ldg(a.scale + c0 + j) : 1.f;
+        sh[j] = a.shift ? __ldg(a.shift + c0 + j) : 0.f;
+    }
+    const float *fe = a.feats + (size_t)b * a.T * a.F;
+    constexpr int NR = kStemRows + 2;
+    for (int i = threadIdx.x; i < NR * Tp; i += blockDim.x) {
+        const int tt = i / NR - 1, r = i % NR, ff = f0 + r - 1;         // r fastest: adjacent floats of one frame
+        rows[r * Tp + tt + 1] = (ff >= 0 && ff < a.F && tt >= 0 && tt < a.T) ? __ldg(fe + (size_t)tt * a.F + ff) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int rr = 0; rr < 2; ++rr) {
+        const int r = warp * 2 + rr, f = f0 + r;
+        if (f >= a.F) break;
+        TOut *y = static_cast<TOut *>(a.y) + ((size_t)b * a.F + f) * a.T * a.out_ld + a.out_choff + c0;
+        const float *r0 = rows + r * Tp, *r1 = r0 + Tp, *r2 = r1 + Tp;
+        for (int t = p; t < a.T; t += PIX) {
+            const float in[9] = {r0[t], r0[t + 1], r0[t + 2], r1[t], r1[t + 1], r1[t + 2], r2[t], r2[t + 1], r2[t + 2]};
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = fmaf(in[k], w[k][j], o[j]);
+            float q0[4], q1[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                q0[j] = apply_act(fmaf(o[j], sc[j], sh[j]), a.act);
+                q1[j] = apply_act(fmaf(o[4 + j], sc[4 + j], sh[4 + j]), a.act);
+            }
+            TOut *yp = y + (size_t)t * a.out_ld;
+            Vec4<TOut>::store(yp, q0);
+            Vec4<TOut>::store(yp + 4, q1);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ CAM context gate
 // gate[b,w,:] = sigmoid(W2 relu(W1 (mean_T(x) + mean_{window w}(x)) + b1) + b2); one CTA of 256
 // threads per segment.  Column sums: thread (g, c4) adds rows g, g+G, ... of 4 adjacent
@@ -433,6 +494,18 @@ int launch_stem(const StemArgs &a, int out_dtype, cudaStream_t s) {
     if (blocks > 0x7fffffffll) {
         set_error("stem: batch too large");
         return SPK_ERR_UNSUPPORTED;
+    }
+    if ((a.Cout == 32 || a.Cout == 64) && (size_t)(kStemRows + 2) * (a.T + 2) * sizeof(float) <= 48 * 1024) {
+        const long long nb = (long long)a.B * ((a.F + kStemRows - 1) / kStemRows);
+        const size_t shb = (size_t)(kStemRows + 2) * (a.T + 2) * sizeof(float);
+        if (a.Cout == 32) {
+            if (out_dtype == SPK_DT_F32) stem_tiled_kernel<float, 4><<<(unsigned)nb, 256, shb, s>>>(a);
+            else stem_tiled_kernel<bf16, 4><<<(unsigned)nb, 256, shb, s>>>(a);
+        } else {
+            if (out_dtype == SPK_DT_F32) stem_tiled_kernel<float, 8><<<(unsigned)nb, 256, shb, s>>>(a);
+            else stem_tiled_kernel<bf16, 8><<<(unsigned)nb, 256, shb, s>>>(a);
+        }
+        return check_launch("stem_tiled_kernel");
     }
     const size_t sh = ((size_t)a.Cout * 11 + 3 * (a.T + 2)) * sizeof(float);
     if (sh > 48 * 1024) {

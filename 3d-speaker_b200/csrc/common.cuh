@@ -64,6 +64,21 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return v;
 }
 
+// the same on a register array, with the (warp-uniform) activation switch taken once instead of per element
+template <int N>
+__device__ __forceinline__ void apply_act_vec(float (&v)[N], int act) {
+    if (act == SPK_ACT_RELU) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) v[e] = fmaxf(v[e], 0.f);
+    } else if (act == SPK_ACT_CLAMP20) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) v[e] = fminf(fmaxf(v[e], 0.f), 20.f);
+    } else if (act == SPK_ACT_SILU) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) v[e] = v[e] / (1.f + __expf(-v[e]));
+    }
+}
+
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace spk

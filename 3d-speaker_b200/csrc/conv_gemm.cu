@@ -330,8 +330,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
 #pragma unroll
                         for (int e = 0; e < 16; ++e) v[e] += to_f32(rp[e]);
                     }
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = apply_act(v[e], a.act);
+                    apply_act_vec(v, a.act);
                     if (grow != nullptr) {
 #pragma unroll
                         for (int e = 0; e < 16; e += 4) {

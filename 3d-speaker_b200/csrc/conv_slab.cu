@@ -310,8 +310,7 @@ conv_slab_kernel(const ConvArgs a, const SlabGeom g, long long n_items, int swap
                             }
                         }
                     }
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = apply_act(v[e], a.act);
+                    apply_act_vec(v, a.act);
                     bf16 *yp = y + opix * a.out_ld + a.out_choff;
 #pragma unroll
                     for (int e = 0; e < 32; e += 8)
@@ -558,8 +557,7 @@ conv_slab2_kernel(const ConvArgs a, const SlabGeom g, long long n_items) {
                             }
                         }
                     }
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = apply_act(v[e], a.act);
+                    apply_act_vec(v, a.act);
                     bf16 *yp = y + opix * a.out_ld + a.out_choff;
 #pragma unroll
                     for (int e = 0; e < 32; e += 8)

@@ -384,8 +384,7 @@ conv_tc_kernel(const ConvArgs a, int n_tiles_n, long long n_tiles) {
 #pragma unroll
                         for (int e = 0; e < 16; ++e) v[e] += to_f32(rp[e]);
                     }
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = apply_act(v[e], a.act);
+                    apply_act_vec(v, a.act);
                     if (grow != nullptr) {
 #pragma unroll
                         for (int e = 0; e < 16; e += 4) {

@@ -11,8 +11,12 @@
 // the loads need no registers and run a full stage ring (5-6 x 32 KB) ahead of the tensor core.
 // The pre-activation BatchNorm+ReLU of the dense block cannot be folded into the producer of
 // the concat buffer (every layer applies its own BN to all earlier channels), so four
-// "transform" warps rewrite the landed A tile in place with packed bf16x2 math
-// (HFMA2.BF16 + HMNMX2), fence it to the async proxy and hand it to the MMA warp.
+// "transform" warps apply it to the landed A tile with packed bf16x2 math (HFMA2.BF16 + HMNMX2).
+// For N <= 128 the transformed tile goes to TENSOR MEMORY (thread = tile row = TMEM lane,
+// tcgen05.st) and the MMA takes A from there: the kernel is bound by shared-memory bandwidth
+// (TMA writes + transform reads + MMA operand reads), and this drops the write-back and the MMA's
+// A read, 96 -> 64 KB of shared-memory traffic per 128x128x64 stage.  For N = 256 the accumulators
+// fill TMEM and the tile is rewritten in place in shared memory instead.
 //
 // Warp roles (320 threads, one persistent CTA per SM): 0 TMA producer, 1 TMEM alloc + MMA issue,
 // 2-5 transform, 6-9 epilogue (folded BN, residual, activation, CAM gate; double-buffered TMEM
@@ -34,7 +38,7 @@ using bf16 = __nv_bfloat16;
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 320;
+constexpr int kThreads = 448;      // 0 TMA, 1 MMA, 2-5 transform A, 6-9 epilogue, 10-13 transform B
 constexpr int kXformThreads = 128;
 constexpr int kEpilogueThreads = 128;
 constexpr uint32_t kSpinLimit = 1u << 26;
@@ -93,6 +97,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+          "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D (+)= A * B^T with A read from tensor memory (lane = row, one 32-bit column = two consecutive K elements)
+__device__ __forceinline__ void umma_bf16_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
     asm volatile(
@@ -101,6 +124,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// SW128 K-major descriptor from 32-bit halves (stepping K by 16 elements = +2 on the low half)
+__device__ __forceinline__ uint32_t sw128_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+constexpr uint32_t kSw128Hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
 }
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -147,7 +183,10 @@ template <int BLOCK_N> struct Cfg {
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
-    static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : 2 * BLOCK_N;
+    static constexpr bool kATmem = BLOCK_N <= 128;          // room for the A ring next to the two accumulators
+    static constexpr int kAColsPerStage = BLOCK_K / 2;       // two bf16 per 32-bit TMEM column
+    static constexpr int kTmemNeed = 2 * BLOCK_N + (kATmem ? kStages * kAColsPerStage : 0);
+    static constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
 };
 
@@ -188,6 +227,21 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
         prefetch_tmap(&wmap);
     }
     if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), C::kTmemCols);
+    // prologue scale/shift -> shared memory (zero beyond K: relu(0*x+0) = 0), read back as broadcast loads
+    const int nk_pre = (a.K + BLOCK_K - 1) / BLOCK_K;
+    const uint32_t s_pro = base + C::kStages * C::kStageBytes + 512u, pro_bytes = (uint32_t)nk_pre * 128u;
+    if (has_pro && C::kATmem) {
+        for (int idx = threadIdx.x; idx < nk_pre * 8; idx += kThreads) {
+            const int c = idx * 8;
+            uint4 s4 = make_uint4(0u, 0u, 0u, 0u), h4 = s4;
+            if (c < a.K) {
+                s4 = ldg16(pro_scale_bf + c);
+                h4 = ldg16(pro_shift_bf + c);
+            }
+            sts16(s_pro + (uint32_t)idx * 16u, s4);
+            sts16(s_pro + pro_bytes + (uint32_t)idx * 16u, h4);
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -228,12 +282,23 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                 mbar_wait(has_pro ? ready_bar(stage) : land_bar(stage), phase);
                 tc_fence_after();
                 GEMM_TS(sidx, 4);
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t sa = base + stage * C::kStageBytes;
-                    const uint64_t ad = make_desc_sw128(sa), bd = make_desc_sw128(sa + C::kABytes);
+                    const uint32_t lo_a = sw128_lo(sa), lo_b = sw128_lo(sa + C::kABytes);
+                    if (C::kATmem && has_pro) {          // A = the transformed tile in tensor memory
+                        const uint32_t ta = tmem_base + 2 * BLOCK_N + stage * C::kAColsPerStage;
+                        if (kc == 0) umma_bf16_ta(d_tmem, ta, desc64(lo_b, kSw128Hi), idesc, 0u);
+                        else umma_bf16_ta(d_tmem, ta, desc64(lo_b, kSw128Hi), idesc, 1u);
 #pragma unroll
-                    for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-                        umma_bf16(d_tmem, ad + 2u * kk, bd + 2u * kk, idesc, (kc > 0 || kk > 0) ? 1u : 0u);
+                        for (int kk = 1; kk < BLOCK_K / UMMA_K; ++kk)
+                            umma_bf16_ta(d_tmem, ta + kk * (UMMA_K / 2), desc64(lo_b + 2u * kk, kSw128Hi), idesc, 1u);
+                    } else {
+                        if (kc == 0) umma_bf16(d_tmem, desc64(lo_a, kSw128Hi), desc64(lo_b, kSw128Hi), idesc, 0u);
+                        else umma_bf16(d_tmem, desc64(lo_a, kSw128Hi), desc64(lo_b, kSw128Hi), idesc, 1u);
+#pragma unroll
+                        for (int kk = 1; kk < BLOCK_K / UMMA_K; ++kk)
+                            umma_bf16(d_tmem, desc64(lo_a + 2u * kk, kSw128Hi), desc64(lo_b + 2u * kk, kSw128Hi), idesc, 1u);
+                    }
                     umma_commit(empty_bar(stage));
                     if (kc == nk - 1) umma_commit(accf_bar(buf));
                 }
@@ -242,9 +307,44 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                 if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp < 6) {
-        // =========================== transform (BN-ReLU prologue, in place) ===========================
-        if (has_pro) {
+    } else if (warp < 6 || warp >= 10) {
+        // =========================== transform (BN-ReLU prologue) ===========================
+        // TMEM path: two groups of four warps (2-5 and 10-13) take alternate stages, so the latency of one stage's
+        // load -> math -> tcgen05.st chain overlaps the next stage's
+        if (has_pro && C::kATmem) {
+            // thread = tile row = TMEM lane: read the row's eight 16-byte chunks (swizzled), transform, store the
+            // 64 bf16 as 32 columns of this lane in the stage's TMEM slot
+            const int q = warp & 3, r = q * 32 + lane;
+            const int grp = warp >= 10 ? 1 : 0;
+            const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128), x = (uint32_t)(r & 7);
+            const bool relu = a.pro_relu != 0;
+            const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            const long long n_stage_uses = my_tiles * nk;
+            for (long long sidx = grp; sidx < n_stage_uses; sidx += 2) {
+                const int stage = (int)(sidx % C::kStages);
+                const uint32_t phase = (uint32_t)((sidx / C::kStages) & 1);
+                const int kc = (int)(sidx % nk);
+                mbar_wait(land_bar(stage), phase);
+                if (lane == 0 && q == 2) GEMM_TS(sidx, 1);
+                const uint32_t sa = base + stage * C::kStageBytes + row_off;
+                const uint32_t sp = s_pro + (uint32_t)kc * 128u;          // this stage's 64 scales, 64 shifts at +pro_bytes
+                uint32_t out[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint4 s4 = lds16(sp + j * 16), h4 = lds16(sp + pro_bytes + j * 16);
+                    const uint4 v = lds16(sa + (((uint32_t)j ^ x) << 4));
+                    out[4 * j] = bnrelu2(v.x, s4.x, h4.x, relu);
+                    out[4 * j + 1] = bnrelu2(v.y, s4.y, h4.y, relu);
+                    out[4 * j + 2] = bnrelu2(v.z, s4.z, h4.z, relu);
+                    out[4 * j + 3] = bnrelu2(v.w, s4.w, h4.w, relu);
+                }
+                tmem_st32(tmem_base + 2 * BLOCK_N + stage * C::kAColsPerStage + ((uint32_t)(q * 32) << 16), out);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(ready_bar(stage));
+                if (lane == 0 && q == 2) GEMM_TS(sidx, 2);
+            }
+        } else if (has_pro && warp < 6) {
             const int t = threadIdx.x - 64;            // 0..127
             const int j = t & 7, r0 = t >> 3;          // 16-byte column j, rows r0 + 16*i
             const uint32_t sw_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((j ^ (r0 & 7)) << 4));
@@ -261,7 +361,6 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                         h4 = ldg16(pro_shift_bf + c);
                     }
                     mbar_wait(land_bar(stage), phase);
-                    if (t == 0) GEMM_TS(sidx, 1);
                     const uint32_t sa = base + stage * C::kStageBytes + sw_off;
                     uint4 v[8];
 #pragma unroll
@@ -276,7 +375,6 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                     }
                     fence_proxy_async();
                     mbar_arrive(ready_bar(stage));
-                    if (t == 0) GEMM_TS(sidx, 2);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -422,7 +520,7 @@ int launch_one(const ConvArgs &a, cudaStream_t s) {
     auto kern = conv_gemm_kernel<BLOCK_N, TOut, TRes>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes); });
+    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
     if (attr_err != cudaSuccess) {
         set_error("cudaFuncSetAttribute(conv_gemm) failed: %s", cudaGetErrorString(attr_err));
         return SPK_ERR_CUDA;
@@ -441,8 +539,14 @@ int launch_one(const ConvArgs &a, cudaStream_t s) {
     const int ntn = (a.Cout + BLOCK_N - 1) / BLOCK_N;
     const long long tiles = mt * ntn;
     const long long grid = std::min<long long>(tiles, sm_count());
-    static const int dbg = getenv("SPK_GEMM_DBG") ? atoi(getenv("SPK_GEMM_DBG")) : 0;
-    kern<<<(unsigned)grid, kThreads, C::kSmemBytes, s>>>(a, ps, ph, ntn, tiles, amap, wmap, dbg);
+    static const int dbg_k = getenv("SPK_GEMM_DBG") ? atoi(getenv("SPK_GEMM_DBG")) : 0;      // timeline of launches with this K
+    const int dbg = dbg_k != 0 && dbg_k == a.K;
+    const int smem_bytes = C::kSmemBytes + 2 * ((a.K + BLOCK_K - 1) / BLOCK_K) * 128;      // + prologue scale/shift
+    if (smem_bytes > 227 * 1024) {
+        set_error("conv_gemm: K=%d too large for the shared-memory prologue tables", a.K);
+        return SPK_ERR_UNSUPPORTED;
+    }
+    kern<<<(unsigned)grid, kThreads, smem_bytes, s>>>(a, ps, ph, ntn, tiles, amap, wmap, dbg);
     return check_launch("conv_gemm_kernel");
 }
 

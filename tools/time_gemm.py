@@ -47,7 +47,7 @@ def main():
         ts = ts.reshape(256, 8)
         t0 = ts[0, 0]
         print("stage  P.issue  X.landed  X.done  M.wait  M.ready  M.issued   | per tile: E.start E.done")
-        for i in range(40):
+        for i in range(8, 48):
             print("%4d " % i + " ".join("%8d" % (ts[i, j] - t0) for j in range(6)) + "   | " + " ".join("%8d" % (ts[i, j] - t0) for j in (6, 7)))
 
 main()

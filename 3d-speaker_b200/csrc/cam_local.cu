@@ -501,6 +501,7 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
         // =========================== epilogue (warps 6-9, 128 threads) ===========================
         const int q = warp & 3;                              // warps 6..9 -> TMEM lane quarters 2,3,0,1
         bf16 *y = static_cast<bf16 *>(a.y);
+        const bool wide_st = (reinterpret_cast<uintptr_t>(a.y) & 31) == 0 && a.out_ld % 16 == 0 && a.out_choff % 16 == 0;
         uint32_t it = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int b0 = item * g.G;
@@ -531,10 +532,19 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(rr[e]) * gr[e];
                     bf16 *yp = y + ((long long)(b0 + gs) * g.T + u) * a.out_ld + a.out_choff;
+                    if (wide_st) {      // two full 32-byte sectors per lane instead of four half-sector stores
 #pragma unroll
-                    for (int e = 0; e < 32; e += 8)
-                        *reinterpret_cast<uint4 *>(yp + e) =
-                            make_uint4(pack2(v[e], v[e + 1]), pack2(v[e + 2], v[e + 3]), pack2(v[e + 4], v[e + 5]), pack2(v[e + 6], v[e + 7]));
+                        for (int e = 0; e < 32; e += 16)
+                            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yp + e), "r"(pack2(v[e], v[e + 1])),
+                                         "r"(pack2(v[e + 2], v[e + 3])), "r"(pack2(v[e + 4], v[e + 5])), "r"(pack2(v[e + 6], v[e + 7])),
+                                         "r"(pack2(v[e + 8], v[e + 9])), "r"(pack2(v[e + 10], v[e + 11])), "r"(pack2(v[e + 12], v[e + 13])),
+                                         "r"(pack2(v[e + 14], v[e + 15])) : "memory");
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 8)
+                            *reinterpret_cast<uint4 *>(yp + e) =
+                                make_uint4(pack2(v[e], v[e + 1]), pack2(v[e + 2], v[e + 3]), pack2(v[e + 4], v[e + 5]), pack2(v[e + 6], v[e + 7]));
+                    }
                 }
             }
             tc_fence_before();

@@ -386,6 +386,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
         const int HoWo = a.Ho * a.Wo;
         TOut *y = static_cast<TOut *>(a.y);
         const TRes *res = static_cast<const TRes *>(a.res);
+        const bool wide_st = sizeof(TOut) == 2 && (reinterpret_cast<uintptr_t>(a.y) & 31) == 0 && a.out_ld % 16 == 0 && a.out_choff % 16 == 0;
         uint32_t it = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const long long mt = tile / n_tiles_n;
@@ -403,47 +404,77 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
             tc_fence_after();
             if (warp == 6) GEMM_TS(it, 6);
             const uint32_t taddr = tmem_base + buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+            // 32 accumulator columns per step: both TMEM loads and the scale/shift loads are in flight together
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                 const int n = n0 + c0;
                 if (n >= a.Cout) break;
-                uint32_t r[16];
-                tmem_ld16(taddr + c0, r);
+                const bool second = n + 16 < a.Cout;         // Cout is a multiple of 16
+                uint32_t r[32];
+                {
+                    uint32_t (&r0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[0]);
+                    uint32_t (&r1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[16]);
+                    tmem_ld16(taddr + c0, r0);
+                    tmem_ld16(taddr + c0 + 16, r1);
+                }
+                float4 s4[8], h4[8];
+                if (a.epi_scale != nullptr) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int ne = (e < 4 || second) ? n + 4 * e : n;
+                        s4[e] = __ldg(reinterpret_cast<const float4 *>(a.epi_scale + ne));
+                        h4[e] = __ldg(reinterpret_cast<const float4 *>(a.epi_shift + ne));
+                    }
+                }
                 tmem_ld_wait();
                 if (m < a.M) {
-                    float v[16];
+                    float v[32];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+                    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
                     if (a.epi_scale != nullptr) {
 #pragma unroll
-                        for (int e = 0; e < 16; e += 4) {
-                            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(a.epi_scale + n + e));
-                            const float4 h4 = __ldg(reinterpret_cast<const float4 *>(a.epi_shift + n + e));
-                            v[e] = fmaf(v[e], s4.x, h4.x); v[e + 1] = fmaf(v[e + 1], s4.y, h4.y);
-                            v[e + 2] = fmaf(v[e + 2], s4.z, h4.z); v[e + 3] = fmaf(v[e + 3], s4.w, h4.w);
+                        for (int e = 0; e < 8; ++e) {
+                            v[4 * e] = fmaf(v[4 * e], s4[e].x, h4[e].x); v[4 * e + 1] = fmaf(v[4 * e + 1], s4[e].y, h4[e].y);
+                            v[4 * e + 2] = fmaf(v[4 * e + 2], s4[e].z, h4[e].z); v[4 * e + 3] = fmaf(v[4 * e + 3], s4[e].w, h4[e].w);
                         }
                     }
                     if (res != nullptr) {
                         const TRes *rp = res + m * a.res_ld + a.res_choff + n;
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] += to_f32(rp[e]);
+                        for (int e = 0; e < 32; ++e)
+                            if (e < 16 || second) v[e] += to_f32(rp[e]);
                     }
                     apply_act_vec(v, a.act);
                     if (grow != nullptr) {
 #pragma unroll
-                        for (int e = 0; e < 16; e += 4) {
-                            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(grow + n + e));
-                            v[e] *= g4.x; v[e + 1] *= g4.y; v[e + 2] *= g4.z; v[e + 3] *= g4.w;
+                        for (int e = 0; e < 32; e += 4) {
+                            if (e < 16 || second) {
+                                const float4 g4 = __ldg(reinterpret_cast<const float4 *>(grow + n + e));
+                                v[e] *= g4.x; v[e + 1] *= g4.y; v[e + 2] *= g4.z; v[e + 3] *= g4.w;
+                            }
                         }
                     }
                     TOut *yp = y + m * a.out_ld + a.out_choff + n;
-                    if constexpr (sizeof(TOut) == 2) {
-                        *reinterpret_cast<uint4 *>(yp) = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-                        *reinterpret_cast<uint4 *>(yp + 8) = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
-                    } else {
 #pragma unroll
-                        for (int e = 0; e < 16; e += 4)
-                            *reinterpret_cast<float4 *>(yp + e) = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                    for (int hb = 0; hb < 2; ++hb) {
+                        if (hb == 1 && !second) break;
+                        const float *vv = v + 16 * hb;
+                        TOut *yq = yp + 16 * hb;
+                        if constexpr (sizeof(TOut) == 2) {
+                            const uint4 lo = make_uint4(pack2(vv[0], vv[1]), pack2(vv[2], vv[3]), pack2(vv[4], vv[5]), pack2(vv[6], vv[7]));
+                            const uint4 hi = make_uint4(pack2(vv[8], vv[9]), pack2(vv[10], vv[11]), pack2(vv[12], vv[13]), pack2(vv[14], vv[15]));
+                            if (wide_st) {      // one full 32-byte sector per lane instead of two half-sector stores
+                                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yq), "r"(lo.x), "r"(lo.y),
+                                             "r"(lo.z), "r"(lo.w), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+                            } else {
+                                *reinterpret_cast<uint4 *>(yq) = lo;
+                                *reinterpret_cast<uint4 *>(yq + 8) = hi;
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; e += 4)
+                                *reinterpret_cast<float4 *>(yq + e) = make_float4(vv[e], vv[e + 1], vv[e + 2], vv[e + 3]);
+                        }
                     }
                 }
             }

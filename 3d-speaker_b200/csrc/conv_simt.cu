@@ -271,8 +271,15 @@ stem_tiled_kernel(const StemArgs a) {
                 q1[j] = apply_act(fmaf(o[4 + j], sc[4 + j], sh[4 + j]), a.act);
             }
             TOut *yp = y + (size_t)t * a.out_ld;
-            Vec4<TOut>::store(yp, q0);
-            Vec4<TOut>::store(yp + 4, q1);
+            if constexpr (sizeof(TOut) == 2) {      // 8 channels = one 16-byte store; a warp step is 512 contiguous bytes
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(q0[0], q0[1]), h1 = __floats2bfloat162_rn(q0[2], q0[3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(q1[0], q1[1]), h3 = __floats2bfloat162_rn(q1[2], q1[3]);
+                *reinterpret_cast<uint4 *>(yp) = make_uint4(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1),
+                                                            *reinterpret_cast<uint32_t *>(&h2), *reinterpret_cast<uint32_t *>(&h3));
+            } else {
+                Vec4<TOut>::store(yp, q0);
+                Vec4<TOut>::store(yp + 4, q1);
+            }
         }
     }
 }
@@ -394,6 +401,53 @@ stats_pool_kernel(const StatsPoolArgs a) {
         float *y = a.y + b * 2ll * a.G * a.C;
         y[(long long)g * a.C + c] = mu;
         y[(long long)(a.G + g) * a.C + c] = sqrtf(var + a.eps);
+    }
+}
+
+// Streaming variant: one CTA per (b, g), a thread owns channel PAIRS (8- or 4-byte loads, a position row is one
+// contiguous 2*C*sizeof(T)-byte read for the CTA) and walks the P positions once with the shifted-data sums
+//   s1 = sum (v - v0),  s2 = sum (v - v0)^2,   v0 = the first position's value
+// (no per-element division, and the shift removes the mean^2 >> variance cancellation of plain sum / sum-of-squares):
+//   mean = v0 + s1 / P,   M2 = s2 - s1^2 / P.
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+stats_pool_stream_kernel(const StatsPoolArgs a) {
+    const int g = blockIdx.x % a.G;
+    const long long b = blockIdx.x / a.G;
+    const TIn *x = static_cast<const TIn *>(a.x) + ((b * a.G + g) * a.P) * (long long)a.in_ld + a.in_choff;
+    float *y = a.y + b * 2ll * a.G * a.C;
+    const float inv_p = 1.f / (float)a.P;
+    const float denom = a.unbiased ? (float)(a.P - 1) : (float)a.P;
+    for (int c = 2 * threadIdx.x; c < a.C; c += 2 * blockDim.x) {
+        const TIn *xc = x + c;
+        float v0x, v0y;
+        if constexpr (sizeof(TIn) == 4) {
+            const float2 f = *reinterpret_cast<const float2 *>(xc);
+            v0x = f.x; v0y = f.y;
+        } else {
+            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(xc);
+            v0x = __low2float(h); v0y = __high2float(h);
+        }
+        float s1x = 0.f, s1y = 0.f, s2x = 0.f, s2y = 0.f;
+#pragma unroll 4
+        for (int p = 1; p < a.P; ++p) {
+            float vx, vy;
+            if constexpr (sizeof(TIn) == 4) {
+                const float2 f = *reinterpret_cast<const float2 *>(xc + (long long)p * a.in_ld);
+                vx = f.x; vy = f.y;
+            } else {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(xc + (long long)p * a.in_ld);
+                vx = __low2float(h); vy = __high2float(h);
+            }
+            const float dx = vx - v0x, dy = vy - v0y;
+            s1x += dx; s1y += dy;
+            s2x = fmaf(dx, dx, s2x); s2y = fmaf(dy, dy, s2y);
+        }
+        const float m2x = fmaxf(s2x - s1x * s1x * inv_p, 0.f), m2y = fmaxf(s2y - s1y * s1y * inv_p, 0.f);
+        y[(long long)g * a.C + c] = v0x + s1x * inv_p;
+        y[(long long)g * a.C + c + 1] = v0y + s1y * inv_p;
+        y[(long long)(a.G + g) * a.C + c] = sqrtf(m2x / denom + a.eps);
+        y[(long long)(a.G + g) * a.C + c + 1] = sqrtf(m2y / denom + a.eps);
     }
 }
 
@@ -540,6 +594,13 @@ int launch_stats_pool(const StatsPoolArgs &a, int in_dtype, cudaStream_t s) {
     if (a.G > 65535 || a.B > 65535) {
         set_error("stats_pool: grid too large (G=%d, B=%d)", a.G, a.B);
         return SPK_ERR_UNSUPPORTED;
+    }
+    if (a.C % 2 == 0 && a.in_ld % 2 == 0 && a.in_choff % 2 == 0 && (long long)a.B * a.G < 0x7fffffffll &&
+        (reinterpret_cast<uintptr_t>(a.x) & 7) == 0) {
+        const unsigned blocks = (unsigned)((long long)a.B * a.G);
+        if (in_dtype == SPK_DT_F32) stats_pool_stream_kernel<float><<<blocks, 256, 0, s>>>(a);
+        else stats_pool_stream_kernel<bf16><<<blocks, 256, 0, s>>>(a);
+        return check_launch("stats_pool_stream_kernel");
     }
     dim3 grid((a.C + 31) / 32, a.G, a.B);
     if (in_dtype == SPK_DT_F32) stats_pool_kernel<float><<<grid, 256, 0, s>>>(a);

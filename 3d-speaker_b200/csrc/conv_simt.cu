@@ -264,12 +264,10 @@ stem_tiled_kernel(const StemArgs a) {
             for (int k = 0; k < 9; ++k)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) o[j] = fmaf(in[k], w[k][j], o[j]);
-            float q0[4], q1[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                q0[j] = apply_act(fmaf(o[j], sc[j], sh[j]), a.act);
-                q1[j] = apply_act(fmaf(o[4 + j], sc[4 + j], sh[4 + j]), a.act);
-            }
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j], sc[j], sh[j]);
+            apply_act_vec(o, a.act);
+            const float q0[4] = {o[0], o[1], o[2], o[3]}, q1[4] = {o[4], o[5], o[6], o[7]};
             TOut *yp = y + (size_t)t * a.out_ld;
             if constexpr (sizeof(TOut) == 2) {      // 8 channels = one 16-byte store; a warp step is 512 contiguous bytes
                 __nv_bfloat162 h0 = __floats2bfloat162_rn(q0[0], q0[1]), h1 = __floats2bfloat162_rn(q0[2], q0[3]);

@@ -4,6 +4,8 @@ Python mirrors of the reference call sites over the C ABI of ``libb200spk.so``:
 
     FBank            <- speakerlab.process.processor.FBank
     CAMPPlus         <- speakerlab.models.campplus.DTDNN.CAMPPlus
+    ERes2NetV2       <- speakerlab.models.eres2net.ERes2NetV2.ERes2NetV2
+    ECAPA_TDNN       <- speakerlab.models.ecapa_tdnn.ECAPA_TDNN.ECAPA_TDNN
     SpectralCluster  <- speakerlab.process.cluster.SpectralCluster
     EmbeddingExtractor: the batched fbank -> model loop of
                      speakerlab/bin/infer_diarization.py:621-639 with host buffers in/out
@@ -15,8 +17,9 @@ from ._lib import SpkError, lib, LIB_PATH  # noqa: F401
 from .fbank import FBank, fbank_batch, num_frames  # noqa: F401
 from .campplus import CAMPPlus  # noqa: F401
 from .eres2netv2 import ERes2NetV2  # noqa: F401
+from .ecapa_tdnn import ECAPA_TDNN  # noqa: F401
 from .cluster import SpectralCluster, cosine_pairs  # noqa: F401
 from .extract import EmbeddingExtractor  # noqa: F401
 from .diarize import Diarizer, cut_windows, gather_embeddings, shard_range  # noqa: F401
 
-__all__ = ["FBank", "CAMPPlus", "ERes2NetV2", "SpectralCluster", "cosine_pairs", "EmbeddingExtractor", "Diarizer", "SpkError", "fbank_batch", "num_frames", "lib"]
+__all__ = ["FBank", "CAMPPlus", "ERes2NetV2", "ECAPA_TDNN", "SpectralCluster", "cosine_pairs", "EmbeddingExtractor", "Diarizer", "SpkError", "fbank_batch", "num_frames", "lib"]

@@ -620,6 +620,7 @@ bool cam_local_supported(const ConvArgs &a, int in_dtype, int out_dtype, int hid
     if (a.Cin != kCin || a.Cout != kCout || a.KH != 1 || a.KW != kTaps || a.H != 1 || a.Ho != 1) return false;
     if (a.sw != 1 || a.sh != 1 || a.pw != a.dw || a.dw < 1 || a.Wo != a.W) return false;
     if (a.pro_scale != nullptr || a.epi_scale != nullptr || a.res != nullptr || a.act != SPK_ACT_NONE) return false;
+    if (a.post_scale != nullptr || a.pad_reflect) return false;
     if (a.in_ld % 8 || a.in_choff % 8 || a.out_ld % 8 || a.out_choff % 8) return false;
     if ((reinterpret_cast<uintptr_t>(a.x) & 15) || (reinterpret_cast<uintptr_t>(a.y) & 15)) return false;
     if (seg_len < 1) return false;

@@ -61,6 +61,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == SPK_ACT_RELU) return fmaxf(v, 0.f);
     if (act == SPK_ACT_CLAMP20) return fminf(fmaxf(v, 0.f), 20.f);
     if (act == SPK_ACT_SILU) return v / (1.f + __expf(-v));
+    if (act == SPK_ACT_TANH) return tanhf(v);
     return v;
 }
 
@@ -76,6 +77,9 @@ __device__ __forceinline__ void apply_act_vec(float (&v)[N], int act) {
     } else if (act == SPK_ACT_SILU) {
 #pragma unroll
         for (int e = 0; e < N; ++e) v[e] = v[e] / (1.f + __expf(-v[e]));
+    } else if (act == SPK_ACT_TANH) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) v[e] = tanhf(v[e]);
     }
 }
 

@@ -444,8 +444,17 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                         for (int e = 0; e < 32; ++e)
                             if (e < 16 || second) v[e] += to_f32(rp[e]);
                     }
+                    if (grow != nullptr && a.gate_additive) {       // per-segment bias before the activation
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            if (e < 16 || second) {
+                                const float4 g4 = __ldg(reinterpret_cast<const float4 *>(grow + n + e));
+                                v[e] += g4.x; v[e + 1] += g4.y; v[e + 2] += g4.z; v[e + 3] += g4.w;
+                            }
+                        }
+                    }
                     apply_act_vec(v, a.act);
-                    if (grow != nullptr) {
+                    if (grow != nullptr && !a.gate_additive) {
 #pragma unroll
                         for (int e = 0; e < 32; e += 4) {
                             if (e < 16 || second) {
@@ -453,6 +462,18 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                                 v[e] *= g4.x; v[e + 1] *= g4.y; v[e + 2] *= g4.z; v[e + 3] *= g4.w;
                             }
                         }
+                    }
+                    if (a.post_scale != nullptr) {                   // conv -> act -> BN (-> act)
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            if (e < 16 || second) {
+                                const float4 p4 = __ldg(reinterpret_cast<const float4 *>(a.post_scale + n + e));
+                                const float4 q4 = __ldg(reinterpret_cast<const float4 *>(a.post_shift + n + e));
+                                v[e] = fmaf(v[e], p4.x, q4.x); v[e + 1] = fmaf(v[e + 1], p4.y, q4.y);
+                                v[e + 2] = fmaf(v[e + 2], p4.z, q4.z); v[e + 3] = fmaf(v[e + 3], p4.w, q4.w);
+                            }
+                        }
+                        apply_act_vec(v, a.post_act);
                     }
                     TOut *yp = y + m * a.out_ld + a.out_choff + n;
 #pragma unroll

@@ -88,7 +88,8 @@ conv_simt_kernel(const ConvArgs a) {
             const int c = k0 - tap * a.Cin + lk;
             const int kh = tap / a.KW, kw = tap - kh * a.KW;
             const int hi = lho * a.sh - a.ph + kh * a.dh;
-            const int wi = lwo * a.sw - a.pw + kw * a.dw;
+            int wi = lwo * a.sw - a.pw + kw * a.dw;
+            if (a.pad_reflect) wi = wi < 0 ? -wi : (wi >= a.W ? 2 * (a.W - 1) - wi : wi);
             if (lrow_ok && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
                 const TIn *src = xin + (((long long)lb * a.H + hi) * a.W + wi) * a.in_ld + a.in_choff + c;
                 Vec4<TIn>::load(src, av);
@@ -150,8 +151,10 @@ conv_simt_kernel(const ConvArgs a) {
             float v = acc[i][j];
             if (a.epi_scale != nullptr) v = fmaf(v, __ldg(a.epi_scale + n), __ldg(a.epi_shift + n));
             if (res != nullptr) v += to_f32(res[m * a.res_ld + a.res_choff + n]);
+            if (grow != nullptr && a.gate_additive) v += __ldg(grow + n);
             v = apply_act(v, a.act);
-            if (grow != nullptr) v *= __ldg(grow + n);
+            if (grow != nullptr && !a.gate_additive) v *= __ldg(grow + n);
+            if (a.post_scale != nullptr) v = apply_act(fmaf(v, __ldg(a.post_scale + n), __ldg(a.post_shift + n)), a.post_act);
             yout[m * a.out_ld + a.out_choff + n] = from_f32<TOut>(v);
         }
     }
@@ -327,7 +330,7 @@ cam_gate_kernel(const CamGateArgs a) {
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int w = 0; w < a.nwin; ++w) {
-        for (int c = threadIdx.x; c < C; c += blockDim.x) ctx[c] = tot[c] + win[w * C + c];
+        for (int c = threadIdx.x; c < C; c += blockDim.x) ctx[c] = a.se_mode ? tot[c] : tot[c] + win[w * C + c];
         __syncthreads();
         for (int j = warp; j < a.hidden; j += nwarps) {
             float s = 0.f;
@@ -398,7 +401,7 @@ stats_pool_kernel(const StatsPoolArgs a) {
         const float var = M2 / denom;
         float *y = a.y + b * 2ll * a.G * a.C;
         y[(long long)g * a.C + c] = mu;
-        y[(long long)(a.G + g) * a.C + c] = sqrtf(var + a.eps);
+        y[(long long)(a.G + g) * a.C + c] = a.var_floor > 0.f ? sqrtf(fmaxf(var, a.var_floor)) : sqrtf(var + a.eps);
     }
 }
 
@@ -444,8 +447,8 @@ stats_pool_stream_kernel(const StatsPoolArgs a) {
         const float m2x = fmaxf(s2x - s1x * s1x * inv_p, 0.f), m2y = fmaxf(s2y - s1y * s1y * inv_p, 0.f);
         y[(long long)g * a.C + c] = v0x + s1x * inv_p;
         y[(long long)g * a.C + c + 1] = v0y + s1y * inv_p;
-        y[(long long)(a.G + g) * a.C + c] = sqrtf(m2x / denom + a.eps);
-        y[(long long)(a.G + g) * a.C + c + 1] = sqrtf(m2y / denom + a.eps);
+        y[(long long)(a.G + g) * a.C + c] = a.var_floor > 0.f ? sqrtf(fmaxf(m2x / denom, a.var_floor)) : sqrtf(m2x / denom + a.eps);
+        y[(long long)(a.G + g) * a.C + c + 1] = a.var_floor > 0.f ? sqrtf(fmaxf(m2y / denom, a.var_floor)) : sqrtf(m2y / denom + a.eps);
     }
 }
 
@@ -463,6 +466,10 @@ aff_blend_kernel(const AffBlendArgs a) {
         const long long m = idx / cg;
         float xv[4], yv[4], zv[4], ov[4];
         Vec4<T>::load(x + m * a.x_ld + a.x_choff + c, xv);
+        if (y == nullptr) {                        // plain (dtype-converting) copy of a channel window
+            Vec4<TO>::store(o + m * a.out_ld + a.out_choff + c, xv);
+            continue;
+        }
         Vec4<T>::load(y + m * a.y_ld + a.y_choff + c, yv);
         if (z != nullptr) {
             Vec4<T>::load(z + m * a.z_ld + a.z_choff + c, zv);
@@ -617,6 +624,7 @@ int launch_aff_blend(const AffBlendArgs &a, int dtype, int out_dtype, cudaStream
     if (dtype == SPK_DT_F32 && out_dtype == SPK_DT_F32) aff_blend_kernel<float, float><<<g, 256, 0, s>>>(a);
     else if (dtype == SPK_DT_BF16 && out_dtype == SPK_DT_BF16) aff_blend_kernel<bf16, bf16><<<g, 256, 0, s>>>(a);
     else if (dtype == SPK_DT_BF16 && out_dtype == SPK_DT_F32) aff_blend_kernel<bf16, float><<<g, 256, 0, s>>>(a);
+    else if (dtype == SPK_DT_F32 && out_dtype == SPK_DT_BF16 && a.y == nullptr) aff_blend_kernel<float, bf16><<<g, 256, 0, s>>>(a);
     else {
         set_error("aff_blend: unsupported dtype combination");
         return SPK_ERR_UNSUPPORTED;

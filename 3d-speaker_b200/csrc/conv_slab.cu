@@ -672,6 +672,7 @@ bool conv_slab_supported(const ConvArgs &a, int in_dtype, int out_dtype, int res
     if (!((a.KH == 3 && a.KW == 3 && a.ph == 1 && a.pw == 1) || (a.KH == 1 && a.KW == 1 && a.ph == 0 && a.pw == 0))) return false;
     if (a.sw != 1 || (a.sh != 1 && a.sh != 2) || a.dh != 1 || a.dw != 1) return false;
     if (a.pro_scale != nullptr || a.gate != nullptr) return false;
+    if (a.post_scale != nullptr || a.pad_reflect) return false;
     if (a.in_ld % 8 || a.in_choff % 8 || a.out_ld % 8 || a.out_choff % 8) return false;
     if (a.res != nullptr && (a.res_ld % 8 || a.res_choff % 8)) return false;
     if (a.Wo != a.W || a.Ho != (a.H + 2 * a.ph - a.KH) / a.sh + 1) return false;

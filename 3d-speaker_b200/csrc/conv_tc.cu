@@ -466,7 +466,7 @@ int launch_conv_tc(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t
     if (a.M == 0) return SPK_OK;
     // the first-generation kernel below stays selectable for A/B runs (SPK_CONV_TC_V1=1)
     static const bool v1 = [] { const char *e = getenv("SPK_CONV_TC_V1"); return e && e[0] == '1'; }();
-    if (!v1) return launch_conv_tc2(a, out_dtype, res_dtype, s);
+    if (!v1 || a.post_scale != nullptr || a.pad_reflect || a.gate_additive) return launch_conv_tc2(a, out_dtype, res_dtype, s);
     const bool res_bf16 = a.res == nullptr ? (out_dtype == SPK_DT_BF16) : (res_dtype == SPK_DT_BF16);
     if (out_dtype == SPK_DT_BF16) {
         if (!res_bf16) {

@@ -230,7 +230,9 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
             }
 #pragma unroll
             for (int i = 0; i < kRowsPerThread; ++i) {
-                const int hi = hi0[i] + kh * a.dh, wi = wi0[i] + kw * a.dw;
+                const int hi = hi0[i] + kh * a.dh;
+                int wi = wi0[i] + kw * a.dw;
+                if (a.pad_reflect) wi = wi < 0 ? -wi : (wi >= a.W ? 2 * (a.W - 1) - wi : wi);
                 if (k_ok && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
                     const long long off = ((long long)pix0[i] + (long long)hi * a.W + wi) * a.in_ld + a.in_choff + c;
                     g.v[i] = ldg16(x + off);
@@ -384,13 +386,30 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
 #pragma unroll
                         for (int e = 0; e < 16; ++e) v[e] += to_f32(rp[e]);
                     }
+                    if (grow != nullptr && a.gate_additive) {
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            const float4 g4 = __ldg(reinterpret_cast<const float4 *>(grow + n + e));
+                            v[e] += g4.x; v[e + 1] += g4.y; v[e + 2] += g4.z; v[e + 3] += g4.w;
+                        }
+                    }
                     apply_act_vec(v, a.act);
-                    if (grow != nullptr) {
+                    if (grow != nullptr && !a.gate_additive) {
 #pragma unroll
                         for (int e = 0; e < 16; e += 4) {
                             const float4 g4 = __ldg(reinterpret_cast<const float4 *>(grow + n + e));
                             v[e] *= g4.x; v[e + 1] *= g4.y; v[e + 2] *= g4.z; v[e + 3] *= g4.w;
                         }
+                    }
+                    if (a.post_scale != nullptr) {                   // conv -> act -> BN (-> act)
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            const float4 p4 = __ldg(reinterpret_cast<const float4 *>(a.post_scale + n + e));
+                            const float4 q4 = __ldg(reinterpret_cast<const float4 *>(a.post_shift + n + e));
+                            v[e] = fmaf(v[e], p4.x, q4.x); v[e + 1] = fmaf(v[e + 1], p4.y, q4.y);
+                            v[e + 2] = fmaf(v[e + 2], p4.z, q4.z); v[e + 3] = fmaf(v[e + 3], p4.w, q4.w);
+                        }
+                        apply_act_vec(v, a.post_act);
                     }
                     TOut *yp = y + m * a.out_ld + a.out_choff + n;
                     if constexpr (sizeof(TOut) == 2) {

@@ -96,6 +96,7 @@ int validate(const spk_model *m, const spk_program &p) {
                 ok = ok && o.KH > 0 && o.KW > 0 && o.sh > 0 && o.sw > 0 && o.Cin > 0 && o.Cout > 0;
                 if (ok && m->param_n[o.w] != (int64_t)o.Cout * o.KH * o.KW * o.Cin) ok = false;
                 if (ok && o.gate_buf >= 0 && o.gate_win <= 0) ok = false;
+                ok = ok && par_ok(o.aux[0], true) && par_ok(o.aux[1], true) && ((o.aux[0] < 0) == (o.aux[1] < 0));
                 break;
             case SPK_OP_CAM_GATE:
                 for (int j = 0; j < 4; ++j) ok = ok && par_ok(o.aux[j], false);
@@ -109,6 +110,12 @@ int validate(const spk_model *m, const spk_program &p) {
                 break;
             case SPK_OP_STATS_POOL:
             case SPK_OP_AFF_BLEND:
+                break;
+            case SPK_OP_SE_SCALE:
+                ok = ok && o.gate_buf >= 0;
+                break;
+            case SPK_OP_ASP_POOL:
+                ok = ok && o.res_buf >= 0;
                 break;
             default:
                 ok = false;
@@ -260,6 +267,10 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                     a.pro_relu = o.pro_relu; a.act = o.act;
                     a.K = o.KH * o.KW * o.Cin;
                     a.M = (long long)n * o.Ho * o.Wo;
+                    if (o.kind == SPK_OP_CONV) {            // ECAPA extras (see b200spk.h)
+                        a.post_scale = param(m, o.aux[0]); a.post_shift = param(m, o.aux[1]);
+                        a.post_act = o.iaux[0]; a.pad_reflect = o.iaux[1]; a.gate_additive = o.iaux[2];
+                    }
                     if (o.kind == SPK_OP_CAM_LOCAL) {
                         const int hidden = o.iaux[0], seg_len = o.iaux[1];
                         a.gate_win = seg_len;
@@ -334,6 +345,7 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                     a.B = n; a.T = o.W; a.C = o.Cin; a.in_ld = o.in_ld; a.in_choff = o.in_choff;
                     a.hidden = o.iaux[0]; a.seg_len = o.iaux[1]; a.Cout = o.Cout;
                     a.nwin = (o.W + a.seg_len - 1) / a.seg_len;
+                    a.se_mode = o.iaux[2];
                     rc = launch_cam_gate(a, dt(o.in_buf), s);
                     break;
                 }
@@ -342,7 +354,7 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                     a.x = ptr(o.in_buf);
                     a.y = static_cast<float *>(ptr(o.out_buf));
                     a.B = n; a.G = o.H; a.P = o.W; a.C = o.Cin; a.in_ld = o.in_ld; a.in_choff = o.in_choff;
-                    a.unbiased = o.iaux[0]; a.eps = o.faux[0];
+                    a.unbiased = o.iaux[0]; a.eps = o.faux[0]; a.var_floor = o.faux[1];
                     rc = launch_stats_pool(a, dt(o.in_buf), s);
                     break;
                 }
@@ -353,6 +365,24 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                     a.x_ld = o.in_ld; a.x_choff = o.in_choff; a.y_ld = o.res_ld; a.y_choff = o.res_choff;
                     a.z_ld = o.iaux[0]; a.z_choff = o.iaux[1]; a.out_ld = o.out_ld; a.out_choff = o.out_choff;
                     rc = launch_aff_blend(a, dt(o.in_buf), dt(o.out_buf), s);
+                    break;
+                }
+                case SPK_OP_SE_SCALE: {
+                    SeScaleArgs a{};
+                    a.x = ptr(o.in_buf); a.res = ptr(o.res_buf); a.gate = static_cast<const float *>(ptr(o.gate_buf)); a.out = ptr(o.out_buf);
+                    a.B = n; a.P = o.H * o.W; a.C = o.Cin;
+                    a.x_ld = o.in_ld; a.x_choff = o.in_choff; a.res_ld = o.res_ld; a.res_choff = o.res_choff;
+                    a.out_ld = o.out_ld; a.out_choff = o.out_choff;
+                    rc = launch_se_scale(a, dt(o.in_buf), dt(o.res_buf), dt(o.out_buf), s);
+                    break;
+                }
+                case SPK_OP_ASP_POOL: {
+                    AspPoolArgs a{};
+                    a.logits = ptr(o.in_buf); a.x = ptr(o.res_buf); a.out = static_cast<float *>(ptr(o.out_buf));
+                    a.B = n; a.P = o.H * o.W; a.C = o.Cin;
+                    a.l_ld = o.in_ld; a.l_choff = o.in_choff; a.x_ld = o.res_ld; a.x_choff = o.res_choff;
+                    a.var_floor = o.faux[0];
+                    rc = launch_asp_pool(a, dt(o.in_buf), dt(o.res_buf), s);
                     break;
                 }
                 default:

@@ -17,6 +17,11 @@ struct ConvArgs {
     int gate_win, gate_nwin, pro_relu, act;
     int K;                // KH*KW*Cin
     long long M;          // B*Ho*Wo
+    // ECAPA-TDNN extras (speakerlab/models/ecapa_tdnn/ECAPA_TDNN.py): conv -> act -> BN blocks, reflect padding, ASP
+    const float *post_scale, *post_shift;   // per-output-channel affine applied AFTER the activation (TDNNBlock: conv-ReLU-BN)
+    int post_act;         // activation after that affine (tanh in the ASP attention)
+    int pad_reflect;      // out-of-range columns mirror (F.pad mode='reflect') instead of reading zero; W axis only
+    int gate_additive;    // gate[b, window, n] is ADDED before the activation (per-segment bias) instead of multiplied after
 };
 
 // fp32-accumulate CUDA-core implicit GEMM (exact-fp32 mode and odd shapes)
@@ -57,6 +62,7 @@ struct CamGateArgs {
     float *gate;          // [B,nwin,Cout]
     const float *w1, *b1, *w2, *b2;   // [hidden,C],[hidden],[Cout,hidden],[Cout]
     int B, T, C, in_ld, in_choff, hidden, Cout, seg_len, nwin;
+    int se_mode;          // squeeze-excitation: context = mean over all positions only (ECAPA SEBlock)
 };
 int launch_cam_gate(const CamGateArgs &a, int in_dtype, cudaStream_t s);
 
@@ -65,6 +71,7 @@ struct StatsPoolArgs {
     float *y;             // [B, 2, G, C]  (mean block then std block)
     int B, G, P, C, in_ld, in_choff, unbiased;
     float eps;            // std = sqrt(var + eps)
+    float var_floor;      // > 0: std = sqrt(max(var, var_floor)) instead (ECAPA ASP global context)
 };
 int launch_stats_pool(const StatsPoolArgs &a, int in_dtype, cudaStream_t s);
 
@@ -75,6 +82,26 @@ struct AffBlendArgs {
     int C, x_ld, x_choff, y_ld, y_choff, z_ld, z_choff, out_ld, out_choff;
 };
 int launch_aff_blend(const AffBlendArgs &a, int dtype, int out_dtype, cudaStream_t s);
+
+// out = x * gate[b, c] + res  (SEBlock scaling + block residual; res may be null)
+struct SeScaleArgs {
+    const void *x, *res;
+    const float *gate;    // [B, C]
+    void *out;
+    long long B;
+    int P, C, x_ld, x_choff, res_ld, res_choff, out_ld, out_choff;
+};
+int launch_se_scale(const SeScaleArgs &a, int dtype, int res_dtype, int out_dtype, cudaStream_t s);
+
+// attentive statistics: p = softmax over the P positions of logits[b, :, c]; out[b] = [sum p x | sqrt(max(sum p (x - mean)^2, floor))]
+struct AspPoolArgs {
+    const void *logits, *x;   // [B, P, ld]
+    float *out;               // [B, 2C]
+    long long B;
+    int P, C, l_ld, l_choff, x_ld, x_choff;
+    float var_floor;
+};
+int launch_asp_pool(const AspPoolArgs &a, int l_dtype, int x_dtype, cudaStream_t s);
 
 int launch_f32_to_bf16(const float *src, __nv_bfloat16 *dst, long long n, cudaStream_t s);
 int launch_widen(const void *src, int dtype, float *dst, long long n, cudaStream_t s);

@@ -89,10 +89,19 @@ enum {
     SPK_OP_CAM_GATE   = 3,  /* CAM context: mean_T + seg-mean -> 1x1 -> relu -> 1x1 -> sigmoid        */
     SPK_OP_STATS_POOL = 4,  /* mean / std over positions                                             */
     SPK_OP_AFF_BLEND  = 5,  /* x*g + y*(2-g), g = 1+tanh(z)  (fusion.py:22-28); z = none: x + y       */
-    SPK_OP_CAM_LOCAL  = 6   /* whole CAMLayer: dilated k=3 conv x context gate (layers.py:93-99); CONV fields +
+    SPK_OP_CAM_LOCAL  = 6,  /* whole CAMLayer: dilated k=3 conv x context gate (layers.py:93-99); CONV fields +
                                aux = w1,b1,w2,b2, iaux = hidden, seg_len, id(w1^T), id(w2^T); gate_buf = scratch for the unfused path */
+    SPK_OP_SE_SCALE   = 7,  /* out = in * gate[b, c] + res   (SEBlock + block residual, ECAPA_TDNN.py:222,345)    */
+    SPK_OP_ASP_POOL   = 8   /* softmax over positions of in (logits), weighted mean/std of res (ECAPA_TDNN.py:279-285);
+                               faux[0] = variance floor */
 };
-enum { SPK_ACT_NONE = 0, SPK_ACT_RELU = 1, SPK_ACT_CLAMP20 = 2, SPK_ACT_SILU = 3 };
+/* SPK_OP_CONV extras for ECAPA-TDNN: aux[0], aux[1] = per-channel scale/shift applied after the activation
+ * (TDNNBlock is conv -> ReLU -> BN), iaux[0] = activation after that affine, iaux[1] = 1: reflect padding along W,
+ * iaux[2] = 1: gate_buf is a per-segment additive bias applied before the activation.
+ * SPK_OP_CAM_GATE: iaux[2] = 1: squeeze-excitation mode (context = mean over all positions only).
+ * SPK_OP_STATS_POOL: faux[1] > 0: std = sqrt(max(var, faux[1])) (ASP global context).
+ * SPK_OP_AFF_BLEND: res_buf = -1: plain (dtype-converting) copy. */
+enum { SPK_ACT_NONE = 0, SPK_ACT_RELU = 1, SPK_ACT_CLAMP20 = 2, SPK_ACT_SILU = 3, SPK_ACT_TANH = 4 };
 
 typedef struct {
     int32_t kind;

@@ -94,6 +94,23 @@ def eres2netv2_cases():
     ]
 
 
+ECAPA_GAIN = 1.0    # same reasoning as ERES_GAIN: keeps the random residual stack out of the chaotic regime
+
+
+def import_ecapa():
+    from speakerlab.models.ecapa_tdnn.ECAPA_TDNN import ECAPA_TDNN
+    return ECAPA_TDNN
+
+
+def ecapa_cases():
+    """(name, ctor kwargs, batch, n_samples, weight seed)"""
+    return [
+        ("c512_t148", dict(channels=[512, 512, 512, 512, 1536]), 2, 24000, 301),
+        ("c1024_t148", dict(channels=[1024, 1024, 1024, 1024, 3072]), 2, 24000, 302),
+        ("c512_t298", dict(channels=[512, 512, 512, 512, 1536]), 1, 48000, 303),
+    ]
+
+
 def cluster_cases():
     """(name, N, D, K, seed, ctor kwargs)"""
     return [
@@ -190,6 +207,29 @@ def main():
     with open(os.path.join(OUT, "state_dict_layouts.json"), "w") as f:
         json.dump(layouts, f)
     print("eres2netv2 goldens:", [k for k in out if k.endswith(".emb")])
+
+    # ---- ECAPA-TDNN
+    ECAPA = import_ecapa()
+    out = {"versions": ver}
+    for name, kw, batch, n_samples, wseed in ecapa_cases():
+        torch.manual_seed(0)
+        model = ECAPA(80, lin_neurons=192, **kw).eval()
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        layouts["ecapa_c%d" % kw["channels"][0]] = {k: list(v) for k, v in shapes.items()}
+        sd = synth.fill_state_dict(shapes, wseed, randomize_bn=True, gain=ECAPA_GAIN)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        wavs = campplus_input(batch, n_samples, seed=wseed + 1000)
+        feats = torch.vmap(fb)(torch.from_numpy(wavs).unsqueeze(1))
+        with torch.no_grad():
+            e = model(feats)
+            e64 = model.double()(feats.double())
+        out[name + ".feats"] = feats.numpy()
+        out[name + ".emb"] = e.numpy()
+        out[name + ".emb_f64"] = e64.numpy()
+    np.savez_compressed(os.path.join(OUT, "ecapa.npz"), **out)
+    with open(os.path.join(OUT, "state_dict_layouts.json"), "w") as f:
+        json.dump(layouts, f)
+    print("ecapa goldens:", [k for k in out if k.endswith(".emb")])
 
     # ---- SpectralCluster
     out = {"versions": ver}

@@ -78,6 +78,17 @@ def test_state_dict_layout_is_the_reference_layout(golden_dir):
         assert all(list(sd[k].shape) == ref[k] for k in ref)
 
 
+def test_ecapa_state_dict_layout_is_the_reference_layout(golden_dir):
+    import json
+    lay = json.load(open(os.path.join(golden_dir, "state_dict_layouts.json")))
+    for c in (512, 1024):
+        sd = b200spk.ECAPA_TDNN(80, channels=[c, c, c, c, 3 * c]).state_dict()
+        ref = lay["ecapa_c%d" % c]
+        assert len(ref) == 231
+        assert list(sd.keys()) == list(ref.keys())
+        assert all(list(sd[k].shape) == ref[k] for k in ref)
+
+
 def test_fbank_mirror_interface():
     fb = b200spk.FBank(80, 16000, mean_nor=True)
     assert (fb.n_mels, fb.sample_rate, fb.mean_nor) == (80, 16000, True)

@@ -146,3 +146,16 @@ def test_eres2netv2_oracle_matches_reference(golden_dir, layouts, case):
     got = eres2netv2_oracle.forward(sd, gold[name + ".feats"], scale=kw["scale"]).numpy()
     ref = gold[name + ".emb"]
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-5
+
+
+@pytest.mark.parametrize("case", gen_golden.ecapa_cases(), ids=lambda c: c[0])
+def test_ecapa_oracle_matches_reference(golden_dir, layouts, case):
+    from oracle import ecapa_oracle
+    gold = np.load(os.path.join(golden_dir, "ecapa.npz"))
+    name, kw, batch, n_samples, wseed = case
+    sd = synth.fill_state_dict(layouts["ecapa_c%d" % kw["channels"][0]], wseed, randomize_bn=True, gain=gen_golden.ECAPA_GAIN)
+    got = ecapa_oracle.forward(sd, gold[name + ".feats"]).numpy()
+    ref = gold[name + ".emb"]
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-5
+    # the fp32 reference itself is within 1e-6 of the same graph in fp64: these test networks are well conditioned
+    assert np.linalg.norm(ref - gold[name + ".emb_f64"]) / np.linalg.norm(ref) < 1e-5

@@ -7,6 +7,7 @@ Python mirrors of the reference call sites over the C ABI of ``libb200spk.so``:
     ERes2NetV2       <- speakerlab.models.eres2net.ERes2NetV2.ERes2NetV2
     ECAPA_TDNN       <- speakerlab.models.ecapa_tdnn.ECAPA_TDNN.ECAPA_TDNN
     SpectralCluster  <- speakerlab.process.cluster.SpectralCluster
+    AHCluster, CommonClustering <- speakerlab.process.cluster.{AHCluster, CommonClustering}
     EmbeddingExtractor: the batched fbank -> model loop of
                      speakerlab/bin/infer_diarization.py:621-639 with host buffers in/out
 
@@ -18,8 +19,8 @@ from .fbank import FBank, fbank_batch, num_frames  # noqa: F401
 from .campplus import CAMPPlus  # noqa: F401
 from .eres2netv2 import ERes2NetV2  # noqa: F401
 from .ecapa_tdnn import ECAPA_TDNN  # noqa: F401
-from .cluster import SpectralCluster, cosine_pairs  # noqa: F401
+from .cluster import SpectralCluster, AHCluster, CommonClustering, cosine_pairs  # noqa: F401
 from .extract import EmbeddingExtractor  # noqa: F401
 from .diarize import Diarizer, cut_windows, gather_embeddings, shard_range  # noqa: F401
 
-__all__ = ["FBank", "CAMPPlus", "ERes2NetV2", "ECAPA_TDNN", "SpectralCluster", "cosine_pairs", "EmbeddingExtractor", "Diarizer", "SpkError", "fbank_batch", "num_frames", "lib"]
+__all__ = ["FBank", "CAMPPlus", "ERes2NetV2", "ECAPA_TDNN", "SpectralCluster", "AHCluster", "CommonClustering", "cosine_pairs", "EmbeddingExtractor", "Diarizer", "SpkError", "fbank_batch", "num_frames", "lib"]

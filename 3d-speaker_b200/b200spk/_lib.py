@@ -80,6 +80,8 @@ _SIGS = {
     "spk_fbank_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                 C.c_void_p]),
     "spk_fbank_host_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int]),
+    "spk_ahc_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
+    "spk_ahc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "spk_model_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "spk_model_destroy": (C.c_int, [C.c_void_p]),
     "spk_model_add_param": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_int64]),

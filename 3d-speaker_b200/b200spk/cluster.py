@@ -165,6 +165,112 @@ class SpectralCluster:
         return labels
 
 
+class AHCluster:
+    """Drop-in for ``speakerlab.process.cluster.AHCluster`` (cluster.py:139-156): average-linkage agglomerative
+    clustering on -cosine, cut at ``fix_cos_thr``.  The affinity GEMM and the whole merge loop run on the GPU
+    (``spk_ahc``); labels come back numbered by the smallest member index of each cluster (the reference's numbering
+    follows scipy's dendrogram order - callers only use label identity)."""
+
+    def __init__(self, fix_cos_thr=0.4, device="cuda:0"):
+        self.fix_cos_thr = fix_cos_thr
+        self.device = torch.device(device)
+        self.last = {}
+
+    def __call__(self, X, **kwargs):
+        if isinstance(X, torch.Tensor):
+            Xd = X.detach().to(self.device, torch.float32).contiguous()
+        else:
+            Xd = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32)).to(self.device)
+        N, D = Xd.shape
+        L = _lib.lib()
+        labels = torch.empty(N, dtype=torch.int32, device=self.device)
+        ws = torch.empty(int(L.spk_ahc_workspace_bytes(N, D)), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            k = _lib.check(L.spk_ahc(C.c_void_p(Xd.data_ptr()), N, D, C.c_float(self.fix_cos_thr), C.c_void_p(labels.data_ptr()),
+                                     C.c_void_p(ws.data_ptr()), ws.numel(), _lib.current_stream_ptr()))
+        self.last["k"] = int(k)
+        return labels.cpu().numpy().astype(np.int64)
+
+
+def _cosine_similarity(a, b):
+    """sklearn.metrics.pairwise.cosine_similarity on float32 rows: L2-normalise (zero rows stay zero), then dot."""
+    def norm(x):
+        x = np.asarray(x, dtype=np.float32)
+        n = np.sqrt((x * x).sum(axis=1, keepdims=True))
+        n[n == 0.0] = 1.0
+        return x / n
+    return norm(a) @ norm(b).T
+
+
+class CommonClustering:
+    """Drop-in for ``speakerlab.process.cluster.CommonClustering`` (cluster.py:158-239): dispatch to the GPU back end
+    (``spectral`` or ``AHC``; recordings shorter than ``cluster_line`` segments always take AHC), then the reference's
+    label post-processing - reassign clusters of at most ``min_cluster_size`` segments to the nearest major centroid,
+    merge clusters whose centroids are closer than ``mer_cos`` - restated with the same numpy arithmetic on the host
+    (O(N K D) on a handful of centroids: control-plane work on the labels, not the data path)."""
+
+    def __init__(self, cluster_type, cluster_line=40, mer_cos=None, min_cluster_size=4, device="cuda:0", **kwargs):
+        self.cluster_type = cluster_type
+        self.cluster_line = cluster_line
+        self.min_cluster_size = min_cluster_size
+        self.mer_cos = mer_cos
+        if self.cluster_type == 'spectral':
+            self.cluster = SpectralCluster(device=device, **kwargs)
+        elif self.cluster_type == 'AHC':
+            self.cluster = AHCluster(device=device, **kwargs)
+        else:
+            raise ValueError('%s is not currently supported.' % self.cluster_type)
+        self.cluster_for_short = AHCluster(device=device) if self.cluster_type != 'AHC' else self.cluster
+
+    def __call__(self, X, **kwargs):
+        assert len(X.shape) == 2, 'Shape of input should be [N, C]'
+        if X.shape[0] <= 1:
+            return np.zeros(X.shape[0], dtype=int)
+        X = np.asarray(X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else X)
+        if X.shape[0] < self.cluster_line:
+            labels = self.cluster_for_short(X)
+        else:
+            labels = self.cluster(X, **kwargs)
+        labels = np.array(labels, dtype=np.int64)
+        labels = self.filter_minor_cluster(labels, X, self.min_cluster_size)
+        if self.mer_cos is not None:
+            labels = self.merge_by_cos(labels, X, self.mer_cos)
+        return labels
+
+    def filter_minor_cluster(self, labels, x, min_cluster_size):
+        cset = np.unique(labels)
+        csize = np.array([(labels == i).sum() for i in cset])
+        minor_idx = np.where(csize <= self.min_cluster_size)[0]
+        if len(minor_idx) == 0:
+            return labels
+        minor_cset = cset[minor_idx]
+        major_idx = np.where(csize > self.min_cluster_size)[0]
+        if len(major_idx) == 0:
+            return np.zeros_like(labels)
+        major_cset = cset[major_idx]
+        major_center = np.stack([x[labels == i].mean(0) for i in major_cset])
+        for i in range(len(labels)):
+            if labels[i] in minor_cset:
+                cos_sim = _cosine_similarity(x[i][np.newaxis], major_center)
+                labels[i] = major_cset[cos_sim.argmax()]
+        return labels
+
+    def merge_by_cos(self, labels, x, cos_thr):
+        assert cos_thr > 0 and cos_thr <= 1
+        while True:
+            cset = np.unique(labels)
+            if len(cset) == 1:
+                break
+            centers = np.stack([x[labels == i].mean(0) for i in cset])
+            affinity = np.triu(_cosine_similarity(centers, centers), 1)
+            idx = np.unravel_index(np.argmax(affinity), affinity.shape)
+            if affinity[idx] < cos_thr:
+                break
+            c1, c2 = cset[np.array(idx)]
+            labels[labels == c2] = c1
+        return labels
+
+
 def cosine_pairs(E, a, b):
     """out[i] = cos(E[a[i]], E[b[i]]): trial scoring (speakerlab/bin/compute_score_metrics.py:113-114).
     E torch f32 [N, D] on the device, a/b int32 index tensors on the device."""

@@ -437,6 +437,200 @@ AffinityPlan affinity_plan(int64_t N, int64_t D) {
     return p;
 }
 
+// normalised rows -> cosine similarity S [Np x Np] (row pitch Np) in the workspace; shared by the spectral and AHC paths
+int cosine_matrix(const float *X, int64_t N, int64_t D, const AffinityPlan &p, char *ws, cudaStream_t s) {
+    bf16 *A = reinterpret_cast<bf16 *>(ws + p.off_a), *B = reinterpret_cast<bf16 *>(ws + p.off_b);
+    float *Xn = reinterpret_cast<float *>(ws + p.off_xn);
+    const int Np = p.Np, Dp = p.Dp;
+    float *S = reinterpret_cast<float *>(ws + p.off_s);
+    normalize_split_kernel<<<Np, 256, 0, s>>>(X, (int)N, (int)D, Np, Dp, p.tensor ? A : nullptr, p.tensor ? B : nullptr, Xn);
+    int rc = check_launch("normalize_split_kernel");
+    if (rc != SPK_OK) return rc;
+    ConvArgs a{};
+    a.y = S; a.B = 1; a.H = 1; a.W = Np; a.Ho = 1; a.Wo = Np; a.Cout = Np;
+    a.KH = a.KW = a.sh = a.sw = a.dh = a.dw = 1;
+    a.out_ld = Np; a.gate_win = 1; a.gate_nwin = 1; a.M = Np;
+    if (p.tensor) {
+        a.x = A; a.w = B; a.Cin = 6 * Dp; a.K = 6 * Dp; a.in_ld = 6 * Dp;
+        if (!conv_gemm_supported(a, SPK_DT_BF16)) {
+            set_error("affinity: GEMM shape not supported (N=%d, D=%d)", Np, Dp);
+            return SPK_ERR_UNSUPPORTED;
+        }
+        return launch_conv_gemm(a, SPK_DT_F32, SPK_DT_F32, s);
+    }
+    a.x = Xn; a.w = Xn; a.Cin = Dp; a.K = Dp; a.in_ld = Dp;
+    return launch_conv_simt(a, SPK_DT_F32, SPK_DT_F32, SPK_DT_F32, s);
+}
+
+// ------------------------------------------------------------------ agglomerative clustering (average linkage)
+// speakerlab/process/cluster.py:139-156: average-linkage AHC on the distance -cos, cut where the linkage distance
+// exceeds -fix_cos_thr.  UPGMA is monotone, so the flat clustering is "keep merging the closest pair while its
+// distance is <= the cut"; no dendrogram is stored.  The distance matrix lives in HBM/L2 (it IS the negated affinity);
+// every row keeps its nearest active neighbour, one persistent CTA runs the merge loop:
+//   argmin over rows -> Lance-Williams update of the merged row and column -> refresh the neighbours it invalidated.
+constexpr int kAhcThreads = 1024;
+constexpr float kAhcInf = 3.0e38f;
+
+__global__ void __launch_bounds__(256)
+ahc_init_kernel(float *Dm, int N, int ld, int *nn, float *nnd) {
+    __shared__ float s_v[256];
+    __shared__ int s_i[256];
+    const int i = blockIdx.x;
+    float *row = Dm + (size_t)i * ld;
+    float best = kAhcInf;
+    int bj = -1;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const float d = (j == i) ? kAhcInf : -row[j];
+        row[j] = d;
+        if (d < best) { best = d; bj = j; }
+    }
+    s_v[threadIdx.x] = best; s_i[threadIdx.x] = bj;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const float v = s_v[threadIdx.x + o];
+            const int k = s_i[threadIdx.x + o];
+            if (v < s_v[threadIdx.x] || (v == s_v[threadIdx.x] && k >= 0 && (s_i[threadIdx.x] < 0 || k < s_i[threadIdx.x]))) {
+                s_v[threadIdx.x] = v; s_i[threadIdx.x] = k;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { nn[i] = s_i[0]; nnd[i] = s_v[0]; }
+}
+
+// block-wide (value, index) argmin with ties to the smaller index; result broadcast through shared memory
+__device__ __forceinline__ void block_argmin(float &v, int &idx, float *s_v, int *s_i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov < v || (ov == v && oi >= 0 && (idx < 0 || oi < idx))) { v = ov; idx = oi; }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) { s_v[warp] = v; s_i[warp] = idx; }
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < (int)(blockDim.x >> 5) ? s_v[lane] : kAhcInf;
+        idx = lane < (int)(blockDim.x >> 5) ? s_i[lane] : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov < v || (ov == v && oi >= 0 && (idx < 0 || oi < idx))) { v = ov; idx = oi; }
+        }
+        if (lane == 0) { s_v[0] = v; s_i[0] = idx; }
+    }
+    __syncthreads();
+    v = s_v[0]; idx = s_i[0];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kAhcThreads, 1)
+ahc_merge_kernel(float *Dm, int N, int ld, int *nn, float *nnd, int *size, int *parent, float cut, int *labels, int *n_clusters) {
+    __shared__ float s_v[32];
+    __shared__ int s_i[32];
+    __shared__ int s_todo[kAhcThreads];
+    __shared__ int s_ntodo;
+    for (int k = threadIdx.x; k < N; k += blockDim.x) { size[k] = 1; parent[k] = k; }
+    __syncthreads();
+    for (int step = 0; step < N - 1; ++step) {
+        // ---- closest pair
+        float v = kAhcInf;
+        int i = -1;
+        for (int k = threadIdx.x; k < N; k += blockDim.x)
+            if (size[k] > 0 && (nnd[k] < v || (nnd[k] == v && (i < 0 || k < i)))) { v = nnd[k]; i = k; }
+        block_argmin(v, i, s_v, s_i);
+        if (i < 0 || !(v <= cut)) break;
+        const int j = nn[i];
+        const float ni = (float)size[i], nj = (float)size[j], inv = 1.f / (ni + nj);
+        if (threadIdx.x == 0) s_ntodo = 0;
+        __syncthreads();
+        // ---- Lance-Williams (average): d(i+j, k) = (ni d(i,k) + nj d(j,k)) / (ni + nj); row i becomes the merged cluster
+        float *ri = Dm + (size_t)i * ld, *rj = Dm + (size_t)j * ld;
+        float bv = kAhcInf;
+        int bk = -1;
+        for (int k = threadIdx.x; k < N; k += blockDim.x) {
+            if (size[k] <= 0 || k == i || k == j) continue;
+            const float d = (ni * ri[k] + nj * rj[k]) * inv;
+            ri[k] = d;
+            Dm[(size_t)k * ld + i] = d;
+            Dm[(size_t)k * ld + j] = kAhcInf;
+            if (d < bv || (d == bv && (bk < 0 || k < bk))) { bv = d; bk = k; }
+            // neighbour bookkeeping of row k
+            if (nn[k] == i || nn[k] == j) {
+                const int slot = atomicAdd(&s_ntodo, 1);
+                if (slot < kAhcThreads) s_todo[slot] = k;
+            } else if (d < nnd[k] || (d == nnd[k] && i < nn[k])) {
+                nn[k] = i; nnd[k] = d;
+            }
+        }
+        block_argmin(bv, bk, s_v, s_i);
+        if (threadIdx.x == 0) {
+            ri[j] = kAhcInf; rj[i] = kAhcInf;
+            nn[i] = bk; nnd[i] = bk >= 0 ? bv : kAhcInf;
+            size[i] += size[j]; size[j] = 0; parent[j] = i;
+            nnd[j] = kAhcInf; nn[j] = -1;
+        }
+        __syncthreads();
+        // ---- rows whose nearest neighbour was i or j: full rescan (rows are distinct, any order gives the same result)
+        const int ntodo = s_ntodo;
+        if (ntodo > kAhcThreads) {          // cannot happen for N <= kAhcThreads * (N / kAhcThreads); rescan everything
+            for (int k = 0; k < N; ++k) {
+                if (size[k] <= 0 || k == i) continue;
+                const float *rk = Dm + (size_t)k * ld;
+                float tv = kAhcInf; int tk = -1;
+                for (int q = threadIdx.x; q < N; q += blockDim.x)
+                    if (size[q] > 0 && q != k && (rk[q] < tv || (rk[q] == tv && (tk < 0 || q < tk)))) { tv = rk[q]; tk = q; }
+                block_argmin(tv, tk, s_v, s_i);
+                if (threadIdx.x == 0) { nn[k] = tk; nnd[k] = tk >= 0 ? tv : kAhcInf; }
+            }
+        } else {
+            for (int t = 0; t < ntodo; ++t) {
+                const int k = s_todo[t];
+                const float *rk = Dm + (size_t)k * ld;
+                float tv = kAhcInf; int tk = -1;
+                for (int q = threadIdx.x; q < N; q += blockDim.x)
+                    if (size[q] > 0 && q != k && (rk[q] < tv || (rk[q] == tv && (tk < 0 || q < tk)))) { tv = rk[q]; tk = q; }
+                block_argmin(tv, tk, s_v, s_i);
+                if (threadIdx.x == 0) { nn[k] = tk; nnd[k] = tk >= 0 ? tv : kAhcInf; }
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    // ---- flat labels: root of the merge chain, renumbered 0..K-1 in order of the smallest member index
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+        int r = k;
+        while (parent[r] != r) r = parent[r];
+        labels[k] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int next = 0;
+        for (int k = 0; k < N; ++k)
+            if (parent[k] == k) size[k] = -(++next);      // reuse size[] of the roots: -(new label + 1)
+        *n_clusters = next;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < N; k += blockDim.x) labels[k] = -size[labels[k]] - 1;
+}
+
+struct AhcPlan { AffinityPlan aff; int64_t off_nn, off_nnd, off_size, off_parent, off_k, total; };
+AhcPlan ahc_plan(int64_t N, int64_t D) {
+    AhcPlan p;
+    p.aff = affinity_plan(N, D);
+    int64_t cur = p.aff.total;
+    p.off_nn = cur; cur += align_up(N * 4, 256);
+    p.off_nnd = cur; cur += align_up(N * 4, 256);
+    p.off_size = cur; cur += align_up(N * 4, 256);
+    p.off_parent = cur; cur += align_up(N * 4, 256);
+    p.off_k = cur; cur += 256;
+    p.total = cur;
+    return p;
+}
+
 }  // namespace
 }  // namespace spk
 
@@ -462,28 +656,9 @@ extern "C" int spk_affinity_laplacian(const float *X, int64_t N, int64_t D, int6
         return SPK_ERR_WORKSPACE;
     }
     char *ws = static_cast<char *>(workspace);
-    bf16 *A = reinterpret_cast<bf16 *>(ws + p.off_a), *B = reinterpret_cast<bf16 *>(ws + p.off_b);
-    float *Xn = reinterpret_cast<float *>(ws + p.off_xn);
-    const int Np = p.Np, Dp = p.Dp;
+    const int Np = p.Np;
     float *S = reinterpret_cast<float *>(ws + p.off_s);     // affinity, pruned in place
-    normalize_split_kernel<<<Np, 256, 0, s>>>(X, (int)N, (int)D, Np, Dp, p.tensor ? A : nullptr, p.tensor ? B : nullptr, Xn);
-    rc = check_launch("normalize_split_kernel");
-    if (rc != SPK_OK) return rc;
-    ConvArgs a{};
-    a.y = S; a.B = 1; a.H = 1; a.W = Np; a.Ho = 1; a.Wo = Np; a.Cout = Np;
-    a.KH = a.KW = a.sh = a.sw = a.dh = a.dw = 1;
-    a.out_ld = Np; a.gate_win = 1; a.gate_nwin = 1; a.M = Np;
-    if (p.tensor) {
-        a.x = A; a.w = B; a.Cin = 6 * Dp; a.K = 6 * Dp; a.in_ld = 6 * Dp;
-        if (!conv_gemm_supported(a, SPK_DT_BF16)) {
-            set_error("affinity: GEMM shape not supported (N=%d, D=%d)", Np, Dp);
-            return SPK_ERR_UNSUPPORTED;
-        }
-        rc = launch_conv_gemm(a, SPK_DT_F32, SPK_DT_F32, s);
-    } else {
-        a.x = Xn; a.w = Xn; a.Cin = Dp; a.K = Dp; a.in_ld = Dp;
-        rc = launch_conv_simt(a, SPK_DT_F32, SPK_DT_F32, SPK_DT_F32, s);
-    }
+    rc = cosine_matrix(X, N, D, p, ws, s);
     if (rc != SPK_OK) return rc;
     const size_t sh = ((size_t)N + 256) * sizeof(unsigned);
     if (sh > 200 * 1024) {
@@ -725,4 +900,42 @@ extern "C" int spk_cosine_pairs(const float *E, int64_t N, int64_t D, const int3
     SPK_REQUIRE(blocks < (1ll << 31), "too many pairs for one call");
     cosine_pairs_kernel<<<(unsigned)blocks, 256, 0, s>>>(E, N, (int)D, a, b, n_pairs, out);
     return check_launch("cosine_pairs_kernel");
+}
+
+extern "C" int64_t spk_ahc_workspace_bytes(int64_t N, int64_t D) {
+    if (N <= 0 || D <= 0) return 0;
+    return ahc_plan(N, D).total;
+}
+
+// Average-linkage agglomerative clustering on -cos, cut at -cos_thr (AHCluster, cluster.py:139-156).
+// labels: device int32 [N], numbered by the smallest member index of each cluster; returns the number of clusters.
+extern "C" int spk_ahc(const float *X, int64_t N, int64_t D, float cos_thr, int32_t *labels, void *workspace,
+                       int64_t workspace_bytes, void *stream_) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    SPK_REQUIRE(X != nullptr && labels != nullptr, "null buffer");
+    SPK_REQUIRE(N >= 1 && D >= 1 && N < (1 << 24), "bad shape N=%lld D=%lld", (long long)N, (long long)D);
+    int rc = require_device();
+    if (rc != SPK_OK) return rc;
+    const AhcPlan p = ahc_plan(N, D);
+    if (workspace_bytes < p.total || workspace == nullptr) {
+        set_error("workspace too small: need %lld bytes", (long long)p.total);
+        return SPK_ERR_WORKSPACE;
+    }
+    char *ws = static_cast<char *>(workspace);
+    rc = cosine_matrix(X, N, D, p.aff, ws, s);
+    if (rc != SPK_OK) return rc;
+    float *S = reinterpret_cast<float *>(ws + p.aff.off_s);
+    int *nn = reinterpret_cast<int *>(ws + p.off_nn), *size = reinterpret_cast<int *>(ws + p.off_size);
+    int *parent = reinterpret_cast<int *>(ws + p.off_parent), *kdev = reinterpret_cast<int *>(ws + p.off_k);
+    float *nnd = reinterpret_cast<float *>(ws + p.off_nnd);
+    ahc_init_kernel<<<(unsigned)N, 256, 0, s>>>(S, (int)N, p.aff.Np, nn, nnd);
+    rc = check_launch("ahc_init_kernel");
+    if (rc != SPK_OK) return rc;
+    ahc_merge_kernel<<<1, kAhcThreads, 0, s>>>(S, (int)N, p.aff.Np, nn, nnd, size, parent, -cos_thr, labels, kdev);
+    rc = check_launch("ahc_merge_kernel");
+    if (rc != SPK_OK) return rc;
+    int k = 0;
+    SPK_CUDA_OK(cudaMemcpyAsync(&k, kdev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SPK_CUDA_OK(cudaStreamSynchronize(s));
+    return k;
 }

@@ -174,6 +174,13 @@ int spk_lanczos_extend(const float *L, int64_t N, int32_t k, int32_t m_from, int
 int spk_lanczos_ritz(int64_t N, int32_t k, int32_t m, const float *S_host, float *evecs, void *workspace,
                      int64_t workspace_bytes, void *stream);
 int32_t spk_lanczos_max_dim(int64_t N, int32_t k);
+/* Average-linkage agglomerative clustering on the distance -cos, cut where the linkage distance exceeds -cos_thr
+ * (AHCluster.__call__, speakerlab/process/cluster.py:139-156; the reference's default back end for short
+ * recordings, cluster.py:178-181, 189-190).  X: device [N,D] f32; labels: device int32 [N], clusters numbered
+ * by their smallest member index.  Returns the number of clusters (>= 1) or an error (synchronises the stream). */
+int64_t spk_ahc_workspace_bytes(int64_t N, int64_t D);
+int spk_ahc(const float *X, int64_t N, int64_t D, float cos_thr, int32_t *labels, void *workspace,
+            int64_t workspace_bytes, void *stream);
 /* Lloyd k-means on device points [N,d] f32 from caller-provided initial centres (host [k,d]);
  * stops when no label changes or the summed squared centre shift is <= tol.  labels: device
  * int32 [N].  Deterministic (fixed-order reductions).  Returns iterations run or an error. */

@@ -95,3 +95,69 @@ def match_labels(ref, got):
             nxt += 1
         out[got == g] = mapping[g]
     return out
+
+
+# ---------------------------------------------------------------------------- AHC / CommonClustering
+def ahc(X, fix_cos_thr=0.4):
+    """AHCluster.__call__ (speakerlab/process/cluster.py:139-156) with scipy's average linkage standing in for
+    fastcluster.linkage (same algorithm and output format; fastcluster is not installed here)."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    from scipy.spatial.distance import squareform
+    scr = sim_mat(np.asarray(X))
+    scr = squareform(-scr, checks=False)
+    lin = linkage(scr, method="average")
+    adjust = abs(lin[:, 2].min())
+    lin[:, 2] += adjust
+    return fcluster(lin, -fix_cos_thr + adjust, criterion="distance") - 1
+
+
+def filter_minor_cluster(labels, x, min_cluster_size):
+    """CommonClustering.filter_minor_cluster (cluster.py:200-219)."""
+    from sklearn.metrics.pairwise import cosine_similarity
+    cset = np.unique(labels)
+    csize = np.array([(labels == i).sum() for i in cset])
+    minor_idx = np.where(csize <= min_cluster_size)[0]
+    if len(minor_idx) == 0:
+        return labels
+    minor_cset = cset[minor_idx]
+    major_idx = np.where(csize > min_cluster_size)[0]
+    if len(major_idx) == 0:
+        return np.zeros_like(labels)
+    major_cset = cset[major_idx]
+    major_center = np.stack([x[labels == i].mean(0) for i in major_cset])
+    for i in range(len(labels)):
+        if labels[i] in minor_cset:
+            labels[i] = major_cset[cosine_similarity(x[i][np.newaxis], major_center).argmax()]
+    return labels
+
+
+def merge_by_cos(labels, x, cos_thr):
+    """CommonClustering.merge_by_cos (cluster.py:221-238)."""
+    from sklearn.metrics.pairwise import cosine_similarity
+    while True:
+        cset = np.unique(labels)
+        if len(cset) == 1:
+            break
+        centers = np.stack([x[labels == i].mean(0) for i in cset])
+        affinity = np.triu(cosine_similarity(centers, centers), 1)
+        idx = np.unravel_index(np.argmax(affinity), affinity.shape)
+        if affinity[idx] < cos_thr:
+            break
+        c1, c2 = cset[np.array(idx)]
+        labels[labels == c2] = c1
+    return labels
+
+
+def common_clustering(X, cluster_type="spectral", cluster_line=40, mer_cos=None, min_cluster_size=4, **kw):
+    """CommonClustering.__call__ (cluster.py:184-198)."""
+    X = np.asarray(X)
+    if X.shape[0] <= 1:
+        return np.zeros(X.shape[0], dtype=int)
+    if X.shape[0] < cluster_line or cluster_type == "AHC":
+        labels = ahc(X, **(kw if cluster_type == "AHC" else {}))
+    else:
+        labels = spectral_cluster(X, **kw)
+    labels = filter_minor_cluster(np.array(labels), X, min_cluster_size)
+    if mer_cos is not None:
+        labels = merge_by_cos(labels, X, mer_cos)
+    return labels

@@ -120,6 +120,29 @@ def cluster_cases():
     ]
 
 
+def common_cases():
+    """(name, N, D, K, seed, noise, outliers, CommonClustering kwargs)"""
+    return [
+        ("ahc_n30_k3", 30, 64, 3, 31, 0.35, 0, dict(cluster_type="AHC", fix_cos_thr=0.4)),
+        ("ahc_n500_k5", 500, 192, 5, 32, 0.35, 0, dict(cluster_type="AHC", fix_cos_thr=0.4)),
+        ("spectral_short_n25", 25, 64, 2, 33, 0.35, 0, dict(cluster_type="spectral", min_num_spks=1, max_num_spks=15, pval=0.012)),
+        ("spectral_n400_minor_merge", 400, 96, 4, 34, 0.35, 3, dict(cluster_type="spectral", mer_cos=0.8, min_cluster_size=4,
+                                                                    min_num_spks=1, max_num_spks=15, pval=0.012)),
+        ("ahc_n300_minor", 300, 96, 4, 35, 0.5, 5, dict(cluster_type="AHC", fix_cos_thr=0.3, min_cluster_size=4, mer_cos=0.9)),
+    ]
+
+
+def common_input(n, d, k, seed, noise, outliers):
+    """Gaussian blobs plus a few isolated points (they form minor clusters that filter_minor_cluster reassigns)."""
+    rng = np.random.default_rng([seed, 0xC2])
+    centers = rng.standard_normal((k, d))
+    lab = rng.integers(0, k, n)
+    X = centers[lab] + noise * rng.standard_normal((n, d))
+    for j in range(outliers):
+        X[j] = 2.0 * rng.standard_normal(d)
+    return X.astype(np.float32), lab
+
+
 def cluster_input(n, d, k, seed):
     rng = np.random.default_rng([seed, 0xC1])
     centers = rng.standard_normal((k, d))
@@ -255,6 +278,27 @@ def main():
         out[name + ".lap_fro"] = np.array(np.linalg.norm(L.astype(np.float64)))
     np.savez_compressed(os.path.join(OUT, "cluster.npz"), **out)
     print("cluster goldens:", {k: out[k].tolist() for k in out if k.endswith(".k")})
+    mint_common(ver)
+
+
+def mint_common(ver):
+    """AHCluster / CommonClustering goldens from the imported reference; fastcluster (not installed) is replaced by
+    scipy.cluster.hierarchy.linkage, which implements the same average-linkage algorithm and output format."""
+    import scipy.cluster.hierarchy
+    fc = sys.modules["fastcluster"]
+    fc.linkage = lambda y, method="average", preserve_input=True: scipy.cluster.hierarchy.linkage(y, method=method)
+    from speakerlab.process import cluster as ref_cluster
+    ref_cluster.fastcluster = fc
+    out = {"versions": ver}
+    for name, n, d, k, seed, noise, outliers, kw in common_cases():
+        X, _ = common_input(n, d, k, seed, noise, outliers)
+        np.random.seed(0)
+        labels = ref_cluster.CommonClustering(**kw)(X.copy())
+        out[name + ".labels"] = np.asarray(labels).astype(np.int32)
+        if kw["cluster_type"] == "AHC":
+            out[name + ".raw_ahc"] = np.asarray(ref_cluster.AHCluster(kw.get("fix_cos_thr", 0.4))(X.copy())).astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, "common_clustering.npz"), **out)
+    print("common clustering goldens:", {k: int(v.max()) + 1 for k, v in out.items() if k.endswith(".labels")})
 
 
 if __name__ == "__main__":

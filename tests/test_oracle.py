@@ -159,3 +159,18 @@ def test_ecapa_oracle_matches_reference(golden_dir, layouts, case):
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-5
     # the fp32 reference itself is within 1e-6 of the same graph in fp64: these test networks are well conditioned
     assert np.linalg.norm(ref - gold[name + ".emb_f64"]) / np.linalg.norm(ref) < 1e-5
+
+
+@pytest.mark.parametrize("case", gen_golden.common_cases(), ids=lambda c: c[0])
+def test_common_clustering_oracle_matches_reference(golden_dir, case):
+    from oracle import cluster_oracle
+    gold = np.load(os.path.join(golden_dir, "common_clustering.npz"))
+    name, n, d, k, seed, noise, outliers, kw = case
+    X, _ = gen_golden.common_input(n, d, k, seed, noise, outliers)
+    np.random.seed(0)
+    got = cluster_oracle.common_clustering(X.copy(), **kw)
+    ref = gold[name + ".labels"]
+    assert np.array_equal(cluster_oracle.match_labels(ref, got), ref)
+    if kw["cluster_type"] == "AHC":
+        raw = cluster_oracle.ahc(X, kw.get("fix_cos_thr", 0.4))
+        assert np.array_equal(cluster_oracle.match_labels(gold[name + ".raw_ahc"], raw), gold[name + ".raw_ahc"])

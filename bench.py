@@ -30,6 +30,7 @@ import torch  # noqa: E402
 N_SAMPLES = 24000                 # 1.5 s @ 16 kHz  (infer_diarization.py:285 chunk_dur)
 T_FRAMES = 148
 EMB = 512                         # CAM++ 7.2 M variant (BASELINE config 0)
+DRAM_BYTES_PER_SEG_BF16 = 31.29e9 / 2048      # measured with ncu on the bf16 path (profiles/r01_traffic_o.md)
 GFLOP_PER_SEG = 1.588             # minimal conv/linear FLOPs per 1.5 s segment
 FBANK_BYTES_PER_SEG = 4 * N_SAMPLES + 4 * T_FRAMES * 80
 WEIGHT_SEED = 7
@@ -383,6 +384,8 @@ def main():
         segs_per_call = S / (S // args.batch + (1 if S % args.batch else 0))
         tf = GFLOP_PER_SEG * segs_per_call / fw_avg          # GFLOP/ms == TFLOP/s
         gbs = FBANK_BYTES_PER_SEG * segs_per_call / fb_avg / 1e6
+        # DRAM bytes of one forward call (ncu, profiles/r01_traffic_o.md: 31.29 GB per 2048 segments in bf16 mode)
+        traffic = DRAM_BYTES_PER_SEG_BF16 * segs_per_call if args.precision == "bf16" else None
         line = {
             "metric": "CAM++ embeddings/sec (1.5 s windows)", "value": value, "unit": "embeddings/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -394,8 +397,13 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"kernel": "CAM++ conv stack (all implicit-GEMM launches of one forward call)",
                          "bound": "tensor", "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": tf / pk["bf16_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
-                         "flops_per_launch": GFLOP_PER_SEG * 1e9 * segs_per_call, "ms_per_launch": fw_avg},
+                         "frac": tf / pk["bf16_sustained"], "traffic": traffic, "peak_source": pk["source"] + " (sustained)",
+                         "flops_per_launch": GFLOP_PER_SEG * 1e9 * segs_per_call, "ms_per_launch": fw_avg,
+                         "traffic_source": "ncu dram__bytes_read+write over one forward call, profiles/r01_traffic_o.md"},
+            # the same forward call against HBM: 15.3 MB of DRAM traffic per segment (measured) is the tighter bound
+            "roofline_hbm": {"kernel": "CAM++ forward call (all launches)", "bound": "hbm",
+                             "achieved": (traffic / (fw_avg * 1e-3) / 1e9) if traffic else None, "peak": pk["hbm"], "unit": "GB/s",
+                             "frac": (traffic / (fw_avg * 1e-3) / 1e9 / pk["hbm"]) if traffic else None, "traffic": traffic},
             "roofline_fbank": {"kernel": "fbank_kernel<fused>", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"],
                                "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
                                "bytes_per_launch": FBANK_BYTES_PER_SEG * segs_per_call, "ms_per_launch": fb_avg},

@@ -383,8 +383,25 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
                     }
                     if (res != nullptr) {
                         const TRes *rp = res + m * a.res_ld + a.res_choff + n;
+                        if constexpr (sizeof(TRes) == 2) {       // 16-byte loads (res_ld, res_choff are multiples of 8)
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] += to_f32(rp[e]);
+                            for (int e = 0; e < 16; e += 8) {
+                                const uint4 t = ldg16(rp + e);
+                                const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                                for (int h = 0; h < 4; ++h) {
+                                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&w4[h]);
+                                    v[e + 2 * h] += __low2float(b2);
+                                    v[e + 2 * h + 1] += __high2float(b2);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 16; e += 4) {
+                                const float4 t = __ldg(reinterpret_cast<const float4 *>(rp + e));
+                                v[e] += t.x; v[e + 1] += t.y; v[e + 2] += t.z; v[e + 3] += t.w;
+                            }
+                        }
                     }
                     if (grow != nullptr && a.gate_additive) {
 #pragma unroll

@@ -237,14 +237,18 @@ stem_tiled_kernel(const StemArgs a) {
     const int cg = lane % CG, p = lane / CG;
     constexpr int PIX = 32 / CG;             // pixels per warp step
     const int c0 = cg * 8;
-    float w[9][8], sc[8], sh[8];
+    // weights as channel pairs: the 72 FMAs of a pixel issue as 36 packed FFMA2 (bit-identical to scalar fmaf)
+    float2 w[9][4];
+    float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) w[k][j] = __ldg(a.w + (c0 + j) * 9 + k);
         sc[j] = a.scale ? __ldg(a.scale + c0 + j) : 1.f;
         sh[j] = a.shift ? __ldg(a.shift + c0 + j) : 0.f;
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k][j] = make_float2(__ldg(a.w + (c0 + 2 * j) * 9 + k), __ldg(a.w + (c0 + 2 * j + 1) * 9 + k));
     const float *fe = a.feats + (size_t)b * a.T * a.F;
     constexpr int NR = kStemRows + 2;
     for (int i = threadIdx.x; i < NR * Tp; i += blockDim.x) {
@@ -260,15 +264,21 @@ stem_tiled_kernel(const StemArgs a) {
         const float *r0 = rows + r * Tp, *r1 = r0 + Tp, *r2 = r1 + Tp;
         for (int t = p; t < a.T; t += PIX) {
             const float in[9] = {r0[t], r0[t + 1], r0[t + 2], r1[t], r1[t + 1], r1[t + 2], r2[t], r2[t + 1], r2[t + 2]};
+            float2 o2[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o2[j] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const float2 x2 = make_float2(in[k], in[k]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o2[j] = __ffma2_rn(x2, w[k][j], o2[j]);
+            }
             float o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = 0.f;
-#pragma unroll
-            for (int k = 0; k < 9; ++k)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = fmaf(in[k], w[k][j], o[j]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = fmaf(o[j], sc[j], sh[j]);
+            for (int j = 0; j < 4; ++j) {
+                o[2 * j] = fmaf(o2[j].x, sc[2 * j], sh[2 * j]);
+                o[2 * j + 1] = fmaf(o2[j].y, sc[2 * j + 1], sh[2 * j + 1]);
+            }
             apply_act_vec(o, a.act);
             const float q0[4] = {o[0], o[1], o[2], o[3]}, q1[4] = {o[4], o[5], o[6], o[7]};
             TOut *yp = y + (size_t)t * a.out_ld;

@@ -132,3 +132,20 @@ def test_extractor_host_buffers_roundtrip():
     assert not got.is_cuda and got.shape == (9, emb)
     dev = ex.extract_device(wavs.cuda()).cpu()
     assert torch.equal(got, dev)
+
+
+def test_bf16_forward_takes_the_fused_kernels():
+    """One kernel launch per op of the compiled program: the fused CAM layer, the TMA slab kernels and the TMA GEMM
+    are the paths that run (a geometry or dispatch regression that silently drops to the unfused CAM layer or a
+    two-kernel path shows up as extra launches)."""
+    model = b200spk.CAMPPlus(embedding_size=192, precision="bf16").cuda().eval()
+    feats = torch.randn(256, 148, 80, device="cuda")
+    with torch.no_grad():
+        model(feats)                                   # compiles, uploads and converts the weights
+        torch.cuda.synchronize()
+        before = b200spk.lib().spk_launch_count()
+        model(feats)
+        torch.cuda.synchronize()
+        launches = b200spk.lib().spk_launch_count() - before
+    prog = model._engine.model.programs[148]
+    assert launches == len(prog.ops), (launches, len(prog.ops))

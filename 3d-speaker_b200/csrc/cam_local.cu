@@ -300,6 +300,7 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t acc_cols = (uint32_t)g.n_tiles * 32u + 2 * kSumCols;  // per TMEM buffer: conv tiles, then the two sum halves
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         tmap_prefetch(&xmap);
         for (int i = 0; i < 2; ++i) {
@@ -352,6 +353,7 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // everything above read only parameters; the activations come from the previous kernel
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
@@ -651,7 +653,11 @@ int launch_cam_local(const ConvArgs &a, const float *w1t, const float *b1, const
     const int items = (a.B + g.G - 1) / g.G;
     const int grid = std::min(items, sm_count());
     static const int dbg = getenv("SPK_CAM_DBG") ? atoi(getenv("SPK_CAM_DBG")) : 0;
-    cam_local_kernel<<<grid, kThreads, g.smem_bytes, s>>>(a, g, w1t, b1, w2t, b2, items, dbg, xmap);
+    const cudaError_t le = launch_pdl(cam_local_kernel, dim3(grid), dim3(kThreads), (size_t)g.smem_bytes, s, a, g, w1t, b1, w2t, b2, items, dbg, xmap);
+    if (le != cudaSuccess) {
+        set_error("cam_local_kernel launch failed: %s", cudaGetErrorString(le));
+        return SPK_ERR_CUDA;
+    }
     return check_launch("cam_local_kernel");
 }
 

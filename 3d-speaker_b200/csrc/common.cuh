@@ -1,5 +1,6 @@
 // Shared helpers for libb200spk (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -81,6 +82,28 @@ __device__ __forceinline__ void apply_act_vec(float (&v)[N], int act) {
 #pragma unroll
         for (int e = 0; e < N; ++e) v[e] = tanhf(v[e]);
     }
+}
+
+// ---- programmatic dependent launch: the grid may start while the previous kernel of the stream drains.  Kernels
+// launched this way do their input-independent prologue (barrier init, TMEM allocation, weight staging), then
+// pdl_wait() before the first read of anything an earlier kernel wrote; pdl_trigger() at their own start lets the
+// next kernel do the same.  SPK_NO_PDL=1 falls back to plain stream order.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const bool on = [] { const char *e = getenv("SPK_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }

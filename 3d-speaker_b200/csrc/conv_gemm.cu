@@ -212,6 +212,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool has_pro = pro_scale_bf != nullptr;
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; ++s) {
             mbar_init(land_bar(s), 1);
@@ -247,6 +248,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nk = (a.K + BLOCK_K - 1) / BLOCK_K;
+    pdl_wait();          // everything above read only parameters; the activations come from the previous kernel
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
@@ -603,8 +605,14 @@ int launch_one(const ConvArgs &a, cudaStream_t s) {
     if (rc != SPK_OK) return rc;
     const bf16 *ps = nullptr, *ph = nullptr;
     if (a.pro_scale != nullptr) {
-        rc = bf16_vector(a.pro_scale, a.Cin, &ps, s);
-        if (rc == SPK_OK) rc = bf16_vector(a.pro_shift, a.Cin, &ph, s);
+        if (a.pro_scale_bf != nullptr && a.pro_shift_bf != nullptr) {      // prepared by the model at set_program time
+            ps = static_cast<const bf16 *>(a.pro_scale_bf);
+            ph = static_cast<const bf16 *>(a.pro_shift_bf);
+            rc = SPK_OK;
+        } else {
+            rc = bf16_vector(a.pro_scale, a.Cin, &ps, s);
+            if (rc == SPK_OK) rc = bf16_vector(a.pro_shift, a.Cin, &ph, s);
+        }
         if (rc != SPK_OK) return rc;
     }
     const long long mt = (a.M + BLOCK_M - 1) / BLOCK_M;
@@ -618,7 +626,11 @@ int launch_one(const ConvArgs &a, cudaStream_t s) {
         set_error("conv_gemm: K=%d too large for the shared-memory prologue tables", a.K);
         return SPK_ERR_UNSUPPORTED;
     }
-    kern<<<(unsigned)grid, kThreads, smem_bytes, s>>>(a, ps, ph, ntn, tiles, amap, wmap, dbg);
+    const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), (size_t)smem_bytes, s, a, ps, ph, ntn, tiles, amap, wmap, dbg);
+    if (le != cudaSuccess) {
+        set_error("conv_gemm_kernel launch failed: %s", cudaGetErrorString(le));
+        return SPK_ERR_CUDA;
+    }
     return check_launch("conv_gemm_kernel");
 }
 

@@ -84,6 +84,7 @@ conv_slab3_kernel(const ConvArgs a, const Slab3Geom g, long long n_items, const 
     const uint32_t acc_cols = (uint32_t)g.n_tiles * 32u;
     const uint32_t sub_o = (uint32_t)g.px_e * 64u;          // byte offset of the odd sub-slab inside a slab buffer
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         tmap_prefetch(&xmap_e);
         if (S == 2 && KS == 3) tmap_prefetch(&xmap_o);
@@ -130,6 +131,7 @@ conv_slab3_kernel(const ConvArgs a, const Slab3Geom g, long long n_items, const 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();          // everything above read only parameters; the activations come from the previous kernel
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
@@ -413,7 +415,11 @@ int launch(const ConvArgs &a, const Slab3Geom &g, cudaStream_t s) {
     const long long items = (long long)a.B * g.n_bands;
     const long long grid = std::min<long long>(items, sm_count());
     static const int dbg = getenv("SPK_SLAB_DBG") ? atoi(getenv("SPK_SLAB_DBG")) : 0;
-    kern<<<(unsigned)grid, kThreads, g.smem_bytes, s>>>(a, g, items, me, mo, my, mr, dbg);
+    const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), (size_t)g.smem_bytes, s, a, g, items, me, mo, my, mr, dbg);
+    if (le != cudaSuccess) {
+        set_error("conv_slab3_kernel launch failed: %s", cudaGetErrorString(le));
+        return SPK_ERR_CUDA;
+    }
     return check_launch("conv_slab3_kernel");
 }
 

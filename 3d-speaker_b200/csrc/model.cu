@@ -179,6 +179,20 @@ extern "C" int spk_model_set_program(spk_model_t *m, int64_t T, const spk_buf_t 
     SPK_REQUIRE(p.bufs[0].dtype == SPK_DT_F32 && p.bufs[1].dtype == SPK_DT_F32, "input/output buffers are f32");
     int rc = validate(m, p);
     if (rc != SPK_OK) return rc;
+    if (m->precision == SPK_PREC_BF16) {
+        // bf16 copies of every conv weight and prologue vector NOW, finished before the call returns: the forward
+        // path then never launches a conversion kernel, so kernels started early by programmatic dependent launch
+        // may stage their weights before waiting on the previous kernel
+        const __nv_bfloat16 *tmp = nullptr;
+        for (const spk_op_t &o : p.ops) {
+            if (o.kind != SPK_OP_CONV && o.kind != SPK_OP_CAM_LOCAL) continue;
+            rc = param_bf16(m, o.w, &tmp, nullptr);
+            if (rc == SPK_OK && o.pro_scale >= 0) rc = param_bf16(m, o.pro_scale, &tmp, nullptr);
+            if (rc == SPK_OK && o.pro_shift >= 0) rc = param_bf16(m, o.pro_shift, &tmp, nullptr);
+            if (rc != SPK_OK) return rc;
+        }
+        SPK_CUDA_OK(cudaDeviceSynchronize());
+    }
     m->programs[T] = std::move(p);
     return SPK_OK;
 }
@@ -267,6 +281,13 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                     a.pro_relu = o.pro_relu; a.act = o.act;
                     a.K = o.KH * o.KW * o.Cin;
                     a.M = (long long)n * o.Ho * o.Wo;
+                    if (m->precision == SPK_PREC_BF16 && o.pro_scale >= 0) {      // converted at set_program time
+                        const __nv_bfloat16 *psb = nullptr, *phb = nullptr;
+                        rc = param_bf16(m, o.pro_scale, &psb, s);
+                        if (rc == SPK_OK) rc = param_bf16(m, o.pro_shift, &phb, s);
+                        if (rc != SPK_OK) break;
+                        a.pro_scale_bf = psb; a.pro_shift_bf = phb;
+                    }
                     if (o.kind == SPK_OP_CONV) {            // ECAPA extras (see b200spk.h)
                         a.post_scale = param(m, o.aux[0]); a.post_shift = param(m, o.aux[1]);
                         a.post_act = o.iaux[0]; a.pad_reflect = o.iaux[1]; a.gate_additive = o.iaux[2];

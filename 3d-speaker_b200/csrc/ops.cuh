@@ -22,6 +22,7 @@ struct ConvArgs {
     int post_act;         // activation after that affine (tanh in the ASP attention)
     int pad_reflect;      // out-of-range columns mirror (F.pad mode='reflect') instead of reading zero; W axis only
     int gate_additive;    // gate[b, window, n] is ADDED before the activation (per-segment bias) instead of multiplied after
+    const void *pro_scale_bf, *pro_shift_bf;   // bf16 copies of pro_scale/pro_shift owned by the model (tensor-core prologue)
 };
 
 // fp32-accumulate CUDA-core implicit GEMM (exact-fp32 mode and odd shapes)

@@ -7,12 +7,18 @@ import torch
 
 
 class EmbeddingExtractor:
-    def __init__(self, feature_extractor, embedding_model, device="cuda:0", batchsize=64):
+    def __init__(self, feature_extractor, embedding_model, device="cuda:0", batchsize=64, reuse_output=False, head=512):
+        """``reuse_output``: return a cached pinned host buffer (allocating pinned memory costs milliseconds per call);
+        the result is then only valid until the next call.  ``head``: size of the first sub-batch - nothing overlaps
+        the first host-to-device copy, so it is kept short; the remaining batches use ``batchsize``."""
         self.feature_extractor = feature_extractor
         self.embedding_model = embedding_model
         self.device = torch.device(device)
         self.batchsize = batchsize
+        self.reuse_output = reuse_output
+        self.head = head
         self._copy_stream = None
+        self._out = None
 
     def __call__(self, wavs):
         """wavs: host tensor [N, L] (pinned for async copies) or [N, 1, L] -> host [N, E].
@@ -29,11 +35,16 @@ class EmbeddingExtractor:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(dev)
         cs = self._copy_stream
-        starts = list(range(0, N, self.batchsize))
+        first = min(self.batchsize, self.head) if (self.head and N > self.batchsize) else self.batchsize
+        bounds = [0, min(first, N)]
+        while bounds[-1] < N:
+            bounds.append(min(bounds[-1] + self.batchsize, N))
+        starts = bounds[:-1]
+        ends = dict(zip(bounds[:-1], bounds[1:]))
 
         def stage(st):
             with torch.cuda.stream(cs):
-                buf = wavs[st:st + self.batchsize].to(dev, non_blocking=True)
+                buf = wavs[st:ends[st]].to(dev, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(cs)
             return buf, ev
@@ -50,7 +61,12 @@ class EmbeddingExtractor:
                 feats = self.feature_extractor.batch(wb)
                 emb = self.embedding_model(feats)
                 if out is None:
-                    out = torch.empty((N, emb.shape[1]), dtype=torch.float32, pin_memory=wavs.is_pinned())
+                    if self.reuse_output and self._out is not None and self._out.shape == (N, emb.shape[1]):
+                        out = self._out
+                    else:
+                        out = torch.empty((N, emb.shape[1]), dtype=torch.float32, pin_memory=wavs.is_pinned())
+                        if self.reuse_output:
+                            self._out = out
                 out[st:st + emb.shape[0]].copy_(emb, non_blocking=True)
         main.synchronize()
         return out

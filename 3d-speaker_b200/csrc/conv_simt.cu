@@ -238,17 +238,14 @@ stem_tiled_kernel(const StemArgs a) {
     constexpr int PIX = 32 / CG;             // pixels per warp step
     const int c0 = cg * 8;
     // weights as channel pairs: the 72 FMAs of a pixel issue as 36 packed FFMA2 (bit-identical to scalar fmaf)
-    float2 w[9][4];
-    float sc[8], sh[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = a.scale ? __ldg(a.scale + c0 + j) : 1.f;
-        sh[j] = a.shift ? __ldg(a.shift + c0 + j) : 0.f;
+    // parameters through shared memory: two coalesced loads per thread instead of 88 scalar L2 round trips
+    constexpr int COUT = CG * 8;
+    __shared__ float s_w[COUT * 9], s_sc[COUT], s_sh[COUT];
+    for (int i = threadIdx.x; i < COUT * 9; i += blockDim.x) s_w[i] = __ldg(a.w + i);
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+        s_sc[i] = a.scale ? __ldg(a.scale + i) : 1.f;
+        s_sh[i] = a.shift ? __ldg(a.shift + i) : 0.f;
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) w[k][j] = make_float2(__ldg(a.w + (c0 + 2 * j) * 9 + k), __ldg(a.w + (c0 + 2 * j + 1) * 9 + k));
     const float *fe = a.feats + (size_t)b * a.T * a.F;
     constexpr int NR = kStemRows + 2;
     for (int i = threadIdx.x; i < NR * Tp; i += blockDim.x) {
@@ -256,6 +253,14 @@ stem_tiled_kernel(const StemArgs a) {
         rows[r * Tp + tt + 1] = (ff >= 0 && ff < a.F && tt >= 0 && tt < a.T) ? __ldg(fe + (size_t)tt * a.F + ff) : 0.f;
     }
     __syncthreads();
+    float2 w[9][4];
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = s_sc[c0 + j]; sh[j] = s_sh[c0 + j]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) w[k][j] = make_float2(s_w[(c0 + 2 * j) * 9 + k], s_w[(c0 + 2 * j + 1) * 9 + k]);
 #pragma unroll 1
     for (int rr = 0; rr < 2; ++rr) {
         const int r = warp * 2 + rr, f = f0 + r;

@@ -302,7 +302,7 @@ def main():
     model.load_state_dict(tsd)
     model = model.to(dev).eval()
     fb = b200spk.FBank(80, 16000, mean_nor=True)
-    ex = b200spk.EmbeddingExtractor(fb, model, device=dev, batchsize=args.batch)
+    ex = b200spk.EmbeddingExtractor(fb, model, device=dev, batchsize=args.batch, reuse_output=True)
 
     S = args.segments
     host = torch.from_numpy(make_windows(S, seed=1000 + rank)).pin_memory()

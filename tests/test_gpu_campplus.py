@@ -132,6 +132,12 @@ def test_extractor_host_buffers_roundtrip():
     assert not got.is_cuda and got.shape == (9, emb)
     dev = ex.extract_device(wavs.cuda()).cpu()
     assert torch.equal(got, dev)
+    # a short first sub-batch (nothing overlaps the first copy) and a reused pinned result buffer change nothing
+    ex2 = b200spk.EmbeddingExtractor(b200spk.FBank(80, 16000, mean_nor=True), model, batchsize=4, head=1, reuse_output=True)
+    a = ex2(wavs)
+    assert torch.equal(a, got)
+    b = ex2(wavs)
+    assert b.data_ptr() == a.data_ptr() and torch.equal(b, got)
 
 
 def test_bf16_forward_takes_the_fused_kernels():

@@ -153,6 +153,21 @@ def test_conv_prologue_epilogue_relu(precision):
     _check(y, ref, 1e-4 if precision == "fp32" else 2e-3)       # bf16: single- vs double-rounded fma moves a few A elements by one ulp
 
 
+@pytest.mark.parametrize("Cin,Cout,B", [(352, 128, 40), (160, 64, 24), (96, 32, 24), (1024, 128, 8), (64, 256, 12)])
+def test_gemm_prologue_many_tiles(Cin, Cout, B):
+    """The TMA GEMM with the BN-ReLU prologue over many M tiles per CTA ring wrap-around: the prologue goes through
+    tensor memory for Cout <= 128 (two transform groups on alternate stages, partial last K stage) and stays in
+    shared memory for Cout = 256."""
+    g = torch.Generator().manual_seed(Cin + Cout)
+    W = 74
+    x = torch.randn(B, 1, W, Cin, generator=g)
+    w = torch.randn(Cout, 1, 1, Cin, generator=g) / math.sqrt(Cin)
+    pro = (torch.rand(Cin, generator=g) + 0.5, 0.1 * torch.randn(Cin, generator=g))
+    epi = (torch.rand(Cout, generator=g) + 0.5, 0.1 * torch.randn(Cout, generator=g))
+    y, ref = run_conv(x, w, pro=pro, epi=epi, act=_lib.ACT_RELU, precision="bf16")
+    _check(y, ref, 2e-3)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_conv_padding_stays_zero_after_prologue(precision):
     # padded taps must contribute 0, not relu(shift): the prologue applies to real pixels only

@@ -155,3 +155,22 @@ def test_bf16_forward_takes_the_fused_kernels():
         launches = b200spk.lib().spk_launch_count() - before
     prog = model._engine.model.programs[148]
     assert launches == len(prog.ops), (launches, len(prog.ops))
+
+
+def test_ten_second_segments_take_the_fallback_kernels():
+    """T = 998 frames (10 s, the bulk-extraction chunk length): the fused CAM layer (band pitch > 256 rows) and the TMA
+    slab kernel (row pitch > 256 pixels) do not apply, so the unfused gate + generic tcgen05 kernels and the cp.async
+    slab kernel run instead.  fp32 against the CPU oracle, bf16 against fp32."""
+    name, emb, batch, n_samples, wseed, bnrand = gen_golden.campplus_cases()[3]       # fresh-BN weights: well conditioned
+    wavs = gen_golden.campplus_input(2, 160000, seed=55)
+    feats = b200spk.fbank_batch(torch.from_numpy(wavs).cuda())
+    assert feats.shape[1] == 998
+    m32, sd = _model(emb, wseed, bnrand)
+    m16, _ = _model(emb, wseed, bnrand, precision="bf16")
+    with torch.no_grad():
+        e32 = m32(feats).cpu().numpy()
+        e16 = m16(feats).cpu().numpy()
+    ref = campplus_oracle.forward({k: torch.from_numpy(v) for k, v in sd.items()}, feats.cpu().numpy()).numpy()
+    assert _rel(e32, ref) <= 1e-4, _rel(e32, ref)
+    cos = float(((e16 * e32).sum(1) / (np.linalg.norm(e16, axis=1) * np.linalg.norm(e32, axis=1))).min())
+    assert cos >= 0.999, cos

@@ -251,7 +251,6 @@ conv_slab3_kernel(const ConvArgs a, const Slab3Geom g, long long n_items, const 
                     }
                 }
                 apply_act_vec(v, a.act);
-                if (!(dbg & 2))
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
                     sts16(prow + (((uint32_t)e ^ x) << 4),
@@ -261,7 +260,7 @@ conv_slab3_kernel(const ConvArgs a, const Slab3Geom g, long long n_items, const 
             }
             tc_fence_before();
             mbar_arrive(aempty(buf));
-            if (!(dbg & 8)) fence_proxy_async();            // staging writes (generic proxy) -> TMA store (async proxy)
+            fence_proxy_async();            // staging writes (generic proxy) -> TMA store (async proxy)
             mbar_arrive(gfull(buf));
             if (warp == 2) SLAB_TS(it, 5);
         }
@@ -274,11 +273,9 @@ conv_slab3_kernel(const ConvArgs a, const Slab3Geom g, long long n_items, const 
                 const int band = (int)(item - (long long)b * g.n_bands);
                 const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
                 mbar_wait(gfull(buf), ph);
-                if (!(dbg & 16)) {
                 tmap_store_4d(&ymap, a.out_choff, 0, band * g.R, b, s_stg + buf * g.stg_bytes);
                 bulk_commit();
                 bulk_wait_read0();          // the box has been read out of shared memory
-                }
                 mbar_arrive(gfree(buf));
             }
             bulk_wait_all();

@@ -122,6 +122,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -178,28 +186,32 @@ __device__ __forceinline__ uint32_t bnrelu2(uint32_t x, uint32_t s, uint32_t b, 
 __device__ long long g_gemm_ts[256 * 8];
 #define GEMM_TS(idx, slot) do { if (dbg && blockIdx.x == 0 && (idx) < 256 && (threadIdx.x & 31) == 0) g_gemm_ts[(idx) * 8 + (slot)] = clock64(); } while (0)
 
-template <int BLOCK_N> struct Cfg {
+template <int BLOCK_N, bool TEPI = false> struct Cfg {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    // TEPI (TMA epilogue): one output tile [128 x BLOCK_N] bf16 is staged in shared memory, so the ring is shorter
+    static constexpr int kStgBytes = TEPI ? BLOCK_M * BLOCK_N * 2 : 0;
+    static constexpr int kStages = TEPI ? ((BLOCK_N >= 256) ? 3 : 5) : ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8));
     static constexpr bool kATmem = BLOCK_N <= 128;          // room for the A ring next to the two accumulators
     static constexpr int kAColsPerStage = BLOCK_K / 2;       // two bf16 per 32-bit TMEM column
     static constexpr int kTmemNeed = 2 * BLOCK_N + (kATmem ? kStages * kAColsPerStage : 0);
     static constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStgBytes + 1024 + 512;
 };
 
-template <int BLOCK_N, typename TOut, typename TRes>
+template <int BLOCK_N, typename TOut, typename TRes, bool TEPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const bf16 *__restrict__ pro_shift_bf,
                  int n_tiles_n, long long n_tiles, const __grid_constant__ CUtensorMap amap,
-                 const __grid_constant__ CUtensorMap wmap, int dbg) {
-    using C = Cfg<BLOCK_N>;
+                 const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap ymap,
+                 const __grid_constant__ CUtensorMap rmap, int dbg) {
+    using C = Cfg<BLOCK_N, TEPI>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (base - raw) + C::kStages * C::kStageBytes);
+    const uint32_t s_stg = base + C::kStages * C::kStageBytes;       // TEPI: output staging tile
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (base - raw) + C::kStages * C::kStageBytes + C::kStgBytes);
     const uint32_t bar0 = smem_u32(bars);
     // [0,S) landed (TMA tx)  [S,2S) ready (transformed)  [2S,3S) empty  then accum full/empty x2
     auto land_bar = [&](int s) { return bar0 + 8u * s; };
@@ -207,7 +219,9 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
     auto empty_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + s); };
     auto accf_bar = [&](int b) { return bar0 + 8u * (3 * C::kStages + b); };
     auto acce_bar = [&](int b) { return bar0 + 8u * (3 * C::kStages + 2 + b); };
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + 3 * C::kStages + 4);
+    auto rfull_bar = [&]() { return bar0 + 8u * (3 * C::kStages + 4); };     // TEPI: residual tile landed in the staging buffer
+    auto sfree_bar = [&]() { return bar0 + 8u * (3 * C::kStages + 5); };     // TEPI: the TMA store has read the staging buffer
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + 3 * C::kStages + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool has_pro = pro_scale_bf != nullptr;
@@ -223,6 +237,12 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
             mbar_init(accf_bar(b), 1);
             mbar_init(acce_bar(b), kEpilogueThreads);
         }
+        mbar_init(rfull_bar(), 1);
+        mbar_init(sfree_bar(), 1);
+        if (TEPI) {
+            prefetch_tmap(&ymap);
+            prefetch_tmap(&rmap);
+        }
         fence_barrier_init();
         prefetch_tmap(&amap);
         prefetch_tmap(&wmap);
@@ -230,7 +250,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
     if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), C::kTmemCols);
     // prologue scale/shift -> shared memory (zero beyond K: relu(0*x+0) = 0), read back as broadcast loads
     const int nk_pre = (a.K + BLOCK_K - 1) / BLOCK_K;
-    const uint32_t s_pro = base + C::kStages * C::kStageBytes + 512u, pro_bytes = (uint32_t)nk_pre * 128u;
+    const uint32_t s_pro = base + C::kStages * C::kStageBytes + C::kStgBytes + 512u, pro_bytes = (uint32_t)nk_pre * 128u;
     if (has_pro && C::kATmem) {
         for (int idx = threadIdx.x; idx < nk_pre * 8; idx += kThreads) {
             const int c = idx * 8;
@@ -254,7 +274,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
         // =========================== TMA producer ===========================
         if (lane == 0) {
             int stage = 0, sidx = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, pit = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const long long mt = tile / n_tiles_n;
                 const int nt = (int)(tile - mt * n_tiles_n);
@@ -267,6 +287,15 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                     tma_load_2d(sa + C::kABytes, &wmap, kc * BLOCK_K, nt * BLOCK_N, land_bar(stage));
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
+                if (TEPI && a.res != nullptr) {
+                    // residual tile -> staging buffer, once the store of the previous tile has read it
+                    mbar_wait(sfree_bar(), (pit & 1u) ^ 1u);
+                    const int nblk = min(BLOCK_N / 64, (a.Cout - nt * BLOCK_N + 63) / 64);
+                    mbar_arrive_expect_tx(rfull_bar(), (uint32_t)nblk * (BLOCK_M * 128u));
+                    for (int j = 0; j < nblk; ++j)
+                        tma_load_2d(s_stg + (uint32_t)j * (BLOCK_M * 128u), &rmap, nt * BLOCK_N + 64 * j, (int)(mt * BLOCK_M), rfull_bar());
+                }
+                ++pit;
             }
         }
     } else if (warp == 1) {
@@ -402,6 +431,100 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                 const int wo = (int)(m % a.Wo);
                 grow = a.gate + ((long long)b * a.gate_nwin + wo / a.gate_win) * a.Cout;
             }
+            if constexpr (TEPI) {
+                // ---- TMA epilogue: the tile goes through a 128B-swizzled staging buffer ([BLOCK_N/64] blocks of
+                // 128 rows x 64 columns).  A residual tile was TMA-loaded into it by the producer and is updated in
+                // place; one thread then stores the blocks with TMA (rows past M / columns past Cout are clipped).
+                // Row-strided per-lane global accesses - 32 different lines per warp instruction - are what made the
+                // residual GEMMs of ERes2NetV2 run below 1 TB/s.
+                if (res != nullptr) mbar_wait(rfull_bar(), it & 1u);
+                else mbar_wait(sfree_bar(), (it & 1u) ^ 1u);
+                mbar_wait(accf_bar(buf), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+                const uint32_t srow = s_stg + (uint32_t)row * 128u, x7 = (uint32_t)(row & 7);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    const int n = n0 + c0;
+                    if (n >= a.Cout) break;
+                    const bool second = n + 16 < a.Cout;
+                    uint32_t r[32];
+                    {
+                        uint32_t (&r0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[0]);
+                        uint32_t (&r1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[16]);
+                        tmem_ld16(taddr + c0, r0);
+                        tmem_ld16(taddr + c0 + 16, r1);
+                    }
+                    float4 s4[8], h4[8];
+                    if (a.epi_scale != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int ne = (e < 4 || second) ? n + 4 * e : n;
+                            s4[e] = __ldg(reinterpret_cast<const float4 *>(a.epi_scale + ne));
+                            h4[e] = __ldg(reinterpret_cast<const float4 *>(a.epi_shift + ne));
+                        }
+                    }
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+                    if (a.epi_scale != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            v[4 * e] = fmaf(v[4 * e], s4[e].x, h4[e].x); v[4 * e + 1] = fmaf(v[4 * e + 1], s4[e].y, h4[e].y);
+                            v[4 * e + 2] = fmaf(v[4 * e + 2], s4[e].z, h4[e].z); v[4 * e + 3] = fmaf(v[4 * e + 3], s4[e].w, h4[e].w);
+                        }
+                    }
+                    // this step's four 16-byte chunks of the row inside block c0 / 64
+                    const uint32_t blk = srow + (uint32_t)(c0 >> 6) * (BLOCK_M * 128u);
+                    const uint32_t ch0 = (uint32_t)((c0 & 63) >> 3);
+                    if (res != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint4 t = lds16(blk + (((ch0 + e) ^ x7) << 4));
+                            const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&w4[h]);
+                                v[8 * e + 2 * h] += __low2float(b2);
+                                v[8 * e + 2 * h + 1] += __high2float(b2);
+                            }
+                        }
+                    }
+                    apply_act_vec(v, a.act);
+                    if (a.post_scale != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            if (e < 16 || second) {
+                                const float4 p4 = __ldg(reinterpret_cast<const float4 *>(a.post_scale + n + e));
+                                const float4 q4 = __ldg(reinterpret_cast<const float4 *>(a.post_shift + n + e));
+                                v[e] = fmaf(v[e], p4.x, q4.x); v[e + 1] = fmaf(v[e + 1], p4.y, q4.y);
+                                v[e + 2] = fmaf(v[e + 2], p4.z, q4.z); v[e + 3] = fmaf(v[e + 3], p4.w, q4.w);
+                            }
+                        }
+                        apply_act_vec(v, a.post_act);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        sts16(blk + (((ch0 + e) ^ x7) << 4),
+                              make_uint4(pack2(v[8 * e], v[8 * e + 1]), pack2(v[8 * e + 2], v[8 * e + 3]), pack2(v[8 * e + 4], v[8 * e + 5]),
+                                         pack2(v[8 * e + 6], v[8 * e + 7])));
+                }
+                tc_fence_before();
+                mbar_arrive(acce_bar(buf));
+                fence_proxy_async();
+                epi_bar_sync();
+                if (warp == 6 && elect_one()) {
+                    const int nblk = min(BLOCK_N / 64, (a.Cout - n0 + 63) / 64);
+                    for (int j = 0; j < nblk; ++j)
+                        tma_store_2d(&ymap, n0 + 64 * j, (int)(mt * BLOCK_M), s_stg + (uint32_t)j * (BLOCK_M * 128u));
+                    bulk_commit();
+                    bulk_wait_read0();
+                    mbar_arrive(sfree_bar());
+                }
+                __syncwarp();
+                continue;
+            }
             mbar_wait(accf_bar(buf), acc_phase);
             tc_fence_after();
             if (warp == 6) GEMM_TS(it, 6);
@@ -525,6 +648,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
             mbar_arrive(acce_bar(buf));
             if (warp == 6) GEMM_TS(it, 7);
         }
+        if (TEPI) bulk_wait_all();          // the stores of the last tile have left shared memory and reached global
     }
 
     tc_fence_before();
@@ -588,10 +712,10 @@ int bf16_vector(const float *src, int n, const bf16 **out, cudaStream_t s) {
     return SPK_OK;
 }
 
-template <int BLOCK_N, typename TOut, typename TRes>
+template <int BLOCK_N, typename TOut, typename TRes, bool TEPI = false>
 int launch_one(const ConvArgs &a, cudaStream_t s) {
-    using C = Cfg<BLOCK_N>;
-    auto kern = conv_gemm_kernel<BLOCK_N, TOut, TRes>;
+    using C = Cfg<BLOCK_N, TEPI>;
+    auto kern = conv_gemm_kernel<BLOCK_N, TOut, TRes, TEPI>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
@@ -603,6 +727,13 @@ int launch_one(const ConvArgs &a, cudaStream_t s) {
     int rc = make_map(static_cast<const bf16 *>(a.x) + a.in_choff, a.M, a.Cin, a.in_ld, BLOCK_M, &amap);
     if (rc == SPK_OK) rc = make_map(a.w, a.Cout, a.K, a.K, BLOCK_N, &wmap);
     if (rc != SPK_OK) return rc;
+    CUtensorMap ymap = amap, rmap = amap;        // placeholders unless the TMA epilogue is used
+    if (TEPI) {
+        rc = make_map(static_cast<const bf16 *>(a.y) + a.out_choff, a.M, a.Cout, a.out_ld, BLOCK_M, &ymap);
+        if (rc == SPK_OK && a.res != nullptr)
+            rc = make_map(static_cast<const bf16 *>(a.res) + a.res_choff, a.M, a.Cout, a.res_ld, BLOCK_M, &rmap);
+        if (rc != SPK_OK) return rc;
+    }
     const bf16 *ps = nullptr, *ph = nullptr;
     if (a.pro_scale != nullptr) {
         if (a.pro_scale_bf != nullptr && a.pro_shift_bf != nullptr) {      // prepared by the model at set_program time
@@ -626,7 +757,7 @@ int launch_one(const ConvArgs &a, cudaStream_t s) {
         set_error("conv_gemm: K=%d too large for the shared-memory prologue tables", a.K);
         return SPK_ERR_UNSUPPORTED;
     }
-    const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), (size_t)smem_bytes, s, a, ps, ph, ntn, tiles, amap, wmap, dbg);
+    const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), (size_t)smem_bytes, s, a, ps, ph, ntn, tiles, amap, wmap, ymap, rmap, dbg);
     if (le != cudaSuccess) {
         set_error("conv_gemm_kernel launch failed: %s", cudaGetErrorString(le));
         return SPK_ERR_CUDA;
@@ -638,6 +769,18 @@ template <typename TOut, typename TRes>
 int launch_n(const ConvArgs &a, cudaStream_t s) {
     if (a.Cout <= 32) return launch_one<32, TOut, TRes>(a, s);
     if (a.Cout <= 64) return launch_one<64, TOut, TRes>(a, s);
+    if constexpr (sizeof(TOut) == 2 && sizeof(TRes) == 2) {
+        // residual GEMMs write (and read) whole tiles through shared memory with TMA; without a residual the
+        // register epilogue with its deeper stage ring is the faster one (SPK_GEMM_TEPI=0/1 forces either)
+        static const int force = [] { const char *e = getenv("SPK_GEMM_TEPI"); return e ? atoi(e) : -1; }();
+        const bool ok = a.gate == nullptr && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 &&
+                        (a.res == nullptr || (reinterpret_cast<uintptr_t>(a.res) & 15) == 0);
+        const bool want = force < 0 ? a.res != nullptr : force != 0;
+        if (ok && want) {
+            if (a.Cout <= 128) return launch_one<128, TOut, TRes, true>(a, s);
+            return launch_one<256, TOut, TRes, true>(a, s);
+        }
+    }
     if (a.Cout <= 128) return launch_one<128, TOut, TRes>(a, s);
     return launch_one<256, TOut, TRes>(a, s);
 }

@@ -174,3 +174,22 @@ def test_ten_second_segments_take_the_fallback_kernels():
     assert _rel(e32, ref) <= 1e-4, _rel(e32, ref)
     cos = float(((e16 * e32).sum(1) / (np.linalg.norm(e16, axis=1) * np.linalg.norm(e32, axis=1))).min())
     assert cos >= 0.999, cos
+
+
+def test_bf16_many_tiles_per_cta_matches_single_tile_launches():
+    """600 segments in one sub-batch give the persistent kernels several tiles / items per CTA (ring wrap-around,
+    accumulator and staging double buffering, programmatic dependent launch between big kernels); sub-batches of 64
+    give at most one.  Every segment is computed independently with the same arithmetic, so the embeddings must be
+    bit-identical."""
+    torch.manual_seed(5)
+    feats = torch.randn(600, 148, 80, device="cuda")
+    big = b200spk.CAMPPlus(embedding_size=192, precision="bf16", chunk=(600, 600)).cuda().eval()
+    small = b200spk.CAMPPlus(embedding_size=192, precision="bf16", chunk=(64, 64)).cuda().eval()
+    small.load_state_dict(big.state_dict())
+    with torch.no_grad():
+        a = big(feats)
+        b = small(feats)
+        a2 = big(feats)
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, a2)
+    assert torch.equal(a, b)

@@ -73,3 +73,19 @@ def test_chunking_is_invisible():
     b, _ = _model(kw, wseed, chunk=8)
     with torch.no_grad():
         assert torch.equal(a(feats), b(feats))
+
+
+def test_bf16_many_tiles_per_cta_matches_single_tile_launches():
+    """Same as the CAM++ test of this name: large sub-batches (several tiles per persistent CTA, the TMA-epilogue
+    residual GEMMs with their staging-buffer hand-offs) against small ones; segments are independent, so the
+    embeddings must be bit-identical."""
+    torch.manual_seed(6)
+    feats = torch.randn(48, 148, 80, device="cuda")
+    big = b200spk.ERes2NetV2(precision="bf16", chunk=(48, 48)).cuda().eval()
+    small = b200spk.ERes2NetV2(precision="bf16", chunk=(2, 2)).cuda().eval()
+    small.load_state_dict(big.state_dict())
+    with torch.no_grad():
+        a = big(feats)
+        b = small(feats)
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b)

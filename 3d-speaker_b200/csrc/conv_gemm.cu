@@ -770,8 +770,10 @@ int launch_n(const ConvArgs &a, cudaStream_t s) {
     if (a.Cout <= 32) return launch_one<32, TOut, TRes>(a, s);
     if (a.Cout <= 64) return launch_one<64, TOut, TRes>(a, s);
     if constexpr (sizeof(TOut) == 2 && sizeof(TRes) == 2) {
-        // residual GEMMs write (and read) whole tiles through shared memory with TMA; without a residual the
-        // register epilogue with its deeper stage ring is the faster one (SPK_GEMM_TEPI=0/1 forces either)
+        // residual GEMMs write (and read) whole tiles through shared memory with TMA; without a residual the register
+        // epilogue with its deeper stage ring is used.  SPK_GEMM_TEPI=0/1 forces either for experiments: forcing it on
+        // is faster for ECAPA-TDNN (+12 %) but the CAM++ forward at 2048-segment sub-batches then ends in a launch
+        // failure that is not understood yet (known issues) - do not ship it forced.
         static const int force = [] { const char *e = getenv("SPK_GEMM_TEPI"); return e ? atoi(e) : -1; }();
         const bool ok = a.gate == nullptr && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 &&
                         (a.res == nullptr || (reinterpret_cast<uintptr_t>(a.res) & 15) == 0);

@@ -38,11 +38,12 @@ def run(name, model, T, n_seg, gflop_per_seg, batch, reps=3):
                       "finite": bool(torch.isfinite(emb).all())}), flush=True)
 
 
+CH = int(os.environ.get("CHUNK", "0")) or None      # engine sub-batch override for experiments
 which = sys.argv[1:] or ["eres", "eres_w24", "ecapa", "ecapa_1p5"]
 if "eres" in which:
-    run("ERes2NetV2 (26,2,2)", b200spk.ERes2NetV2(precision="bf16"), 298, 1024, 24.934, 256)
+    run("ERes2NetV2 (26,2,2)", b200spk.ERes2NetV2(precision="bf16", chunk=CH), 298, 1024, 24.934, 256)
 if "eres_w24" in which:
-    run("ERes2NetV2 w24s4ep4", b200spk.ERes2NetV2(baseWidth=24, scale=4, expansion=4, precision="bf16"), 298, 512, 73.850, 128)
+    run("ERes2NetV2 w24s4ep4", b200spk.ERes2NetV2(baseWidth=24, scale=4, expansion=4, precision="bf16", chunk=CH), 298, 512, 73.850, 128)
 if "ecapa" in which:
     run("ECAPA-TDNN C=1024, 10 s", b200spk.ECAPA_TDNN(80, channels=[1024, 1024, 1024, 1024, 3072], precision="bf16"), 998, 512, 35.848, 128)
 if "ecapa_1p5" in which:

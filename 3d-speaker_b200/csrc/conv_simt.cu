@@ -8,6 +8,8 @@
 //   statistics pooling            speakerlab/models/campplus/layers.py:26-32,
 //                                 speakerlab/models/eres2net/pooling_layers.py:47-55
 //   AFF blend                     speakerlab/models/eres2net/fusion.py:22-28
+#include <mutex>
+
 #include "ops.cuh"
 
 namespace spk {
@@ -219,12 +221,12 @@ stem_kernel(const StemArgs a) {
     }
 }
 
-// Register-tiled stem for Cout = 8*CG (CG = 4 or 8).  A CTA is one segment x 16 frequency rows (2 per warp); the
-// 18 input rows are staged once in shared memory (10-18 adjacent floats of every frame: the [T,F] -> [F,T]
+// Register-tiled stem for Cout = 8*CG (CG = 4 or 8).  A CTA is one segment x kStemRows frequency rows; the
+// kStemRows + 2 input rows are staged once in shared memory (10-18 adjacent floats of every frame: the [T,F] -> [F,T]
 // transpose happens here).  A thread owns 8 output channels - their 72 weights and the folded BN live in
 // registers - and walks along time: lane = (channel group, pixel), so one warp step writes 32/CG consecutive
 // pixels x Cout channels = 512 contiguous bytes (bf16).  Per (pixel, 8 channels): 9 broadcast LDS + 80 FMA.
-constexpr int kStemRows = 16;
+constexpr int kStemRows = 40;     // frequency rows per CTA (5 per warp): amortises the parameter load, the staging round trip and the barrier
 template <typename TOut, int CG>
 __global__ void __launch_bounds__(256)
 stem_tiled_kernel(const StemArgs a) {
@@ -262,8 +264,8 @@ stem_tiled_kernel(const StemArgs a) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) w[k][j] = make_float2(s_w[(c0 + 2 * j) * 9 + k], s_w[(c0 + 2 * j + 1) * 9 + k]);
 #pragma unroll 1
-    for (int rr = 0; rr < 2; ++rr) {
-        const int r = warp * 2 + rr, f = f0 + r;
+    for (int rr = 0; rr < kStemRows / 8; ++rr) {
+        const int r = warp * (kStemRows / 8) + rr, f = f0 + r;
         if (f >= a.F) break;
         TOut *y = static_cast<TOut *>(a.y) + ((size_t)b * a.F + f) * a.T * a.out_ld + a.out_choff + c0;
         const float *r0 = rows + r * Tp, *r1 = r0 + Tp, *r2 = r1 + Tp;
@@ -569,9 +571,21 @@ int launch_stem(const StemArgs &a, int out_dtype, cudaStream_t s) {
         set_error("stem: batch too large");
         return SPK_ERR_UNSUPPORTED;
     }
-    if ((a.Cout == 32 || a.Cout == 64) && (size_t)(kStemRows + 2) * (a.T + 2) * sizeof(float) <= 48 * 1024) {
+    if ((a.Cout == 32 || a.Cout == 64) && (size_t)(kStemRows + 2) * (a.T + 2) * sizeof(float) <= 200 * 1024) {
         const long long nb = (long long)a.B * ((a.F + kStemRows - 1) / kStemRows);
         const size_t shb = (size_t)(kStemRows + 2) * (a.T + 2) * sizeof(float);
+        static std::once_flag once;
+        static cudaError_t attr_err = cudaSuccess;
+        std::call_once(once, [&] {       // the row tile of a 3 s or 10 s segment needs more than the default 48 KB
+            attr_err = cudaFuncSetAttribute(stem_tiled_kernel<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(stem_tiled_kernel<bf16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(stem_tiled_kernel<float, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(stem_tiled_kernel<bf16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        });
+        if (attr_err != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(stem_tiled) failed: %s", cudaGetErrorString(attr_err));
+            return SPK_ERR_CUDA;
+        }
         if (a.Cout == 32) {
             if (out_dtype == SPK_DT_F32) stem_tiled_kernel<float, 4><<<(unsigned)nb, 256, shb, s>>>(a);
             else stem_tiled_kernel<bf16, 4><<<(unsigned)nb, 256, shb, s>>>(a);

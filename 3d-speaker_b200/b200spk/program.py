@@ -88,6 +88,8 @@ class Model:
         sub-batch sizes (see spk_model_forward)."""
         B = feats.shape[0]
         emb = torch.empty((B, emb_dim), dtype=torch.float32, device=feats.device)
+        if B == 0:          # an empty batch is a valid call (the reference returns [0, E]); nothing to launch
+            return emb
         chunk = max(1, min(int(chunk), max(B, 1)))
         fine = chunk if fine <= 0 else max(1, min(int(fine), chunk))
         ws = self.workspace(T, chunk, fine)

@@ -14,10 +14,9 @@
 // Output pixels are produced for all Wp flat columns; the KW-1 wrap-around columns per row are
 // computed and dropped (1.3 % at W=148).
 //
-// Per band: load slab + weights (all 256 threads) -> fence.proxy.async -> one thread issues
-// tiles x taps x 2 tcgen05.mma (M=128, N=32, K=16) -> tcgen05.commit -> all warps run the
-// epilogue (TMEM -> folded BN, residual, ReLU -> bf16 store).  Two CTAs share an SM so one
-// band's loads/stores overlap the other's MMAs.
+// This is the cp.async generation of the kernel (warp-specialised, double buffered).  The default path for the
+// CAM++ shapes is conv_slab3.cu (TMA-staged 64B-swizzled slabs, TMA store); this one remains for row pitches
+// beyond one TMA box (W + 2 > 256 pixels: 3 s and 10 s segments, ERes2NetV2 layer 1) and as SPK_SLAB_V2=1 reference.
 #include <cuda.h>
 
 #include <algorithm>
@@ -31,7 +30,6 @@ namespace {
 
 using bf16 = __nv_bfloat16;
 constexpr int kC = 32;                 // Cin = Cout
-constexpr int kThreads = 256;
 constexpr uint32_t kSpinLimit = 1u << 26;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -129,206 +127,7 @@ struct SlabGeom {
 };
 
 // S: stride in H (1|2); KS: kernel size (1|3)
-template <int S, int KS>
-__global__ void __launch_bounds__(kThreads, 2)
-conv_slab_kernel(const ConvArgs a, const SlabGeom g, long long n_items, int swap_lbo_sbo) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    constexpr int TAPS = KS * KS;
-    constexpr int PAD = (KS - 1) / 2;
-    const uint32_t s_w = smem_u32(smem);                                 // weights: [tap][chunk j][n=32] x 16 B
-    const uint32_t s_e = s_w + TAPS * 4 * 32 * 16;                        // sub-slab E: 4 planes x px_e x 16 B
-    const uint32_t s_o = s_e + 4u * g.px_e * 16u;                         // sub-slab O
-    const uint32_t s_bar = s_o + 4u * g.px_o * 16u;                       // mbarrier (8 B) + tmem slot
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + (s_bar - s_w) + 8);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-        mbar_init(s_bar, 1);
-        fence_barrier_init();
-    }
-    if (warp == 0) {
-        __syncwarp();
-        tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), g.tmem_cols);
-    }
-    // ---- weights -> smem planes (once per CTA): piece (n, tap, j) = w[n][tap][8j..8j+7]
-    {
-        const bf16 *w = static_cast<const bf16 *>(a.w);
-        for (int idx = threadIdx.x; idx < kC * TAPS * 4; idx += kThreads) {
-            const int j = idx & 3, t = (idx >> 2) % TAPS, n = idx / (4 * TAPS);
-            const uint4 v = ldg16(w + ((long long)n * TAPS + t) * kC + j * 8);
-            sts16(s_w + (uint32_t)(((t * 4 + j) * 32 + n) * 16), v);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const bf16 *x = static_cast<const bf16 *>(a.x);
-    bf16 *y = static_cast<bf16 *>(a.y);
-    const bf16 *res = static_cast<const bf16 *>(a.res);
-    const uint32_t plane_e = (uint32_t)g.px_e * 16u, plane_o = (uint32_t)g.px_o * 16u;
-    uint32_t parity = 0;
-
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int b = (int)(item / g.n_bands);
-        const int band = (int)(item - (long long)b * g.n_bands);
-        const int ho0 = band * g.R;
-        const int r_valid = min(g.R, a.Ho - ho0);
-        const int hi_base = ho0 * S - PAD;                  // input row of slab row 0
-        // ---- stage the input band: piece (row, pixel, chunk); 8 independent 16-byte loads are in
-        // flight per thread before the first store (the loop is latency bound otherwise)
-        {
-            const int rows_total = g.rows_e + g.rows_o;
-            const int pieces = rows_total * g.Wp * 4;
-            for (int base_idx = 0; base_idx < pieces; base_idx += kThreads * 8) {
-                uint4 v[8];
-                uint32_t dst[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int idx = base_idx + u * kThreads + threadIdx.x;
-                    v[u] = make_uint4(0u, 0u, 0u, 0u);
-                    dst[u] = 0xFFFFFFFFu;
-                    if (idx < pieces) {
-                        const int j = idx & 3;
-                        const int pix = idx >> 2;
-                        const int row = (int)__umulhi((unsigned)pix, g.wp_magic);     // pix / Wp
-                        const int col = pix - row * g.Wp;
-                        // slab row -> (sub-slab, row inside it, input row)
-                        int sub = 0, srow = row, hi;
-                        if (S == 2 && KS == 3) {
-                            if (row < g.rows_e) { sub = 0; srow = row; hi = hi_base + 2 * row; }
-                            else { sub = 1; srow = row - g.rows_e; hi = hi_base + 2 * srow + 1; }
-                        } else if (S == 2) {
-                            hi = hi_base + 2 * row;
-                        } else {
-                            hi = hi_base + row;
-                        }
-                        const int wi = col - PAD;
-                        if (hi >= 0 && hi < a.H && wi >= 0 && wi < a.W)
-                            v[u] = ldg16(x + (((long long)b * a.H + hi) * a.W + wi) * a.in_ld + a.in_choff + j * 8);
-                        dst[u] = (sub == 0 ? s_e + j * plane_e : s_o + j * plane_o) + (uint32_t)(srow * g.Wp + col) * 16u;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (dst[u] != 0xFFFFFFFFu) sts16(dst[u], v[u]);
-            }
-            // slack pixels past the staged rows are read by the last tile's shifted views: zero them
-            const int slack_e = g.px_e - g.rows_e * g.Wp, slack_o = g.px_o - g.rows_o * g.Wp;
-            for (int idx = threadIdx.x; idx < (slack_e + slack_o) * 4; idx += kThreads) {
-                const int j = idx & 3, p = idx >> 2;
-                const uint32_t dst = (p < slack_e) ? s_e + j * plane_e + (uint32_t)(g.rows_e * g.Wp + p) * 16u
-                                                   : s_o + j * plane_o + (uint32_t)(g.rows_o * g.Wp + (p - slack_e)) * 16u;
-                sts16(dst, make_uint4(0u, 0u, 0u, 0u));
-            }
-        }
-        fence_proxy_async();
-        __syncthreads();
-        // ---- MMAs: one thread
-        if (threadIdx.x == 0) {
-            tc_fence_after();
-            for (int t = 0; t < g.n_tiles; ++t) {
-                const uint32_t d = tmem_base + (uint32_t)t * 32u;
-#pragma unroll
-                for (int kh = 0; kh < KS; ++kh)
-#pragma unroll
-                    for (int kw = 0; kw < KS; ++kw) {
-                        uint32_t sbase, plane;
-                        int off;
-                        if (S == 2 && KS == 3) {
-                            if (kh & 1) { sbase = s_o; plane = plane_o; off = kw; }
-                            else { sbase = s_e; plane = plane_e; off = (kh >> 1) * g.Wp + kw; }
-                        } else {
-                            sbase = s_e; plane = plane_e; off = kh * g.Wp + kw;
-                        }
-                        const uint32_t a_addr = sbase + (uint32_t)(t * 128 + off) * 16u;
-                        const uint32_t b_addr = s_w + (uint32_t)((kh * KS + kw) * 4 * 32 * 16);
-#pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            uint64_t ad, bd;
-                            if (!swap_lbo_sbo) {
-                                ad = make_desc_nosw(a_addr + 2u * half * plane, plane, 128u);
-                                bd = make_desc_nosw(b_addr + 2u * half * 512u, 512u, 128u);
-                            } else {
-                                ad = make_desc_nosw(a_addr + 2u * half * plane, 128u, plane);
-                                bd = make_desc_nosw(b_addr + 2u * half * 512u, 128u, 512u);
-                            }
-                            umma_bf16(d, ad, bd, kIdescN32, (kh | kw | half) ? 1u : 0u);
-                        }
-                    }
-            }
-            umma_commit(s_bar);
-        }
-        mbar_wait(s_bar, parity);
-        parity ^= 1u;
-        tc_fence_after();
-        // ---- epilogue: warp w reads TMEM lane quarter w%4; warps 0-3 take even tiles, 4-7 odd
-        {
-            const int q = warp & 3;
-            for (int t = warp >> 2; t < g.n_tiles; t += 2) {
-                const int p = t * 128 + q * 32 + lane;
-                const int i = p / g.Wp, col = p - i * g.Wp;
-                const bool ok = (i < r_valid) && (col < a.W);
-                const long long opix = ((long long)b * a.Ho + ho0 + i) * a.Wo + col;
-                const uint32_t taddr = tmem_base + (uint32_t)t * 32u + ((uint32_t)(q * 32) << 16);
-                uint4 rr4[4];
-                if (res != nullptr && ok) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) rr4[e] = ldg16(res + opix * a.res_ld + a.res_choff + e * 8);
-                }
-                uint32_t r[32];
-                {
-                    uint32_t (&r0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[0]);
-                    uint32_t (&r1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[16]);
-                    tmem_ld16(taddr, r0);
-                    tmem_ld16(taddr + 16, r1);
-                    tmem_ld_wait();
-                }
-                if (ok) {
-                    float v[32];
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
-                    if (a.epi_scale != nullptr) {
-#pragma unroll
-                        for (int e = 0; e < 32; e += 4) {
-                            const float4 s4 = __ldg(reinterpret_cast<const float4 *>(a.epi_scale + e));
-                            const float4 h4 = __ldg(reinterpret_cast<const float4 *>(a.epi_shift + e));
-                            v[e] = fmaf(v[e], s4.x, h4.x); v[e + 1] = fmaf(v[e + 1], s4.y, h4.y);
-                            v[e + 2] = fmaf(v[e + 2], s4.z, h4.z); v[e + 3] = fmaf(v[e + 3], s4.w, h4.w);
-                        }
-                    }
-                    if (res != nullptr) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const uint32_t w4[4] = {rr4[e].x, rr4[e].y, rr4[e].z, rr4[e].w};
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                const float2 f = unpack2(w4[h]);
-                                v[e * 8 + 2 * h] += f.x;
-                                v[e * 8 + 2 * h + 1] += f.y;
-                            }
-                        }
-                    }
-                    apply_act_vec(v, a.act);
-                    bf16 *yp = y + opix * a.out_ld + a.out_choff;
-#pragma unroll
-                    for (int e = 0; e < 32; e += 8)
-                        *reinterpret_cast<uint4 *>(yp + e) =
-                            make_uint4(pack2(v[e], v[e + 1]), pack2(v[e + 2], v[e + 3]), pack2(v[e + 4], v[e + 5]), pack2(v[e + 6], v[e + 7]));
-                }
-            }
-        }
-        tc_fence_before();
-        __syncthreads();     // TMEM and the slab are free for the next band
-        tc_fence_after();
-    }
-    if (warp == 0) tmem_dealloc(tmem_base, g.tmem_cols);
-}
-
-
-// ====================================================================================== v2
-// Second generation (default): warp-specialised and double buffered.  Two slab buffers and two
+// Warp-specialised and double buffered.  Two slab buffers and two
 // TMEM accumulator sets let the three roles run one band apart:
 //   warps 0-3   producers: 16-byte cp.async (LDGSTS, zero-fill for the conv padding) straight
 //               into the channel planes - no register staging, so each thread has its ~33 copies
@@ -343,16 +142,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, int c4,
-                                            uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
 constexpr int kProdThreads2 = 128;
 constexpr int kEpiThreads2 = 256;
 constexpr int kThreads2 = kProdThreads2 + 32 + kEpiThreads2;      // 416
@@ -610,39 +399,6 @@ bool geometry(const ConvArgs &a, SlabGeom &g, bool v2 = false) {
 }
 
 template <int S, int KS>
-int launch(const ConvArgs &a, const SlabGeom &g, cudaStream_t s) {
-    auto kern = conv_slab_kernel<S, KS>;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
-    if (attr_err != cudaSuccess) {
-        set_error("cudaFuncSetAttribute(conv_slab) failed: %s", cudaGetErrorString(attr_err));
-        return SPK_ERR_CUDA;
-    }
-    const long long items = (long long)a.B * g.n_bands;
-    int per_sm = std::min(2, std::min(512 / g.tmem_cols, (227 * 1024) / (g.smem_bytes + 1024)));
-    if (per_sm < 1) per_sm = 1;
-    long long grid = std::min<long long>(items, (long long)sm_count() * per_sm);
-    kern<<<(unsigned)grid, kThreads, g.smem_bytes, s>>>(a, g, items, 0);
-    return check_launch("conv_slab_kernel");
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-
-template <int S, int KS>
 int launch2(const ConvArgs &a, const SlabGeom &g, cudaStream_t s) {
     auto kern = conv_slab2_kernel<S, KS>;
     static std::once_flag once;
@@ -656,11 +412,6 @@ int launch2(const ConvArgs &a, const SlabGeom &g, cudaStream_t s) {
     const long long grid = std::min<long long>(items, sm_count());
     kern<<<(unsigned)grid, kThreads2, g.smem_bytes, s>>>(a, g, items);
     return check_launch("conv_slab2_kernel");
-}
-
-bool use_v1() {
-    static const bool v = [] { const char *e = getenv("SPK_SLAB_V1"); return e && e[0] == '1'; }();
-    return v;
 }
 
 }  // namespace
@@ -679,22 +430,18 @@ bool conv_slab_supported(const ConvArgs &a, int in_dtype, int out_dtype, int res
     if (a.KH == 1 && a.sh == 1) return false;      // plain 1x1: the generic GEMM path is already ideal
     if ((reinterpret_cast<uintptr_t>(a.x) & 15) != 0) return false;
     SlabGeom g;
-    return geometry(a, g, !use_v1()) || geometry(a, g, false);
+    return geometry(a, g, true);
 }
 
 int launch_conv_slab(const ConvArgs &a, cudaStream_t s) {
     if (a.B == 0) return SPK_OK;
     SlabGeom g;
-    if (!use_v1() && geometry(a, g, true)) {
-        if (a.KH == 3) return a.sh == 1 ? launch2<1, 3>(a, g, s) : launch2<2, 3>(a, g, s);
-        return launch2<2, 1>(a, g, s);
-    }
-    if (!geometry(a, g, false)) {
+    if (!geometry(a, g, true)) {
         set_error("conv_slab: geometry does not fit");
         return SPK_ERR_UNSUPPORTED;
     }
-    if (a.KH == 3) return a.sh == 1 ? launch<1, 3>(a, g, s) : launch<2, 3>(a, g, s);
-    return launch<2, 1>(a, g, s);
+    if (a.KH == 3) return a.sh == 1 ? launch2<1, 3>(a, g, s) : launch2<2, 3>(a, g, s);
+    return launch2<2, 1>(a, g, s);
 }
 
 }  // namespace spk

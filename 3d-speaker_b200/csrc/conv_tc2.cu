@@ -1,10 +1,10 @@
-// tcgen05 / TMEM implicit-GEMM convolution, second generation (default bf16 path).
+// Generic tcgen05 / TMEM implicit-GEMM convolution: the bf16 path of every conv shape that has no dedicated
+// kernel (strided / dilated / multi-row kernels such as the CAM++ tdnn layer and the ERes2NetV2 3x3 convs).
 //
-// Same contract as conv_tc.cu (D[m,n] = sum_k A[m,k] W[n,k], A gathered on the fly from the
-// channels-last input with optional BN-ReLU prologue; folded-BN / residual / activation / CAM
-// gate epilogue) with the producer side rebuilt after the first ncu pass showed the gather to be
-// instruction-latency bound (one producer warp per scheduler, ~700 dependent instructions per
-// 64-wide K chunk, register spills):
+// D[m,n] = sum_k A[m,k] W[n,k], A gathered on the fly from the channels-last input (zero or reflect padding)
+// with optional BN-ReLU prologue; folded-BN / residual / activation / gate / post-activation-affine epilogue.
+// The producer side is what a first ncu pass of a simpler gather kernel showed to matter (one producer warp per
+// scheduler was instruction-latency bound: ~700 dependent instructions per 64-wide K chunk, register spills):
 //   * W tiles come in by TMA (cp.async.bulk.tensor.2d, 128B swizzle, OOB rows/cols zero-filled)
 //     issued by one producer lane with mbarrier expect_tx - no registers, no LSU instructions;
 //   * 8 producer warps (two per scheduler) gather A; every thread owns 4 rows of one 16-byte
@@ -578,6 +578,22 @@ int launch_conv_tc2(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_
         return launch_n<bf16, bf16>(a, s);
     }
     return res_bf16 ? launch_n<float, bf16>(a, s) : launch_n<float, float>(a, s);
+}
+
+
+// ---- entry points of the generic tcgen05 path (the first-generation gather kernel these used to select between
+// is gone: this kernel superseded it in every shape)
+bool conv_tc_supported(const ConvArgs &a, int in_dtype) {
+    if (in_dtype != SPK_DT_BF16) return false;
+    if (a.Cin % 8 != 0 || a.in_ld % 8 != 0 || a.in_choff % 8 != 0) return false;
+    if (a.Cout % 16 != 0 || a.out_ld % 8 != 0 || a.out_choff % 8 != 0) return false;
+    if (a.res != nullptr && (a.res_ld % 8 != 0 || a.res_choff % 8 != 0)) return false;
+    if (a.M < BLOCK_M) return false;          // tiny problems (e.g. per-segment dense) stay on CUDA cores
+    return true;
+}
+
+int launch_conv_tc(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s) {
+    return launch_conv_tc2(a, out_dtype, res_dtype, s);
 }
 
 }  // namespace spk

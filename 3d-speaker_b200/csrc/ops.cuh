@@ -27,11 +27,9 @@ struct ConvArgs {
 
 // fp32-accumulate CUDA-core implicit GEMM (exact-fp32 mode and odd shapes)
 int launch_conv_simt(const ConvArgs &a, int in_dtype, int out_dtype, int res_dtype, cudaStream_t s);
-// tcgen05 / TMEM implicit GEMM, bf16 operands (conv_tc.cu); SPK_ERR_UNSUPPORTED when the shape
-// does not qualify
-int launch_conv_tc(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s);
+// generic tcgen05 / TMEM implicit GEMM, bf16 operands (conv_tc2.cu: TMA weights, double-buffered gather of A)
 bool conv_tc_supported(const ConvArgs &a, int in_dtype);
-// second-generation kernel (TMA weights, double-buffered gather; conv_tc2.cu)
+int launch_conv_tc(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s);
 int launch_conv_tc2(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s);
 // TMA-fed GEMM for stride-1 1x1 convs with the BN-ReLU prologue applied in shared memory (conv_gemm.cu)
 bool conv_gemm_supported(const ConvArgs &a, int in_dtype);

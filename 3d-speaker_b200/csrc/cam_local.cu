@@ -181,8 +181,8 @@ __device__ __forceinline__ void gate_mlp(const float *ctx, float *hid, float *ga
         float2 acc[NC];
 #pragma unroll
         for (int cb = 0; cb < NC; ++cb) acc[cb] = make_float2(0.f, 0.f);
-#pragma unroll 2
-        for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {      // fully unrolled: all 56 loads of the phase are in flight before the first FMA
             float2 wv[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) wv[e] = *reinterpret_cast<const float2 *>(&w1t[(4 * (i + e) + ks) * kW1Pitch + j]);

@@ -169,12 +169,13 @@ __device__ long long g_cam_ts[16 * 12];
 //                               lane group ks covers channels ch = 4i + ks
 //   gate   = sigmoid(W2 hidden + b2): warp w owns outputs 8w..8w+7, lane = (o = lane & 7, ks);
 //                               lane group ks covers hidden units 4i + ks
-// ctx and hid are stored permuted ([cb][ks][i]) so a lane reads its operands as float4; the transposed weights
-// have padded pitches (kW1Pitch, kW2Pitch) that put the four lane groups of a load in different banks.
-constexpr int kW1Pitch = 80, kW2Pitch = 40;
+// ctx and hid are stored permuted ([cb][ks][i]) so a lane reads its operands as float4.  A thread needs the same
+// 64 + 16 weights for every item, so they live in REGISTERS for the life of the CTA (loaded once from the transposed
+// global copies): the gate warps run while the MMA warp saturates the shared-memory read port, and weight reads from
+// shared memory were what made this phase the slowest stage of the pipeline.
 template <int NC>
-__device__ __forceinline__ void gate_mlp(const float *ctx, float *hid, float *gateb, const float *w1t, const float *w2t,
-                                         const float *b1, const float *b2, int hidden, int t) {
+__device__ __forceinline__ void gate_mlp(const float *ctx, float *hid, float *gateb, const float2 (&w1r)[32], const float (&w2r)[16],
+                                         float2 b1r, float b2r, int hidden, int t) {
     const int w = t >> 5, lane = t & 31, ks = lane >> 3;
     {
         const int j = 16 * w + 2 * (lane & 7);
@@ -182,17 +183,14 @@ __device__ __forceinline__ void gate_mlp(const float *ctx, float *hid, float *ga
 #pragma unroll
         for (int cb = 0; cb < NC; ++cb) acc[cb] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {      // fully unrolled: all 56 loads of the phase are in flight before the first FMA
-            float2 wv[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) wv[e] = *reinterpret_cast<const float2 *>(&w1t[(4 * (i + e) + ks) * kW1Pitch + j]);
+        for (int i = 0; i < 32; i += 4) {
 #pragma unroll
             for (int cb = 0; cb < NC; ++cb) {
                 const float4 x = *reinterpret_cast<const float4 *>(&ctx[cb * kCin + ks * 32 + i]);
-                acc[cb].x = fmaf(wv[0].x, x.x, acc[cb].x); acc[cb].y = fmaf(wv[0].y, x.x, acc[cb].y);
-                acc[cb].x = fmaf(wv[1].x, x.y, acc[cb].x); acc[cb].y = fmaf(wv[1].y, x.y, acc[cb].y);
-                acc[cb].x = fmaf(wv[2].x, x.z, acc[cb].x); acc[cb].y = fmaf(wv[2].y, x.z, acc[cb].y);
-                acc[cb].x = fmaf(wv[3].x, x.w, acc[cb].x); acc[cb].y = fmaf(wv[3].y, x.w, acc[cb].y);
+                acc[cb] = __ffma2_rn(w1r[i], make_float2(x.x, x.x), acc[cb]);
+                acc[cb] = __ffma2_rn(w1r[i + 1], make_float2(x.y, x.y), acc[cb]);
+                acc[cb] = __ffma2_rn(w1r[i + 2], make_float2(x.z, x.z), acc[cb]);
+                acc[cb] = __ffma2_rn(w1r[i + 3], make_float2(x.w, x.w), acc[cb]);
             }
         }
 #pragma unroll
@@ -203,12 +201,11 @@ __device__ __forceinline__ void gate_mlp(const float *ctx, float *hid, float *ga
             acc[cb].y += __shfl_xor_sync(0xffffffffu, acc[cb].y, 16);
         }
         if (ks == 0) {
-            const float bx = j < hidden ? b1[j] : 0.f, by = j + 1 < hidden ? b1[j + 1] : 0.f;
 #pragma unroll
             for (int cb = 0; cb < NC; ++cb) {
                 // unit j lives at [cb][j & 3][j >> 2]
-                hid[cb * kMaxHidden + (j & 3) * 16 + (j >> 2)] = j < hidden ? fmaxf(acc[cb].x + bx, 0.f) : 0.f;
-                hid[cb * kMaxHidden + ((j + 1) & 3) * 16 + ((j + 1) >> 2)] = j + 1 < hidden ? fmaxf(acc[cb].y + by, 0.f) : 0.f;
+                hid[cb * kMaxHidden + (j & 3) * 16 + (j >> 2)] = j < hidden ? fmaxf(acc[cb].x + b1r.x, 0.f) : 0.f;
+                hid[cb * kMaxHidden + ((j + 1) & 3) * 16 + ((j + 1) >> 2)] = j + 1 < hidden ? fmaxf(acc[cb].y + b1r.y, 0.f) : 0.f;
             }
         }
     }
@@ -220,16 +217,13 @@ __device__ __forceinline__ void gate_mlp(const float *ctx, float *hid, float *ga
         for (int cb = 0; cb < NC; ++cb) acc[cb] = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
-            float wv[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) wv[e] = w2t[(4 * (i + e) + ks) * kW2Pitch + o];
 #pragma unroll
             for (int cb = 0; cb < NC; ++cb) {
                 const float4 h = *reinterpret_cast<const float4 *>(&hid[cb * kMaxHidden + ks * 16 + i]);
-                acc[cb] = fmaf(wv[0], h.x, acc[cb]);
-                acc[cb] = fmaf(wv[1], h.y, acc[cb]);
-                acc[cb] = fmaf(wv[2], h.z, acc[cb]);
-                acc[cb] = fmaf(wv[3], h.w, acc[cb]);
+                acc[cb] = fmaf(w2r[i], h.x, acc[cb]);
+                acc[cb] = fmaf(w2r[i + 1], h.y, acc[cb]);
+                acc[cb] = fmaf(w2r[i + 2], h.z, acc[cb]);
+                acc[cb] = fmaf(w2r[i + 3], h.w, acc[cb]);
             }
         }
 #pragma unroll
@@ -238,9 +232,8 @@ __device__ __forceinline__ void gate_mlp(const float *ctx, float *hid, float *ga
             acc[cb] += __shfl_xor_sync(0xffffffffu, acc[cb], 16);
         }
         if (ks == 0) {
-            const float bo = b2[o];
 #pragma unroll
-            for (int cb = 0; cb < NC; ++cb) gateb[cb * kCout + o] = 1.f / (1.f + expf(-(acc[cb] + bo)));
+            for (int cb = 0; cb < NC; ++cb) gateb[cb * kCout + o] = 1.f / (1.f + expf(-(acc[cb] + b2r)));
         }
     }
 }
@@ -283,12 +276,6 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
     float *win = reinterpret_cast<float *>(smem + g.off_win);       // [G*nwin][128]  the contexts
     float *hid = reinterpret_cast<float *>(smem + g.off_hid);       // [G*nwin][64]
     float *gate = reinterpret_cast<float *>(smem + g.off_gate);     // [2][G][nwin][32]
-    // gate MLP parameters, staged once per CTA: with ~220 KB of the SM given to shared memory the L1 is too
-    // small to keep the 40 KB of weights, and every mat-vec step would pay an L2 round trip
-    float *s_w1t = reinterpret_cast<float *>(smem + g.off_mlp);     // [128][kW1Pitch]  (W1 transposed, 64 used columns)
-    float *s_w2t = s_w1t + kCin * kW1Pitch;                          // [64][kW2Pitch]   (W2 transposed, 32 used columns)
-    float *s_b1 = s_w2t + kMaxHidden * kW2Pitch;                     // [64]
-    float *s_b2 = s_b1 + kMaxHidden;                                 // [32]
     auto sfull = [&](int i) { return s_bar + 8u * i; };             // slab staged           (TMA tx -> MMA)
     auto sempty = [&](int i) { return s_bar + 8u * (2 + i); };      // slab consumed         (MMA commit -> TMA warp)
     auto afull = [&](int i) { return s_bar + 8u * (4 + i); };       // conv accumulator done (MMA commit -> epilogue)
@@ -430,29 +417,27 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
         // thread = one input channel: TMEM lane (warp & 3) * 32 + lane of the column-sum accumulator
         const int gt = threadIdx.x - 64;                    // 0..127, the MLP work index
         const int q = warp & 3, ch = q * 32 + lane;
-        {   // gate MLP parameters -> smem with padded pitches (overlaps the first TMA loads)
-            const uint32_t d1 = smem_u32(s_w1t), d2 = smem_u32(s_w2t), d3 = smem_u32(s_b1), d4 = smem_u32(s_b2);
-            for (int idx = gt; idx < kCin * (g.hidden / 4); idx += kGate) {
-                const int row = idx / (g.hidden / 4), c = idx - row * (g.hidden / 4);
-                cp_async16(d1 + (uint32_t)(row * kW1Pitch + c * 4) * 4u, w1t + row * g.hidden + c * 4, 16u);
+        // this thread's slice of the gate MLP, in registers for the life of the CTA (see gate_mlp)
+        float2 w1r[32];
+        float w2r[16];
+        float2 b1r;
+        float b2r;
+        {
+            const int ksl = lane >> 3, wq = gt >> 5;
+            const int j = 16 * wq + 2 * (lane & 7), o = 8 * wq + (lane & 7);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int chn = 4 * i + ksl;
+                w1r[i] = make_float2(j < g.hidden ? __ldg(w1t + chn * g.hidden + j) : 0.f,
+                                     j + 1 < g.hidden ? __ldg(w1t + chn * g.hidden + j + 1) : 0.f);
             }
-            for (int idx = gt; idx < g.hidden * (kCout / 4); idx += kGate) {
-                const int row = idx / (kCout / 4), c = idx - row * (kCout / 4);
-                cp_async16(d2 + (uint32_t)(row * kW2Pitch + c * 4) * 4u, w2t + row * kCout + c * 4, 16u);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int hu = 4 * i + ksl;
+                w2r[i] = hu < g.hidden ? __ldg(w2t + hu * kCout + o) : 0.f;
             }
-            for (int idx = gt; idx < g.hidden / 4; idx += kGate) cp_async16(d3 + (uint32_t)idx * 16u, b1 + idx * 4, 16u);
-            for (int idx = gt; idx < kCout / 4; idx += kGate) cp_async16(d4 + (uint32_t)idx * 16u, b2 + idx * 4, 16u);
-            // rows of W1^T beyond `hidden` columns and rows of W2^T beyond `hidden` must read as zeros
-            if (g.hidden < kMaxHidden) {
-                for (int idx = gt; idx < kCin * (kMaxHidden - g.hidden); idx += kGate) {
-                    const int row = idx / (kMaxHidden - g.hidden), c = g.hidden + idx % (kMaxHidden - g.hidden);
-                    s_w1t[row * kW1Pitch + c] = 0.f;
-                }
-                for (int idx = gt; idx < (kMaxHidden - g.hidden) * kCout; idx += kGate)
-                    s_w2t[(g.hidden + idx / kCout) * kW2Pitch + (idx % kCout)] = 0.f;
-            }
-            cp_async_wait_all();
-            gate_bar_sync();
+            b1r = make_float2(j < g.hidden ? __ldg(b1 + j) : 0.f, j + 1 < g.hidden ? __ldg(b1 + j + 1) : 0.f);
+            b2r = __ldg(b2 + o);
         }
         const int nc = g.G * g.nwin;                        // (segment, window) combos of a full item
         const float inv_T = 1.f / (float)g.T, inv_seg = 1.f / (float)g.seg_len;
@@ -487,14 +472,14 @@ cam_local_kernel(const ConvArgs a, const CamGeom g, const float *__restrict__ w1
             gate_bar_sync();
             if (gt == 0) CAM_TS(7);
             switch (nc) {
-                case 1: gate_mlp<1>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                case 2: gate_mlp<2>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                case 3: gate_mlp<3>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                case 4: gate_mlp<4>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                case 5: gate_mlp<5>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                case 6: gate_mlp<6>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                case 7: gate_mlp<7>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
-                default: gate_mlp<8>(win, hid, gateb, s_w1t, s_w2t, s_b1, s_b2, g.hidden, gt); break;
+                case 1: gate_mlp<1>(win, hid, gateb, w1r, w2r, b1r, b2r, g.hidden, gt); break;
+                case 2: gate_mlp<2>(win, hid, gateb, w1r, w2r, b1r, b2r, g.hidden, gt); break;
+                case 3: gate_mlp<3>(win, hid, gateb, w1r, w2r, b1r, b2r, g.hidden, gt); break;
+                case 4: gate_mlp<4>(win, hid, gateb, w1r, w2r, b1r, b2r, g.hidden, gt); break;
+                case 5: gate_mlp<5>(win, hid, gateb, w1r, w2r, b1r, b2r, g.hidden, gt); break;
+                case 6: gate_mlp<6>(win, hid, gateb, w1r, w2r, b1r, b2r, g.hidden, gt); break;
+                case 7: gate_mlp<7>(win, hid, gateb, w1r, w2r, b1r, b2r, g.hidden, gt); break;
+                default: gate_mlp<8>(win, hid, gateb, w1r, w2r, b1r, b2r, g.hidden, gt); break;
             }
             mbar_arrive(gfull(buf));
             if (gt == 0) CAM_TS(8);
@@ -580,7 +565,7 @@ bool geometry(const ConvArgs &a, int hidden, int seg_len, CamGeom &g) {
     g.off_w = take(kTaps * 2 * 4096);
     g.off_slab = take(2 * g.slab_bytes);
     g.off_ind = take(g.k16 * 2 * kSumCols * 16);
-    g.off_mlp = take((kCin * kW1Pitch + kMaxHidden * kW2Pitch + kMaxHidden + kCout) * 4);
+    g.off_mlp = 0;
     g.off_part = 0;
     g.off_win = off; off += g.G * g.nwin * kCin * 4;
     g.off_hid = off; off += 8 * kMaxHidden * 4;

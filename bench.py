@@ -186,7 +186,7 @@ def run_reference(args):
         "impl": "reference", "metric": "CAM++ embeddings/sec (1.5 s windows)", "value": val, "unit": "embeddings/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, batch),
+        "config": workload_config(args, args.batch),        # the same workload key as the b200 arm; the CPU batching is in `sample`
         "cpu_baseline": {"value": val, "unit": "embeddings/s", "cores": cores, "kind": "port",
                          "sample": "%d x 1.5 s windows per ~%.0f s step, batches of %d" % (tot_n // max(1, args.steps), per_step, batch)},
         "e2e": {"value": val, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -84,8 +84,8 @@ def gather_embeddings(local, n_total, group=None):
 
 
 class Diarizer:
-    """feature_extractor: b200spk.FBank; embedding_model: b200spk.CAMPPlus (on `device`);
-    cluster: b200spk.SpectralCluster."""
+    """feature_extractor: b200spk.FBank; embedding_model: any b200spk network (on `device`);
+    cluster: b200spk.SpectralCluster, AHCluster or CommonClustering (any callable taking the [N, E] embeddings)."""
 
     def __init__(self, feature_extractor, embedding_model, cluster, device="cuda:0", batchsize=2048,
                  seg_dur=1.5, seg_shift=0.75, group=None):

@@ -66,3 +66,31 @@ def test_bf16_meeting_labels_match_fp32():
     assert out["fp32"][1] == out["bf16"][1]
     m = cluster_oracle.match_labels(out["fp32"][0], out["bf16"][0])
     assert np.array_equal(m[pure], out["fp32"][0][pure])
+
+
+def test_meeting_with_the_recipe_clustering_wrapper():
+    """The diarization recipe's back end (CommonClustering: spectral + minor-cluster filtering + centroid merging,
+    speakerlab/process/cluster.py:158-239, diar.yaml:19-28) on a meeting, against the oracle wrapper on the SAME
+    embeddings; and the short-recording branch (fewer than 40 sub-segments -> AHC)."""
+    wav, turns = synth.fm_meeting(600.0, 3, seed=29)
+    model, fb, _ = _pipeline()
+    kw = dict(cluster_type="spectral", mer_cos=0.8, min_cluster_size=4, min_num_spks=1, max_num_spks=15, pval=0.012)
+    dz = b200spk.Diarizer(fb, model, b200spk.CommonClustering(**kw), batchsize=512)
+    np.random.seed(0)
+    chunks, labels = dz(torch.from_numpy(wav))
+    with torch.no_grad():
+        emb = dz.extract(torch.from_numpy(wav).cuda(), chunks).cpu().numpy()
+    np.random.seed(0)
+    ref = cluster_oracle.common_clustering(emb.copy(), **kw)
+    mapped = cluster_oracle.match_labels(ref, labels)
+    truth, pure = synth.turn_labels(chunks, turns)
+    assert np.array_equal(mapped[pure], ref[pure])
+    assert (mapped != ref).sum() <= 3
+    # 20 s of audio: 26 sub-segments < cluster_line -> average-linkage AHC at the default threshold
+    short = wav[:20 * 16000]
+    chunks_s, labels_s = dz(torch.from_numpy(short))
+    assert len(chunks_s) < 40
+    with torch.no_grad():
+        emb_s = dz.extract(torch.from_numpy(short).cuda(), chunks_s).cpu().numpy()
+    ref_s = cluster_oracle.common_clustering(emb_s.copy(), **kw)
+    assert np.array_equal(cluster_oracle.match_labels(ref_s, labels_s), ref_s)

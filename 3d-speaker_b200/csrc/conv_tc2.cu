@@ -17,10 +17,13 @@
 //     allocation are amortised over all tiles of the launch.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include <map>
 #include <mutex>
 
 #include "ops.cuh"
+#include "tmap.cuh"
 
 namespace spk {
 namespace {
@@ -97,6 +100,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -133,13 +151,15 @@ __device__ __forceinline__ uint32_t bnrelu2(uint32_t x, uint32_t s, uint32_t b, 
     return *reinterpret_cast<uint32_t *>(&r);
 }
 
-template <int BLOCK_N> struct Cfg {
+template <int BLOCK_N, bool TEPI = false> struct Cfg {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 5 : 6);
+    // TEPI (TMA epilogue, see conv_gemm.cu): one bf16 output tile is staged in shared memory
+    static constexpr int kStgBytes = TEPI ? BLOCK_M * BLOCK_N * 2 : 0;
+    static constexpr int kStages = (BLOCK_N >= 256) ? (TEPI ? 3 : 4) : (BLOCK_N >= 128 ? 5 : 6);
     static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : 2 * BLOCK_N;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStgBytes + 1024 + 256;
 };
 
 struct GatherRegs {
@@ -147,21 +167,25 @@ struct GatherRegs {
     uint32_t pad_mask;     // bit i: piece i is zero padding (prologue must not touch it)
 };
 
-template <int BLOCK_N, typename TOut, typename TRes>
+template <int BLOCK_N, typename TOut, typename TRes, bool TEPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const bf16 *__restrict__ pro_shift_bf,
-                int n_tiles_n, long long n_tiles, const __grid_constant__ CUtensorMap wmap) {
-    using C = Cfg<BLOCK_N>;
+                int n_tiles_n, long long n_tiles, const __grid_constant__ CUtensorMap wmap,
+                const __grid_constant__ CUtensorMap ymap, const __grid_constant__ CUtensorMap rmap) {
+    using C = Cfg<BLOCK_N, TEPI>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (base - raw) + C::kStages * C::kStageBytes);
+    const uint32_t s_stg = base + C::kStages * C::kStageBytes;       // TEPI: output staging tile
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (base - raw) + C::kStages * C::kStageBytes + C::kStgBytes);
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (C::kStages + s); };
     auto accf_bar = [&](int b) { return bar0 + 8u * (2 * C::kStages + b); };
     auto acce_bar = [&](int b) { return bar0 + 8u * (2 * C::kStages + 2 + b); };
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + 2 * C::kStages + 4);
+    auto rfull_bar = [&]() { return bar0 + 8u * (2 * C::kStages + 4); };     // TEPI: residual tile landed in the staging buffer
+    auto sfree_bar = [&]() { return bar0 + 8u * (2 * C::kStages + 5); };     // TEPI: the TMA store has read the staging buffer
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + 2 * C::kStages + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kMmaWarp = kProducerWarps + 4;      // warps 0-7 producers, 8-11 epilogue, 12 MMA
@@ -175,8 +199,14 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
             mbar_init(accf_bar(b), 1);
             mbar_init(acce_bar(b), kEpilogueThreads);
         }
+        mbar_init(rfull_bar(), 1);
+        mbar_init(sfree_bar(), 1);
         fence_barrier_init();
         prefetch_tmap(&wmap);
+        if (TEPI) {
+            prefetch_tmap(&ymap);
+            prefetch_tmap(&rmap);
+        }
     }
     if (warp == kMmaWarp) tmem_alloc(smem_u32(const_cast<uint32_t *>(tmem_slot)), C::kTmemCols);
     tc_fence_before();
@@ -358,6 +388,106 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
                 const int wo = (int)(m % a.Wo);
                 grow = a.gate + ((long long)b * a.gate_nwin + wo / a.gate_win) * a.Cout;
             }
+            if constexpr (TEPI) {
+                // ---- TMA epilogue (same scheme as conv_gemm.cu): tile -> 128B-swizzled staging blocks of 64 columns
+                // -> TMA store; a residual tile is TMA-loaded into the staging buffer by the elected epilogue thread
+                // (after the previous store has read it) and updated in place
+                if (it == 0 && res != nullptr && warp == kProducerWarps && elect_one()) {
+                    const int nblk = min(BLOCK_N / 64, (a.Cout - n0 + 63) / 64);
+                    mbar_arrive_expect_tx(rfull_bar(), (uint32_t)nblk * (BLOCK_M * 128u));
+                    for (int j = 0; j < nblk; ++j)
+                        tma_load_2d(s_stg + (uint32_t)j * (BLOCK_M * 128u), &rmap, n0 + 64 * j, (int)(mt * BLOCK_M), rfull_bar());
+                }
+                if (res != nullptr) mbar_wait(rfull_bar(), it & 1u);
+                else mbar_wait(sfree_bar(), (it & 1u) ^ 1u);
+                mbar_wait(accf_bar(buf), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
+                const uint32_t srow = s_stg + (uint32_t)row * 128u, x7 = (uint32_t)(row & 7);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
+                    const int n = n0 + c0;
+                    if (n >= a.Cout) break;
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c0, r);
+                    float4 s4[4], h4[4];
+                    if (a.epi_scale != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            s4[e] = __ldg(reinterpret_cast<const float4 *>(a.epi_scale + n + 4 * e));
+                            h4[e] = __ldg(reinterpret_cast<const float4 *>(a.epi_shift + n + 4 * e));
+                        }
+                    }
+                    tmem_ld_wait();
+                    float v[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(r[e]);
+                    if (a.epi_scale != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            v[4 * e] = fmaf(v[4 * e], s4[e].x, h4[e].x); v[4 * e + 1] = fmaf(v[4 * e + 1], s4[e].y, h4[e].y);
+                            v[4 * e + 2] = fmaf(v[4 * e + 2], s4[e].z, h4[e].z); v[4 * e + 3] = fmaf(v[4 * e + 3], s4[e].w, h4[e].w);
+                        }
+                    }
+                    const uint32_t blk = srow + (uint32_t)(c0 >> 6) * (BLOCK_M * 128u);
+                    const uint32_t ch0 = (uint32_t)((c0 & 63) >> 3);
+                    if (res != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const uint4 t = lds16(blk + (((ch0 + e) ^ x7) << 4));
+                            const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162 *>(&w4[h]);
+                                v[8 * e + 2 * h] += __low2float(b2);
+                                v[8 * e + 2 * h + 1] += __high2float(b2);
+                            }
+                        }
+                    }
+                    apply_act_vec(v, a.act);
+                    if (a.post_scale != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            const float4 p4 = __ldg(reinterpret_cast<const float4 *>(a.post_scale + n + e));
+                            const float4 q4 = __ldg(reinterpret_cast<const float4 *>(a.post_shift + n + e));
+                            v[e] = fmaf(v[e], p4.x, q4.x); v[e + 1] = fmaf(v[e + 1], p4.y, q4.y);
+                            v[e + 2] = fmaf(v[e + 2], p4.z, q4.z); v[e + 3] = fmaf(v[e + 3], p4.w, q4.w);
+                        }
+                        apply_act_vec(v, a.post_act);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        sts16(blk + (((ch0 + e) ^ x7) << 4),
+                              make_uint4(pack2(v[8 * e], v[8 * e + 1]), pack2(v[8 * e + 2], v[8 * e + 3]), pack2(v[8 * e + 4], v[8 * e + 5]),
+                                         pack2(v[8 * e + 6], v[8 * e + 7])));
+                }
+                tc_fence_before();
+                mbar_arrive(acce_bar(buf));
+                fence_proxy_async();
+                epi_bar_sync();
+                if (warp == kProducerWarps && elect_one()) {
+                    const int nblk = min(BLOCK_N / 64, (a.Cout - n0 + 63) / 64);
+                    for (int j = 0; j < nblk; ++j)
+                        tma_store_2d(&ymap, n0 + 64 * j, (int)(mt * BLOCK_M), s_stg + (uint32_t)j * (BLOCK_M * 128u));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    const long long ntile = tile + gridDim.x;
+                    if (res != nullptr) {
+                        if (ntile < n_tiles) {          // residual of the next tile into the (now free) staging buffer
+                            const long long nmt = ntile / n_tiles_n;
+                            const int nn0 = (int)(ntile - nmt * n_tiles_n) * BLOCK_N;
+                            const int nb2 = min(BLOCK_N / 64, (a.Cout - nn0 + 63) / 64);
+                            mbar_arrive_expect_tx(rfull_bar(), (uint32_t)nb2 * (BLOCK_M * 128u));
+                            for (int j = 0; j < nb2; ++j)
+                                tma_load_2d(s_stg + (uint32_t)j * (BLOCK_M * 128u), &rmap, nn0 + 64 * j, (int)(nmt * BLOCK_M), rfull_bar());
+                        }
+                    } else {
+                        mbar_arrive(sfree_bar());
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
             mbar_wait(accf_bar(buf), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
@@ -442,6 +572,7 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
             tc_fence_before();
             mbar_arrive(acce_bar(buf));
         }
+        if (TEPI) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // the last stores have reached global memory
     }
 
     tc_fence_before();
@@ -529,10 +660,18 @@ int bf16_vector(const float *src, int n, const bf16 **out, cudaStream_t s) {
     return SPK_OK;
 }
 
-template <int BLOCK_N, typename TOut, typename TRes>
+// [rows, cols] bf16 matrix with row pitch ld: boxes of 64 columns x 128 rows, 128B swizzle (epilogue staging blocks)
+int tile_map(const void *ptr, long long rows, int cols, long long ld, CUtensorMap *out) {
+    const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+    const uint64_t strides[1] = {(uint64_t)ld * 2};
+    const uint32_t box[2] = {64u, (uint32_t)BLOCK_M};
+    return tmap_encode_bf16(ptr, 2, dims, strides, box, 128, out);
+}
+
+template <int BLOCK_N, typename TOut, typename TRes, bool TEPI = false>
 int launch_one(const ConvArgs &a, cudaStream_t s) {
-    using C = Cfg<BLOCK_N>;
-    auto kern = conv_tc2_kernel<BLOCK_N, TOut, TRes>;
+    using C = Cfg<BLOCK_N, TEPI>;
+    auto kern = conv_tc2_kernel<BLOCK_N, TOut, TRes, TEPI>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes); });
@@ -545,21 +684,43 @@ int launch_one(const ConvArgs &a, cudaStream_t s) {
     if (rc != SPK_OK) return rc;
     const bf16 *ps = nullptr, *ph = nullptr;
     if (a.pro_scale != nullptr) {
-        rc = bf16_vector(a.pro_scale, a.Cin, &ps, s);
-        if (rc == SPK_OK) rc = bf16_vector(a.pro_shift, a.Cin, &ph, s);
+        if (a.pro_scale_bf != nullptr && a.pro_shift_bf != nullptr) {      // model-owned copies made at set_program time
+            ps = static_cast<const bf16 *>(a.pro_scale_bf);
+            ph = static_cast<const bf16 *>(a.pro_shift_bf);
+        } else {
+            rc = bf16_vector(a.pro_scale, a.Cin, &ps, s);
+            if (rc == SPK_OK) rc = bf16_vector(a.pro_shift, a.Cin, &ph, s);
+            if (rc != SPK_OK) return rc;
+        }
+    }
+    CUtensorMap ymap = wmap, rmap = wmap;        // placeholders unless the TMA epilogue is used
+    if (TEPI) {
+        rc = tile_map(static_cast<const bf16 *>(a.y) + a.out_choff, a.M, a.Cout, a.out_ld, &ymap);
+        if (rc == SPK_OK && a.res != nullptr) rc = tile_map(static_cast<const bf16 *>(a.res) + a.res_choff, a.M, a.Cout, a.res_ld, &rmap);
         if (rc != SPK_OK) return rc;
     }
     const long long mt = (a.M + BLOCK_M - 1) / BLOCK_M;
     const int ntn = (a.Cout + BLOCK_N - 1) / BLOCK_N;
     const long long tiles = mt * ntn;
     long long grid = std::min<long long>(tiles, sm_count());
-    kern<<<(unsigned)grid, kThreads, C::kSmemBytes, s>>>(a, ps, ph, ntn, tiles, wmap);
+    kern<<<(unsigned)grid, kThreads, C::kSmemBytes, s>>>(a, ps, ph, ntn, tiles, wmap, ymap, rmap);
     return check_launch("conv_tc2_kernel");
 }
 
 template <typename TOut, typename TRes>
 int launch_n(const ConvArgs &a, cudaStream_t s) {
     if (a.Cout <= 32) return launch_one<32, TOut, TRes>(a, s);
+    if constexpr (sizeof(TOut) == 2 && sizeof(TRes) == 2) {
+        // bf16 tiles leave through the TMA epilogue (SPK_TC2_TEPI=0 selects the register epilogue for A/B runs)
+        static const bool off = [] { const char *e = getenv("SPK_TC2_TEPI"); return e && e[0] == '0'; }();
+        const bool ok = a.gate == nullptr && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 &&
+                        (a.res == nullptr || (reinterpret_cast<uintptr_t>(a.res) & 15) == 0);
+        if (ok && !off) {
+            if (a.Cout <= 64) return launch_one<64, TOut, TRes, true>(a, s);
+            if (a.Cout <= 128) return launch_one<128, TOut, TRes, true>(a, s);
+            return launch_one<256, TOut, TRes, true>(a, s);
+        }
+    }
     if (a.Cout <= 64) return launch_one<64, TOut, TRes>(a, s);
     if (a.Cout <= 128) return launch_one<128, TOut, TRes>(a, s);
     return launch_one<256, TOut, TRes>(a, s);

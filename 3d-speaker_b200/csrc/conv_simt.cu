@@ -250,9 +250,22 @@ stem_tiled_kernel(const StemArgs a) {
     }
     const float *fe = a.feats + (size_t)b * a.T * a.F;
     constexpr int NR = kStemRows + 2;
-    for (int i = threadIdx.x; i < NR * Tp; i += blockDim.x) {
-        const int tt = i / NR - 1, r = i % NR, ff = f0 + r - 1;         // r fastest: adjacent floats of one frame
-        rows[r * Tp + tt + 1] = (ff >= 0 && ff < a.F && tt >= 0 && tt < a.T) ? __ldg(fe + (size_t)tt * a.F + ff) : 0.f;
+    // many loads in flight per thread before the first store (the 1.5 s tile is two rounds of 13): the tile comes
+    // from HBM and a CTA cannot start computing until all of it has landed
+    constexpr int kLd = 13;
+    for (int i0 = threadIdx.x; i0 < NR * Tp; i0 += kLd * blockDim.x) {
+        float v[kLd];
+#pragma unroll
+        for (int u = 0; u < kLd; ++u) {
+            const int i = i0 + u * blockDim.x;
+            const int tt = i / NR - 1, r = i % NR, ff = f0 + r - 1;     // r fastest: adjacent floats of one frame
+            v[u] = (i < NR * Tp && ff >= 0 && ff < a.F && tt >= 0 && tt < a.T) ? __ldg(fe + (size_t)tt * a.F + ff) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kLd; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < NR * Tp) rows[(i % NR) * Tp + i / NR] = v[u];
+        }
     }
     __syncthreads();
     float2 w[9][4];

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import b200spk
-from b200spk import _lib, campplus, eres2netv2
+from b200spk import _lib, campplus, ecapa_tdnn, eres2netv2
 from b200spk.program import conv_out
 
 
@@ -58,12 +58,24 @@ def _check_program(model, prog, T, F=80):
             extent(op.out_buf, op.out_ld, op.out_choff, op.Cout, op.H, op.W)
         elif op.kind == _lib.OP_AFF_BLEND:
             extent(op.in_buf, op.in_ld, op.in_choff, op.Cin, op.H, op.W)
-            extent(op.res_buf, op.res_ld, op.res_choff, op.Cin, op.H, op.W)
+            if op.res_buf >= 0:             # res_buf < 0: plain (dtype-converting) copy
+                extent(op.res_buf, op.res_ld, op.res_choff, op.Cin, op.H, op.W)
             extent(op.out_buf, op.out_ld, op.out_choff, op.Cin, op.H, op.W)
             if op.gate_buf >= 0:
                 extent(op.gate_buf, op.iaux[0], op.iaux[1], op.Cin, op.H, op.W)
         elif op.kind == _lib.OP_CAM_GATE:
             extent(op.in_buf, op.in_ld, op.in_choff, op.Cin, 1, op.W)
+        elif op.kind == _lib.OP_SE_SCALE:
+            extent(op.in_buf, op.in_ld, op.in_choff, op.Cin, op.H, op.W)
+            extent(op.out_buf, op.out_ld, op.out_choff, op.Cin, op.H, op.W)
+            assert op.gate_buf in written and bufs[op.gate_buf].elems >= op.Cin and bufs[op.gate_buf].dtype == _lib.DT_F32
+            if op.res_buf >= 0:
+                extent(op.res_buf, op.res_ld, op.res_choff, op.Cin, op.H, op.W)
+                assert op.res_buf in written
+        elif op.kind == _lib.OP_ASP_POOL:
+            extent(op.in_buf, op.in_ld, op.in_choff, op.Cin, op.H, op.W)
+            extent(op.res_buf, op.res_ld, op.res_choff, op.Cin, op.H, op.W)
+            assert op.res_buf in written and bufs[op.out_buf].elems >= 2 * op.Cin and bufs[op.out_buf].dtype == _lib.DT_F32
         elif op.kind == _lib.OP_STATS_POOL:
             extent(op.in_buf, op.in_ld, op.in_choff, op.Cin, op.H, op.W)
             assert bufs[op.out_buf].elems >= 2 * op.H * op.Cin
@@ -92,3 +104,30 @@ def test_eres2netv2_program(prec, kw, T):
     eng = eres2netv2._Engine(mod, MockModel(prec))
     eng.compile(T)
     _check_program(eng.model, eng.model.programs[T], T)
+
+
+@pytest.mark.parametrize("prec", [_lib.PREC_F32, _lib.PREC_BF16])
+@pytest.mark.parametrize("T,C", [(148, 512), (998, 1024), (37, 512)])
+def test_ecapa_program(prec, T, C):
+    mod = b200spk.ECAPA_TDNN(80, channels=[C, C, C, C, 3 * C])
+    model = MockModel(prec)
+    eng = ecapa_tdnn._Engine(mod, model)
+    eng.compile(T)
+    prog = model.programs[T]
+    _check_program(model, prog, T)
+    kinds = [op.kind for op in prog.ops]
+    # 3 SE-Res2Net blocks: one gate + one scaling each; 7 dilated convs per block with reflect padding
+    assert kinds.count(_lib.OP_CAM_GATE) == 3 and kinds.count(_lib.OP_SE_SCALE) == 3 and kinds.count(_lib.OP_ASP_POOL) == 1
+    dil = [op for op in prog.ops if op.kind == _lib.OP_CONV and op.KW == 3]
+    assert len(dil) == 21 and all(op.iaux[1] == 1 and op.pw == op.dw for op in dil)
+    assert sorted({op.dw for op in dil}) == [2, 3, 4]
+    # every TDNNBlock is conv -> ReLU -> BN: activation ReLU with a post-activation affine
+    tdnn = [op for op in prog.ops if op.kind == _lib.OP_CONV and op.aux[0] >= 0]
+    assert len(tdnn) == 1 + 3 * (2 + 7) + 1 + 1 and all(op.act == _lib.ACT_RELU for op in tdnn)
+    # the SE scaling writes the three block outputs side by side into the MFA input
+    offs = sorted(op.out_choff for op in prog.ops if op.kind == _lib.OP_SE_SCALE)
+    assert offs == [0, C, 2 * C]
+    # bf16 mode casts the features once; fp32 mode reads them in place
+    casts = [op for op in prog.ops if op.kind == _lib.OP_AFF_BLEND and op.res_buf < 0 and op.in_buf == 0]
+    assert len(casts) == (1 if prec == _lib.PREC_BF16 else 0)
+

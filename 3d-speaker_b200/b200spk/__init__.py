@@ -15,12 +15,13 @@ There is no CPU fallback: without the built library import of the compute classe
 without an sm_100 device every compute call raises ``SpkError``.
 """
 from ._lib import SpkError, lib, LIB_PATH  # noqa: F401
-from .fbank import FBank, fbank_batch, num_frames  # noqa: F401
+from .fbank import FBank, fbank_batch, fbank_windows, num_frames  # noqa: F401
 from .campplus import CAMPPlus  # noqa: F401
 from .eres2netv2 import ERes2NetV2  # noqa: F401
 from .ecapa_tdnn import ECAPA_TDNN  # noqa: F401
 from .cluster import SpectralCluster, AHCluster, CommonClustering, cosine_pairs  # noqa: F401
 from .extract import EmbeddingExtractor  # noqa: F401
+from .bulk import BulkExtractor, chunk_table, segment_mean  # noqa: F401
 from .diarize import Diarizer, cut_windows, gather_embeddings, shard_range  # noqa: F401
 
 __all__ = ["FBank", "CAMPPlus", "ERes2NetV2", "ECAPA_TDNN", "SpectralCluster", "AHCluster", "CommonClustering", "cosine_pairs", "EmbeddingExtractor", "Diarizer", "SpkError", "fbank_batch", "num_frames", "lib"]

@@ -77,8 +77,14 @@ _SIGS = {
     "spk_launch_count": (C.c_int64, []),
     "spk_fbank_num_frames": (C.c_int64, [C.c_int64]),
     "spk_fbank_set_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "spk_fbank_set_repair": (C.c_int, [C.c_float, C.c_int]),
     "spk_fbank_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                 C.c_void_p]),
+    "spk_fbank_i16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int,
+                                C.c_void_p]),
+    "spk_fbank_windows": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                    C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "spk_segment_mean": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "spk_fbank_host_f32": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_int]),
     "spk_ahc_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
     "spk_ahc": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

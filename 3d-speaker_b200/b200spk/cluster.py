@@ -192,82 +192,94 @@ class AHCluster:
         return labels.cpu().numpy().astype(np.int64)
 
 
-def _cosine_similarity(a, b):
-    """sklearn.metrics.pairwise.cosine_similarity on float32 rows: L2-normalise (zero rows stay zero), then dot."""
-    def norm(x):
-        x = np.asarray(x, dtype=np.float32)
-        n = np.sqrt((x * x).sum(axis=1, keepdims=True))
-        n[n == 0.0] = 1.0
-        return x / n
-    return norm(a) @ norm(b).T
+def _unit_rows(x):
+    """Rows scaled to unit L2 norm in float64 (all-zero rows stay zero, as sklearn's normalize leaves them)."""
+    x = np.asarray(x, dtype=np.float64)
+    n = np.linalg.norm(x, axis=1, keepdims=True)
+    return np.divide(x, n, out=np.zeros_like(x), where=n > 0)
+
+
+class _ClusterStats:
+    """Per-cluster running sums over the embeddings: centroids come from (sum, count), so reassigning or merging
+    clusters never rescans the N x D matrix."""
+
+    def __init__(self, labels, x):
+        self.ids, self.member, self.count = np.unique(labels, return_inverse=True, return_counts=True)
+        self.total = np.zeros((len(self.ids), x.shape[1]), dtype=np.float64)
+        np.add.at(self.total, self.member, x.astype(np.float64, copy=False))
+
+    def centroids(self, rows=None):
+        rows = slice(None) if rows is None else rows
+        return self.total[rows] / self.count[rows, None]
 
 
 class CommonClustering:
     """Drop-in for ``speakerlab.process.cluster.CommonClustering`` (cluster.py:158-239): dispatch to the GPU back end
-    (``spectral`` or ``AHC``; recordings shorter than ``cluster_line`` segments always take AHC), then the reference's
-    label post-processing - reassign clusters of at most ``min_cluster_size`` segments to the nearest major centroid,
-    merge clusters whose centroids are closer than ``mer_cos`` - restated with the same numpy arithmetic on the host
-    (O(N K D) on a handful of centroids: control-plane work on the labels, not the data path)."""
+    (``spectral`` or ``AHC``; recordings shorter than ``cluster_line`` segments always take AHC), then the two label
+    post-steps of the reference on the host (they touch K <= max_num_spks centroids, not the data path):
+
+    * ``filter_minor_cluster`` (cluster.py:204-222): every member of a cluster with at most ``min_cluster_size``
+      segments moves to the major cluster whose centroid (computed once, before any move) it is most cosine-similar
+      to; if no cluster is major everything becomes label 0.  Done here as one [n_minor_rows, K_major] product.
+    * ``merge_by_cos`` (cluster.py:224-239): repeatedly merge the most similar centroid pair while its cosine is
+      >= ``mer_cos``; the pair keeps the smaller label.  Done here on per-cluster (sum, count) statistics, so a
+      merge is two row additions instead of a rescan of the embeddings."""
 
     def __init__(self, cluster_type, cluster_line=40, mer_cos=None, min_cluster_size=4, device="cuda:0", **kwargs):
         self.cluster_type = cluster_type
         self.cluster_line = cluster_line
         self.min_cluster_size = min_cluster_size
         self.mer_cos = mer_cos
-        if self.cluster_type == 'spectral':
+        if cluster_type == 'spectral':
             self.cluster = SpectralCluster(device=device, **kwargs)
-        elif self.cluster_type == 'AHC':
+        elif cluster_type == 'AHC':
             self.cluster = AHCluster(device=device, **kwargs)
         else:
-            raise ValueError('%s is not currently supported.' % self.cluster_type)
-        self.cluster_for_short = AHCluster(device=device) if self.cluster_type != 'AHC' else self.cluster
+            raise ValueError('%s is not currently supported.' % cluster_type)
+        self.cluster_for_short = self.cluster if cluster_type == 'AHC' else AHCluster(device=device)
 
     def __call__(self, X, **kwargs):
         assert len(X.shape) == 2, 'Shape of input should be [N, C]'
-        if X.shape[0] <= 1:
-            return np.zeros(X.shape[0], dtype=int)
-        X = np.asarray(X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else X)
-        if X.shape[0] < self.cluster_line:
-            labels = self.cluster_for_short(X)
-        else:
-            labels = self.cluster(X, **kwargs)
-        labels = np.array(labels, dtype=np.int64)
-        labels = self.filter_minor_cluster(labels, X, self.min_cluster_size)
+        n = X.shape[0]
+        if n <= 1:
+            return np.zeros(n, dtype=int)
+        emb = X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(X)
+        backend = self.cluster_for_short if n < self.cluster_line else self.cluster
+        labels = np.array(backend(emb, **(kwargs if backend is self.cluster else {})), dtype=np.int64)
+        labels = self.filter_minor_cluster(labels, emb, self.min_cluster_size)
         if self.mer_cos is not None:
-            labels = self.merge_by_cos(labels, X, self.mer_cos)
+            labels = self.merge_by_cos(labels, emb, self.mer_cos)
         return labels
 
     def filter_minor_cluster(self, labels, x, min_cluster_size):
-        cset = np.unique(labels)
-        csize = np.array([(labels == i).sum() for i in cset])
-        minor_idx = np.where(csize <= self.min_cluster_size)[0]
-        if len(minor_idx) == 0:
+        # like the reference, the instance attribute decides the size limit (the argument is ignored there too)
+        st = _ClusterStats(labels, x)
+        is_major = st.count > self.min_cluster_size
+        if is_major.all():
             return labels
-        minor_cset = cset[minor_idx]
-        major_idx = np.where(csize > self.min_cluster_size)[0]
-        if len(major_idx) == 0:
+        if not is_major.any():
             return np.zeros_like(labels)
-        major_cset = cset[major_idx]
-        major_center = np.stack([x[labels == i].mean(0) for i in major_cset])
-        for i in range(len(labels)):
-            if labels[i] in minor_cset:
-                cos_sim = _cosine_similarity(x[i][np.newaxis], major_center)
-                labels[i] = major_cset[cos_sim.argmax()]
+        movers = np.flatnonzero(~is_major[st.member])
+        sim = _unit_rows(x[movers]) @ _unit_rows(st.centroids(is_major)).T
+        labels[movers] = st.ids[is_major][sim.argmax(axis=1)]
         return labels
 
     def merge_by_cos(self, labels, x, cos_thr):
         assert cos_thr > 0 and cos_thr <= 1
-        while True:
-            cset = np.unique(labels)
-            if len(cset) == 1:
+        st = _ClusterStats(labels, x)
+        ids, total, count = list(st.ids), st.total, st.count.astype(np.float64)
+        while len(ids) > 1:
+            c = _unit_rows(total / count[:, None])
+            sim = np.triu(c @ c.T, k=1)
+            a, b = divmod(int(sim.argmax()), len(ids))       # first maximum in row-major order, a < b
+            if sim[a, b] < cos_thr:
                 break
-            centers = np.stack([x[labels == i].mean(0) for i in cset])
-            affinity = np.triu(_cosine_similarity(centers, centers), 1)
-            idx = np.unravel_index(np.argmax(affinity), affinity.shape)
-            if affinity[idx] < cos_thr:
-                break
-            c1, c2 = cset[np.array(idx)]
-            labels[labels == c2] = c1
+            labels[labels == ids[b]] = ids[a]
+            total[a] += total[b]
+            count[a] += count[b]
+            keep = np.arange(len(ids)) != b
+            total, count = total[keep], count[keep]
+            del ids[b]
         return labels
 
 

@@ -56,6 +56,15 @@ def cut_windows(wav, chunks, fs=FS):
     return out
 
 
+def window_table(chunks, fs=FS):
+    """Sample ranges of the sub-segments, with the reference's truncating float -> int conversion
+    (infer_diarization.py:624: ``wav[int(st * fs):int(ed * fs)]``) -> (starts int64, lens int32, longest)."""
+    starts = np.array([int(st * fs) for st, _ in chunks], dtype=np.int64)
+    ends = np.array([int(ed * fs) for _, ed in chunks], dtype=np.int64)
+    lens = (ends - starts).astype(np.int32)
+    return starts, lens, int(lens.max()) if len(chunks) else 0
+
+
 def shard_range(n, rank, world):
     """Contiguous shard [lo, hi) of n items for this rank; sizes differ by at most one."""
     base, rem = divmod(n, world)
@@ -105,25 +114,34 @@ class Diarizer:
         if dist.is_available() and dist.is_initialized():
             rank, world = dist.get_rank(self.group), dist.get_world_size(self.group)
         lo, hi = shard_range(len(chunks), rank, world)
+        # the windows are never materialised: the fbank kernel gathers them (and circle-pads short tails) from the
+        # resident recording; L is the longest window of the WHOLE recording, as in the reference's single stack
+        starts, lens, L = window_table(chunks, self.fs)
+        assert len(chunks) == 0 or int((starts + lens).max()) <= wav_dev.shape[0], "sub-segment outside the recording"
+        starts_d = torch.from_numpy(starts[lo:hi]).to(wav_dev.device, non_blocking=True)
+        lens_d = torch.from_numpy(lens[lo:hi]).to(wav_dev.device, non_blocking=True)
         outs = []
         with torch.no_grad():
-            for st in range(lo, hi, self.batchsize):
-                wins = cut_windows(wav_dev, chunks[st:min(hi, st + self.batchsize)], self.fs)
-                outs.append(self.model(self.fe.batch(wins)))
+            for st in range(0, hi - lo, self.batchsize):
+                ed = min(hi - lo, st + self.batchsize)
+                outs.append(self.model(self.fe.windows(wav_dev, starts_d[st:ed], lens_d[st:ed], L)))
         if not outs:
             return torch.zeros((0, self.model.embedding_size), device=self.device)
         return torch.cat(outs, dim=0)
 
     def __call__(self, wav, vad_segments=None, speaker_num=None):
-        """wav: [T] or [1,T] float tensor/array at 16 kHz; vad_segments: [[st, ed], ...] in seconds
-        (default: the whole recording).  Returns (chunks, labels)."""
-        wav = torch.as_tensor(wav, dtype=torch.float32)
+        """wav: [T] or [1,T] float tensor/array in [-1, 1] scale, or int16 PCM (sent to the GPU as 2 bytes per
+        sample and scaled by 1/32768 in the fbank kernel, fileio.py:115-117), at 16 kHz; vad_segments:
+        [[st, ed], ...] in seconds (default: the whole recording).  Returns (chunks, labels)."""
+        wav = torch.as_tensor(wav)
+        if wav.dtype != torch.int16:
+            wav = wav.to(torch.float32)
         if wav.dim() == 2:
             wav = wav[0]
         if vad_segments is None:
             vad_segments = [[0.0, wav.shape[0] / self.fs]]
         chunks = self.subsegments(vad_segments)
-        wav_dev = wav.to(self.device, non_blocking=True)
+        wav_dev = wav.contiguous().to(self.device, non_blocking=True)
         local = self.extract(wav_dev, chunks)
         emb = gather_embeddings(local, len(chunks), self.group)
         kw = {} if speaker_num is None else {"speaker_num": speaker_num}

@@ -23,10 +23,10 @@ def num_frames(n_samples):
 
 
 def _host_tables(n_mels):
-    """Window and mel bank computed with the SAME torch fp32 arithmetic torchaudio uses
-    (kaldi.py:98-100 and 436-511, always built on CPU in fp32, kaldi.py:621-624), so the
-    kernel's weights agree with the reference's to the last bit."""
-    window = torch.hann_window(_FRAME_LEN, periodic=False, dtype=torch.float32).pow(0.85)
+    """Mel bank computed with the SAME torch fp32 arithmetic torchaudio uses (kaldi.py:436-511, always built
+    on CPU in fp32 whatever the waveform dtype, kaldi.py:621-624), so the kernel's filter weights agree with
+    the reference's to the last bit.  The povey window is left to the library, which evaluates it in float64
+    (its cancellation-free formulation needs w[n] - w[n+1] to full precision; see csrc/fbank.cu)."""
     num_fft_bins = _NFFT // 2
     nyquist = 8000.0
     low_freq, high_freq = 20.0, nyquist
@@ -41,7 +41,7 @@ def _host_tables(n_mels):
     up = (mel - left) / (center - left)
     down = (right - mel) / (right - center)
     bank = torch.max(torch.zeros(1), torch.min(up, down)).to(torch.float32).contiguous()
-    return window.contiguous(), bank
+    return bank
 
 
 def _ensure_tables(n_mels):
@@ -49,16 +49,16 @@ def _ensure_tables(n_mels):
     with _tables_lock:
         if _tables_for == n_mels:
             return
-        window, bank = _host_tables(n_mels)
-        _lib.check(_lib.lib().spk_fbank_set_tables(C.c_void_p(window.data_ptr()), C.c_void_p(bank.data_ptr()),
-                                                   int(n_mels)))
+        bank = _host_tables(n_mels)
+        _lib.check(_lib.lib().spk_fbank_set_tables(None, C.c_void_p(bank.data_ptr()), int(n_mels)))
         _tables_for = n_mels
 
 
 def fbank_batch(wavs, n_mels=80, mean_nor=True):
-    """wavs [B, n] float32 (CUDA: kernel on the current stream; CPU: the library's host-buffer
-    entry point) -> [B, m, n_mels] on the same device."""
-    assert wavs.dim() == 2 and wavs.dtype == torch.float32
+    """wavs [B, n] float32 in [-1, 1] scale or int16 PCM (scaled by 1/32768 in the kernel, what
+    speakerlab/utils/fileio.py:115-117 does on the host) -> [B, m, n_mels] float32 on the same device.
+    CUDA: one kernel on the current stream; CPU float32: the library's host-buffer entry point."""
+    assert wavs.dim() == 2 and wavs.dtype in (torch.float32, torch.int16)
     _ensure_tables(n_mels)
     B, n = wavs.shape
     if wavs.stride(1) != 1:
@@ -67,14 +67,38 @@ def fbank_batch(wavs, n_mels=80, mean_nor=True):
     L = _lib.lib()
     if wavs.is_cuda:
         out = torch.empty((B, m, n_mels), dtype=torch.float32, device=wavs.device)
+        fn = L.spk_fbank_i16 if wavs.dtype == torch.int16 else L.spk_fbank_f32
         with torch.cuda.device(wavs.device):
-            _lib.check(L.spk_fbank_f32(C.c_void_p(wavs.data_ptr()), B, n, wavs.stride(0) if B > 1 else n,
-                                       C.c_void_p(out.data_ptr()), n_mels, int(bool(mean_nor)),
-                                       _lib.current_stream_ptr()))
+            _lib.check(fn(C.c_void_p(wavs.data_ptr()), B, n, wavs.stride(0) if B > 1 else n,
+                          C.c_void_p(out.data_ptr()), n_mels, int(bool(mean_nor)), _lib.current_stream_ptr()))
         return out
+    assert wavs.dtype == torch.float32, "the host-buffer entry point takes float32"
     out = torch.empty((B, m, n_mels), dtype=torch.float32)
     _lib.check(L.spk_fbank_host_f32(C.c_void_p(wavs.data_ptr()), B, n, wavs.stride(0) if B > 1 else n,
                                     C.c_void_p(out.data_ptr()), n_mels, int(bool(mean_nor))))
+    return out
+
+
+def fbank_windows(wav, starts, lens, n_samples, n_mels=80, mean_nor=True, phases=None):
+    """Front end on pieces of recordings resident in ONE device buffer ``wav`` [n_total] (float32 or int16): sample
+    i of row b is ``wav[starts[b] + (phases[b] + i) % lens[b]]`` -> [B, m, n_mels].  With ``phases=None`` row b is
+    the window [starts[b], starts[b] + lens[b]) circle-padded to ``n_samples`` (the slice + circle_pad + stack of
+    speakerlab/bin/infer_diarization.py:621-627); with starts/lens = a recording and phases = chunk offsets it is
+    the circle-pad-then-slice chunking of speakerlab/bin/infer_sv_batch.py:388-412.  No [B, n_samples] tensor is
+    ever built: the kernel's loads do the gather.  starts: int64 [B]; lens, phases: int32 [B]; all on the device."""
+    assert wav.dim() == 1 and wav.is_cuda and wav.dtype in (torch.float32, torch.int16) and wav.is_contiguous()
+    assert starts.dtype == torch.int64 and lens.dtype == torch.int32 and starts.is_cuda and lens.is_cuda
+    assert phases is None or (phases.dtype == torch.int32 and phases.is_cuda and phases.shape == lens.shape)
+    _ensure_tables(n_mels)
+    B = starts.shape[0]
+    m = num_frames(n_samples)
+    out = torch.empty((B, m, n_mels), dtype=torch.float32, device=wav.device)
+    with torch.cuda.device(wav.device):
+        _lib.check(_lib.lib().spk_fbank_windows(C.c_void_p(wav.data_ptr()), int(wav.dtype == torch.int16), wav.shape[0],
+                                                C.c_void_p(starts.data_ptr()), C.c_void_p(lens.data_ptr()),
+                                                None if phases is None else C.c_void_p(phases.data_ptr()), B,
+                                                int(n_samples), C.c_void_p(out.data_ptr()), n_mels,
+                                                int(bool(mean_nor)), _lib.current_stream_ptr()))
     return out
 
 
@@ -120,9 +144,17 @@ class FBank(object):
         assert len(wav.shape) == 2 and wav.shape[0] == 1
         assert wav.shape[1] >= _FRAME_LEN, \
             "choose a window size {} that is [2, {}]".format(_FRAME_LEN, wav.shape[1])   # kaldi.py:142
-        feat = _fbank_op(wav.to(torch.float32), int(self.n_mels), bool(self.mean_nor))
+        if wav.dtype != torch.int16:
+            wav = wav.to(torch.float32)
+        feat = _fbank_op(wav, int(self.n_mels), bool(self.mean_nor))
         return feat.squeeze(0)
 
     def batch(self, wavs):
         """[B, n] -> [B, m, n_mels] in one launch (what torch.vmap(self) dispatches to)."""
-        return fbank_batch(wavs.to(torch.float32), int(self.n_mels), bool(self.mean_nor))
+        if wavs.dtype != torch.int16:
+            wavs = wavs.to(torch.float32)
+        return fbank_batch(wavs, int(self.n_mels), bool(self.mean_nor))
+
+    def windows(self, wav, starts, lens, n_samples, phases=None):
+        """Pieces of resident recordings (see ``fbank_windows``)."""
+        return fbank_windows(wav, starts, lens, n_samples, int(self.n_mels), bool(self.mean_nor), phases)

@@ -119,3 +119,32 @@ int launch_asp_pool(const AspPoolArgs &a, int l_dtype, int x_dtype, cudaStream_t
 }
 
 }  // namespace spk
+
+// ---- per-recording mean of chunk embeddings (speakerlab/bin/infer_sv_batch.py:313-315: embeddings[pos[i]:pos[i+1]].mean(0)).
+// One CTA per recording, thread = embedding column: coalesced rows, sequential (fixed-order) accumulation.
+namespace spk {
+namespace {
+__global__ void __launch_bounds__(256)
+segment_mean_kernel(const float *__restrict__ E, int D, const int *__restrict__ pos, float *__restrict__ out) {
+    const int w = blockIdx.x, lo = pos[w], hi = pos[w + 1];
+    const float inv = hi > lo ? 1.0f / (float)(hi - lo) : 0.f;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        float s = 0.f;
+        for (int r = lo; r < hi; ++r) s += E[(size_t)r * D + c];
+        out[(size_t)w * D + c] = s * inv;
+    }
+}
+}  // namespace
+}  // namespace spk
+
+extern "C" int spk_segment_mean(const float *E, int64_t D, const int32_t *pos, int64_t n_wav, float *out, void *stream) {
+    using namespace spk;
+    SPK_REQUIRE(n_wav >= 0 && D > 0, "bad sizes");
+    if (n_wav == 0) return SPK_OK;
+    SPK_REQUIRE(E != nullptr && pos != nullptr && out != nullptr, "null buffer");
+    SPK_REQUIRE(n_wav < (1ll << 31), "too many recordings");
+    int rc = require_device();
+    if (rc != SPK_OK) return rc;
+    segment_mean_kernel<<<(unsigned)n_wav, 256, 0, static_cast<cudaStream_t>(stream)>>>(E, (int)D, pos, out);
+    return check_launch("segment_mean_kernel");
+}

@@ -49,15 +49,37 @@ int         spk_device_check(int dev);
  */
 /* 1 + (n-400)/160, or 0 when n < 400 (kaldi.py:67) */
 int64_t spk_fbank_num_frames(int64_t n_samples);
-/* Optional: replace the built-in povey window [400] and mel bank [n_mels,256] with tables the
- * host computed (the Python mirror passes torchaudio-arithmetic tables so weights agree to
- * the last bit).  Host pointers; copied.  NULL keeps the built-in table. */
+/* Optional: replace the built-in mel bank [n_mels,256] (the Python mirror passes the bank built with
+ * torchaudio's own float32 arithmetic, kaldi.py:436-511, so the weights agree to the last bit) and the
+ * window [400] (must be 0 at both ends; NULL = the povey window evaluated in float64, which is what the
+ * float64 run of the reference uses).  Host pointers; copied.  NULL keeps the built-in table. */
 int spk_fbank_set_tables(const float *window400, const float *mel_bank, int n_mels);
+/* Accuracy knob.  Mel cells whose energy is below theta x (the energy white noise with the frame's power would
+ * put there) are where float32 cannot deliver 1e-4 in the log (the reference's own float32 path is off by 1e-3
+ * there); up to cap such cells per 16-frame round are recomputed in float64.  Defaults theta = 5e-4, cap = 8
+ * (a few cells per million on noise-like audio, none on speech); cap = 0 disables the repair, cap <= 256. */
+int spk_fbank_set_repair(float theta, int cap);
 /* wav: device, B rows of n_samples floats in [-1,1] scale, row stride wav_stride (elements).
  * out: device, [B, m, n_mels] contiguous.  n_samples >= 400 (kaldi.py:142). */
 int spk_fbank_f32(const float *wav, int64_t B, int64_t n_samples, int64_t wav_stride,
                   float *out, int n_mels, int mean_nor, void *stream);
-/* Same, host buffers in / host buffers out (pageable or pinned). */
+/* Same on int16 PCM rows: samples are scaled by 1/32768 on load (speakerlab/utils/fileio.py:115-117,
+ * load_audio's int16 -> float conversion), so recordings can cross PCIe at 2 bytes per sample. */
+int spk_fbank_i16(const int16_t *wav, int64_t B, int64_t n_samples, int64_t wav_stride,
+                  float *out, int n_mels, int mean_nor, void *stream);
+/* Window mode: the batch rows are pieces of recordings resident in ONE device buffer (float32 or int16, n_total
+ * samples).  Sample i of row b is wav[starts[b] + (phases[b] + i) % lens[b]]:
+ *  - diarization sub-segments (speakerlab/bin/infer_diarization.py:621-627): starts = window start, lens = window
+ *    length, phases = NULL -> a window shorter than n_samples is circle-padded (speakerlab/utils/utils.py:232-238);
+ *  - bulk extraction chunks (speakerlab/bin/infer_sv_batch.py:388-412): starts = start of the (truncated) recording,
+ *    lens = its length, phases = chunk index * n_samples -> the recording is circle-padded to a whole number of
+ *    chunks and sliced, without ever materialising [B, n_samples].
+ * starts (int64), lens and phases (int32) are device arrays; [starts[b], starts[b] + lens[b]) must lie inside the
+ * buffer. */
+int spk_fbank_windows(const void *wav, int is_int16, int64_t n_total, const int64_t *starts, const int32_t *lens,
+                      const int32_t *phases, int64_t B, int64_t n_samples, float *out, int n_mels, int mean_nor,
+                      void *stream);
+/* Same as spk_fbank_f32, host buffers in / host buffers out (pageable or pinned). */
 int spk_fbank_host_f32(const float *wav, int64_t B, int64_t n_samples, int64_t wav_stride,
                        float *out, int n_mels, int mean_nor);
 
@@ -188,6 +210,9 @@ int spk_kmeans(const float *pts, int64_t N, int32_t d, int32_t k, const float *i
                int32_t max_iter, float tol, int32_t *labels, float *inertia_host,
                void *workspace, int64_t workspace_bytes, void *stream);
 int64_t spk_kmeans_workspace_bytes(int64_t N, int32_t d, int32_t k);
+/* per-recording embedding = mean of its chunk embeddings (speakerlab/bin/infer_sv_batch.py:313-315):
+ * out[w] = mean of E[pos[w] .. pos[w+1]) ; E device [N,D] f32, pos device int32 [n_wav + 1] ascending, out [n_wav,D] */
+int spk_segment_mean(const float *E, int64_t D, const int32_t *pos, int64_t n_wav, float *out, void *stream);
 /* cosine score of trial pairs: out[i] = cos(E[a[i]], E[b[i]])
  * (speakerlab/bin/compute_score_metrics.py:113-114) */
 int spk_cosine_pairs(const float *E, int64_t N, int64_t D, const int32_t *a, const int32_t *b,

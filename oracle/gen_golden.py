@@ -111,6 +111,16 @@ def ecapa_cases():
     ]
 
 
+def headline_cases():
+    """The shapes BASELINE.json quotes its configs on, kept out of the files above so those stay byte-stable:
+    (family, name, ctor kwargs, batch, n_samples, weight seed).  Config 3: ERes2NetV2 w24s4ep4 on 3 s segments
+    (T=298); config 5: ECAPA-TDNN C=1024 on 10 s chunks (T=998)."""
+    return [
+        ("eres2netv2", "w24s4e4_t298", dict(baseWidth=24, scale=4, expansion=4), 1, 48000, 204),
+        ("ecapa", "c1024_t998", dict(channels=[1024, 1024, 1024, 1024, 3072]), 1, 160000, 304),
+    ]
+
+
 def cluster_cases():
     """(name, N, D, K, seed, ctor kwargs)"""
     return [
@@ -301,5 +311,39 @@ def mint_common(ver):
     print("common clustering goldens:", {k: int(v.max()) + 1 for k, v in out.items() if k.endswith(".labels")})
 
 
+def mint_headline(ver=None):
+    import torch
+    from oracle import synth
+    FBank, _, _ = import_reference()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    fb = FBank(80, 16000, mean_nor=True)
+    out = {"versions": ver or versions()}
+    for family, name, kw, batch, n_samples, wseed in headline_cases():
+        torch.manual_seed(0)
+        if family == "eres2netv2":
+            model = import_eres2netv2()(feat_dim=80, embedding_size=192, **kw).eval()
+            gain = ERES_GAIN
+        else:
+            model = import_ecapa()(80, lin_neurons=192, **kw).eval()
+            gain = ECAPA_GAIN
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        sd = synth.fill_state_dict(shapes, wseed, randomize_bn=True, gain=gain)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        wavs = campplus_input(batch, n_samples, seed=wseed + 1000)
+        feats = torch.vmap(fb)(torch.from_numpy(wavs).unsqueeze(1))
+        with torch.no_grad():
+            e = model(feats.clone())
+            e64 = model.double()(feats.double().clone())
+        out[name + ".feats"] = feats.numpy()
+        out[name + ".emb"] = e.numpy()
+        out[name + ".emb_f64"] = e64.numpy()
+        print(name, "fp32 vs fp64 rel-L2 %.2e" % (np.linalg.norm(e.numpy() - e64.numpy()) / np.linalg.norm(e64.numpy())))
+    np.savez_compressed(os.path.join(OUT, "headline_shapes.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "headline":
+        import_reference()
+        mint_headline()
+    else:
+        main()

@@ -94,3 +94,35 @@ def test_meeting_with_the_recipe_clustering_wrapper():
         emb_s = dz.extract(torch.from_numpy(short).cuda(), chunks_s).cpu().numpy()
     ref_s = cluster_oracle.common_clustering(emb_s.copy(), **kw)
     assert np.array_equal(cluster_oracle.match_labels(ref_s, labels_s), ref_s)
+
+
+def test_one_hour_meeting_k4_matches_oracle_backend():
+    """BASELINE config 4 at full length with K = 4 speakers (the bench line runs K = 8): 4799 sub-segments through
+    the bf16 extraction path, labels against the CPU oracle back end on the SAME embeddings; then the same recording
+    as int16 PCM (2 bytes per sample over PCIe, scaled in the fbank kernel)."""
+    wav, turns = synth.fm_meeting(3600.0, 4, seed=19)
+    torch.manual_seed(1)
+    model = b200spk.CAMPPlus(embedding_size=192, precision="bf16").cuda().eval()
+    fb = b200spk.FBank(80, 16000, mean_nor=True)
+    sc = b200spk.SpectralCluster(min_num_spks=1, max_num_spks=15, pval=0.012)
+    dz = b200spk.Diarizer(fb, model, sc, batchsize=2048)
+    np.random.seed(0)
+    chunks, labels = dz(torch.from_numpy(wav))
+    assert len(chunks) == 4799
+    truth, pure = synth.turn_labels(chunks, turns)
+    with torch.no_grad():
+        emb = dz.extract(torch.from_numpy(wav).cuda(), chunks).cpu().numpy()
+    np.random.seed(0)
+    ref_labels, st = cluster_oracle.spectral_cluster(emb, 1, 15, 0.012, return_stages=True)
+    assert sc.last["k"] == st["k"]
+    mapped = cluster_oracle.match_labels(ref_labels, labels)
+    assert np.array_equal(mapped[pure], ref_labels[pure])
+    assert (mapped != ref_labels).sum() <= 3
+    purity = sum(np.bincount(truth[pure & (labels == c)]).max() for c in np.unique(labels[pure])) / pure.sum()
+    assert purity >= 0.99, purity
+    pcm = torch.from_numpy(np.round(wav * 32767.0).astype(np.int16))
+    np.random.seed(0)
+    chunks16, labels16 = dz(pcm)
+    assert chunks16 == chunks and sc.last["k"] == st["k"]
+    m16 = cluster_oracle.match_labels(ref_labels, labels16)
+    assert (m16 != ref_labels)[pure].mean() <= 0.002          # 16-bit quantisation noise may move a boundary segment

@@ -23,15 +23,17 @@ def _run(wavs, mean_nor=True):
     return out.cpu().numpy()
 
 
+TOL = 1e-4      # north-star: fbank within 1e-4 abs
+
+
 def _two_sided(got, ref32, ref64):
-    """(A) as close to the fp64 truth as the reference's own fp32 path is
-    (never worse than 1e-4 unless ref-fp32 itself is), (B) within 1e-4 of ref-fp32 on
-    >= 99.9 % of elements."""
+    """(A) max |ours - ref_fp64| <= 1e-4 EVERYWHERE (the reference's own fp32 run is up to 1.2e-3 from
+    its fp64 run on near-cancelled low-mel cells, so the fp64 run is the truth side), (B) within 1e-4 of ref-fp32
+    on >= 99.9 % of elements."""
     e_truth = np.abs(got - ref64)
-    ref_err = np.abs(ref32 - ref64).max()
-    assert e_truth.max() <= max(1e-4, 1.5 * ref_err), (e_truth.max(), ref_err)
+    assert e_truth.max() <= TOL, e_truth.max()
     assert e_truth.mean() <= 2e-6
-    assert (np.abs(got - ref32) > 1e-4).mean() <= 1e-3
+    assert (np.abs(got - ref32) > TOL).mean() <= 1e-3
 
 
 @pytest.mark.parametrize("case", list(gen_golden.fbank_cases().keys()))
@@ -51,25 +53,106 @@ def test_fbank_bounded_dynamic_range_strict(gold):
 def test_fbank_no_cmn(gold):
     got = _run(gen_golden.fbank_cases()["noise_1p5s"], mean_nor=False)
     ref = gold["noise_1p5s.raw_f32"]
-    assert (np.abs(got - ref) > 1e-4).mean() <= 1e-3
+    assert (np.abs(got - ref) > TOL).mean() <= 1e-3          # vs the reference's fp32 run (itself off on starved cells)
+    ref64 = fbank_oracle.fbank_batch(gen_golden.fbank_cases()["noise_1p5s"], mean_nor=False, dtype=np.float64)
+    assert np.abs(got - ref64).max() <= TOL
 
 
 def test_fbank_vs_oracle_batch():
     wavs = synth.white_noise(37, 24000, seed=77)
     got = _run(wavs)
     ref64 = fbank_oracle.fbank_batch(wavs, dtype=np.float64)
-    assert (np.abs(got - ref64) > 1e-4).mean() <= 1e-3
+    assert np.abs(got - ref64).max() <= TOL
     assert np.abs(got - ref64).mean() < 2e-6
 
 
+def test_fbank_config2_size_vs_fp64_truth():
+    """BASELINE config 2 / SURVEY 8d set A: 1024 x 3 s of 0.1 * randn (torch.manual_seed(1)), every one of the
+    24.4 M cells within 1e-4 of the float64 run (oracle restatement, pinned to the imported reference by
+    tests/test_oracle.py)."""
+    torch.manual_seed(1)
+    wav = 0.1 * torch.randn(1024, 48000)
+    got = b200spk.fbank_batch(wav.cuda(), 80, True).cpu().numpy()
+    worst = 0.0
+    for i in range(0, 1024, 64):
+        ref64 = fbank_oracle.fbank_batch(wav[i:i + 64].numpy(), dtype=np.float64)
+        worst = max(worst, float(np.abs(got[i:i + 64] - ref64).max()))
+    assert worst <= TOL, worst
+
+
 def test_fbank_long_utterance_two_pass_path():
-    # 10 s -> 998 frames: too big for the fused-CMN tile, takes the frame-range + cmn kernels
+    # 10 s -> 998 frames, small batch: frame-range CTAs + the separate CMN kernel
     wavs = synth.white_noise(2, 160000, seed=78)
     got = _run(wavs)
     ref64 = fbank_oracle.fbank_batch(wavs, dtype=np.float64)
     assert got.shape == (2, 998, 80)
-    assert (np.abs(got - ref64) > 1e-4).mean() <= 1e-3
+    assert np.abs(got - ref64).max() <= TOL
     assert np.abs(got.mean(axis=1)).max() < 1e-4          # CMN: zero column means
+
+
+def test_fbank_fused_and_frame_range_paths_agree():
+    # the same utterances through one-CTA-per-utterance (large batch) and frame-range CTAs (small batch)
+    wavs = synth.white_noise(600, 24000, seed=83)
+    x = torch.from_numpy(wavs).cuda()
+    big = b200spk.fbank_batch(x, 80, False)
+    small = b200spk.fbank_batch(x[:3], 80, False)
+    assert torch.equal(big[:3], small)
+    big_n = b200spk.fbank_batch(x, 80, True)
+    small_n = b200spk.fbank_batch(x[:3], 80, True)
+    assert (big_n[:3] - small_n).abs().max().item() < 2e-6      # the two CMN reductions differ in summation order
+
+
+def test_fbank_int16_pcm_matches_float_path():
+    # int16 samples are scaled by 1/32768 on load (fileio.py:115-117): bit-identical to the float path on x / 32768
+    rng = np.random.default_rng(84)
+    pcm = rng.integers(-20000, 20000, size=(5, 24000), dtype=np.int16)
+    a = b200spk.fbank_batch(torch.from_numpy(pcm).cuda(), 80, True)
+    b = b200spk.fbank_batch(torch.from_numpy(pcm.astype(np.float32) / 32768.0).cuda(), 80, True)
+    assert torch.equal(a, b)
+    ref64 = fbank_oracle.fbank_batch(pcm.astype(np.float32) / 32768.0, dtype=np.float64)
+    assert np.abs(a.cpu().numpy() - ref64).max() <= TOL
+
+
+def test_fbank_windows_of_one_recording_match_cut_windows():
+    # the kernel-side gather (+ circle_pad of the short tail window) against materialised windows
+    from b200spk import diarize
+    wav = torch.from_numpy(synth.white_noise(1, 16000 * 7 + 4321, seed=85)[0])
+    chunks = diarize.chunk(0.0, wav.shape[0] / 16000.0)            # last window is shorter than 1.5 s
+    assert chunks[-1][1] - chunks[-1][0] < 1.5
+    wins = diarize.cut_windows(wav, chunks)
+    ref = b200spk.fbank_batch(wins.cuda(), 80, True)
+    starts = torch.tensor([int(st * 16000) for st, _ in chunks], dtype=torch.int64, device="cuda")
+    lens = torch.tensor([int(ed * 16000) - int(st * 16000) for st, ed in chunks], dtype=torch.int32, device="cuda")
+    got = b200spk.fbank_windows(wav.cuda(), starts, lens, wins.shape[1], 80, True)
+    assert torch.equal(got, ref)
+    pcm = (wav * 20000).to(torch.int16)
+    got16 = b200spk.fbank_windows(pcm.cuda(), starts, lens, wins.shape[1], 80, True)
+    ref16 = b200spk.fbank_batch(diarize.cut_windows(pcm, chunks).cuda(), 80, True)
+    assert torch.equal(got16, ref16)
+
+
+def test_fbank_float64_repair_of_starved_cells():
+    """Audio with (almost) nothing below 150 Hz: the low mel cells sit 60 dB under the frame's level, where no
+    float32 pipeline reaches 1e-4 in the log.  With the repair budget opened up the kernel recomputes those cells
+    in float64 and matches the truth; with the repair off it is as far out as the reference's float32 run."""
+    from b200spk import _lib
+    rng = np.random.default_rng(86)
+    x = rng.standard_normal((2, 8000))
+    spec = np.fft.rfft(x, axis=1)
+    freqs = np.fft.rfftfreq(8000, 1 / 16000.0)
+    spec[:, freqs < 150.0] *= 1e-3
+    wavs = (0.1 * np.fft.irfft(spec, n=8000, axis=1)).astype(np.float32)
+    ref64 = fbank_oracle.fbank_batch(wavs, mean_nor=False, dtype=np.float64)
+    L = _lib.lib()
+    try:
+        _lib.check(L.spk_fbank_set_repair(2e-3, 256))
+        on = _run(wavs, mean_nor=False)
+        _lib.check(L.spk_fbank_set_repair(2e-3, 0))
+        off = _run(wavs, mean_nor=False)
+    finally:
+        _lib.check(L.spk_fbank_set_repair(5e-4, 8))
+    assert np.abs(on - ref64).max() <= TOL, np.abs(on - ref64).max()
+    assert np.abs(off - ref64).max() > np.abs(on - ref64).max()
 
 
 def test_fbank_properties_full_size():
@@ -95,9 +178,9 @@ def test_fbank_properties_full_size():
 def test_fbank_strided_rows_and_unaligned():
     wavs = synth.white_noise(3, 24001, seed=80)
     x = torch.from_numpy(wavs).cuda()
-    got = b200spk.fbank_batch(x[:, 1:], 80, True).cpu().numpy()      # odd offset: scalar-load path
+    got = b200spk.fbank_batch(x[:, 1:], 80, True).cpu().numpy()      # rows start at an odd (4-byte aligned) offset
     ref64 = fbank_oracle.fbank_batch(wavs[:, 1:], dtype=np.float64)
-    assert (np.abs(got - ref64) > 1e-4).mean() <= 1e-3
+    assert np.abs(got - ref64).max() <= TOL
 
 
 def test_fbank_class_and_vmap_match_batch():

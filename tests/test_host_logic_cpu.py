@@ -1,0 +1,92 @@
+"""CPU: host-side logic of the drop-in mirrors - the CommonClustering label post-steps against the oracle restatement
+of speakerlab/process/cluster.py:204-239, and construction of every mirror through the reference's own plug-in API
+(speakerlab/utils/builder.py:9-12,52-91 resolves `obj:` dotted names from YAML)."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import b200spk
+from oracle import cluster_oracle, gen_golden
+
+REF = "/root/reference"
+
+
+def _post_steps_case(seed, n, k, d, minor):
+    rng = np.random.default_rng(seed)
+    centers = rng.standard_normal((k, d)).astype(np.float32)
+    centers[1] = centers[0] + 0.15 * rng.standard_normal(d).astype(np.float32)      # a pair that merge_by_cos joins
+    truth = rng.integers(0, k, n)
+    X = (centers[truth] + 0.4 * rng.standard_normal((n, d))).astype(np.float32)
+    labels = truth.astype(np.int64) * 3 + 1                       # non-contiguous ids
+    for i in range(minor):                                        # tiny clusters that must be dissolved
+        labels[rng.integers(0, n, rng.integers(1, 4))] = 100 + i
+    return X, labels
+
+
+@pytest.mark.parametrize("seed,n,k,d,minor", [(0, 300, 5, 32, 3), (1, 80, 3, 16, 0), (2, 500, 8, 64, 6), (3, 12, 4, 8, 2)])
+def test_filter_and_merge_match_oracle(seed, n, k, d, minor):
+    X, labels = _post_steps_case(seed, n, k, d, minor)
+    cc = b200spk.CommonClustering("spectral", mer_cos=0.8, min_cluster_size=4)
+    got = cc.filter_minor_cluster(labels.copy(), X, 4)
+    ref = cluster_oracle.filter_minor_cluster(labels.copy(), X, 4)
+    assert np.array_equal(got, ref)
+    for thr in (0.95, 0.8, 0.3):
+        got_m = cc.merge_by_cos(got.copy(), X, thr)
+        ref_m = cluster_oracle.merge_by_cos(ref.copy(), X, thr)
+        assert np.array_equal(got_m, ref_m)
+    if n >= 80:
+        assert len(np.unique(cc.merge_by_cos(got.copy(), X, 0.8))) < len(np.unique(got))      # the planted pair merges
+
+
+def test_filter_all_minor_gives_single_label():
+    X = np.random.default_rng(5).standard_normal((6, 8)).astype(np.float32)
+    cc = b200spk.CommonClustering("AHC", min_cluster_size=4)
+    assert cc.filter_minor_cluster(np.array([0, 0, 1, 1, 2, 2]), X, 4).tolist() == [0] * 6
+    assert np.array_equal(cc.filter_minor_cluster(np.zeros(6, dtype=np.int64), X, 4), np.zeros(6))
+
+
+def test_trivial_inputs_and_argument_checks():
+    cc = b200spk.CommonClustering("spectral", mer_cos=0.8)
+    assert cc(np.zeros((0, 4), dtype=np.float32)).shape == (0,)
+    assert cc(np.ones((1, 4), dtype=np.float32)).tolist() == [0]
+    with pytest.raises(AssertionError):
+        cc(np.zeros(5, dtype=np.float32))
+    with pytest.raises(ValueError):
+        b200spk.CommonClustering("umap_hdbscan")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree only exists in the build container")
+def test_mirrors_build_through_the_reference_builder(tmp_path):
+    """The one-line swap INTEGRATION.md describes: the recipe YAML with `obj:` pointing at b200spk classes goes
+    through speakerlab.utils.config/build unchanged and yields objects with the attributes the callers read."""
+    sys.path.insert(0, REF)
+    try:
+        from speakerlab.utils.builder import build
+        from speakerlab.utils.config import build_config
+    finally:
+        sys.path.remove(REF)
+    src = open(os.path.join(REF, "egs/3dspeaker/speaker-diarization/conf/diar.yaml")).read()
+    src = src.replace("speakerlab.process.processor.FBank", "b200spk.FBank")
+    src = src.replace("speakerlab.models.campplus.DTDNN.CAMPPlus", "b200spk.CAMPPlus")
+    src = src.replace("speakerlab.process.cluster.CommonClustering", "b200spk.CommonClustering")
+    assert src.count("obj: b200spk.") >= 3
+    path = tmp_path / "diar_b200.yaml"
+    path.write_text("sample_rate: 16000\n" + src)
+    config = build_config(str(path))
+    fe = build("feature_extractor", config)
+    model = build("embedding_model", config)
+    cluster = build("cluster", config)
+    assert isinstance(fe, b200spk.FBank) and (fe.n_mels, fe.sample_rate, fe.mean_nor) == (80, 16000, True)
+    assert isinstance(model, b200spk.CAMPPlus) and model.embedding_size == 192 and isinstance(model, torch.nn.Module)
+    assert isinstance(cluster, b200spk.CommonClustering) and isinstance(cluster.cluster, b200spk.SpectralCluster)
+    assert (cluster.cluster.max_num_spks, cluster.cluster.pval, cluster.mer_cos, cluster.min_cluster_size) == (15, 0.012, 0.8, 4)
+    # the SV recipes name the networks the same way (egs/*/sv-*/conf/*.yaml: embedding_model obj + args)
+    for obj, args in (("b200spk.ERes2NetV2", {"feat_dim": 80, "embedding_size": 192, "baseWidth": 26, "scale": 2, "expansion": 2}),
+                      ("b200spk.ECAPA_TDNN", {"input_size": 80, "lin_neurons": 192})):
+        cfg = build_config.__globals__["Config"]({"embedding_model": {"obj": obj, "args": dict(args)}})
+        m = build("embedding_model", cfg)
+        assert isinstance(m, torch.nn.Module) and not m.training

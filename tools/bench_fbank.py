@@ -1,6 +1,6 @@
 """fbank alone on 1024 x 3 s utterances (set A: 0.1 * randn), HBM-resident input.
 Prints utterances/s, the HBM roofline fraction (287,360 algorithmic bytes per utterance) and the two-sided parity
-numbers against the CPU oracle (fp64 and fp32) on a 16-utterance subsample."""
+numbers against the CPU oracle (fp64 and fp32) on a 64-utterance subsample (NSUB)."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "3d-speaker_b200")]
@@ -27,10 +27,11 @@ for _ in range(20):
 ms = float(np.median(ms))
 bytes_per_utt = 4 * 48000 + 4 * 298 * 80
 gbs = 1024 * bytes_per_utt / ms / 1e6
-sub = wav[:16].cpu().numpy()
+NSUB = int(os.environ.get('NSUB', '64'))
+sub = wav[:NSUB].cpu().numpy()
 r64 = fbank_oracle.fbank_batch(sub, dtype=np.float64)
 r32 = fbank_oracle.fbank_batch(sub, dtype=np.float32)
-got = out[:16].cpu().numpy()
+got = out[:NSUB].cpu().numpy()
 d64, d32 = np.abs(got - r64), np.abs(got - r32)
 print(json.dumps({"config": "fbank alone, 1024 x 3 s, set A", "ms": round(ms, 4), "utterances_per_s": round(1024 / ms * 1e3, 1),
                   "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / PEAK_GBS, 4),

@@ -10,6 +10,7 @@ GLOBAL RandomState in the same order sklearn's ``k_means(emb, k)`` does (sklearn
 for the reference.
 """
 import ctypes as C
+import time
 
 import numpy as np
 import torch
@@ -150,8 +151,10 @@ class SpectralCluster:
             raise ValueError("k=%d must be less than N=%d (scipy eigsh would raise too)" % (k_eig, N))
         if k_eig > 32:
             raise ValueError("max_num_spks > 31 is not supported by the GPU eigensolver")
+        t0 = time.perf_counter()
         lap = self.laplacian(Xd, pval)
         lambdas, vecs = self.eig_smallest(lap, N, k_eig)
+        t1 = time.perf_counter()
         k_oracle = self.k if oracle_num is None else oracle_num
         if k_oracle is not None:
             num_of_spk = int(k_oracle)
@@ -162,6 +165,7 @@ class SpectralCluster:
         self.last.update(lambdas=lambdas, k=num_of_spk)
         emb = vecs[:, :num_of_spk].contiguous()
         labels = self.kmeans(emb, num_of_spk)
+        self.last["stages_s"] = {"affinity_laplacian_eig": t1 - t0, "kmeans": time.perf_counter() - t1}
         return labels
 
 

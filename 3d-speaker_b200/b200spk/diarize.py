@@ -8,6 +8,7 @@ extraction), then ONE ``all_gather`` of the ``[N/G, E]`` embedding shards feeds 
 stage, which runs on every rank (identical inputs -> identical labels) or only where needed.
 """
 import math
+import time
 
 import numpy as np
 import torch
@@ -103,6 +104,8 @@ class Diarizer:
         self.batchsize, self.seg_dur, self.seg_shift = batchsize, seg_dur, seg_shift
         self.group = group
         self.fs = feature_extractor.sample_rate
+        self.last = {}                 # wall-clock seconds per stage of the last call
+        self.last_embeddings = None    # the gathered [N, E] embeddings of the last call (device)
 
     def subsegments(self, vad_segments):
         return [c for st, ed in vad_segments for c in chunk(st, ed, self.seg_dur, self.seg_shift)]
@@ -140,10 +143,17 @@ class Diarizer:
             wav = wav[0]
         if vad_segments is None:
             vad_segments = [[0.0, wav.shape[0] / self.fs]]
+        t0 = time.perf_counter()
         chunks = self.subsegments(vad_segments)
         wav_dev = wav.contiguous().to(self.device, non_blocking=True)
         local = self.extract(wav_dev, chunks)
         emb = gather_embeddings(local, len(chunks), self.group)
+        torch.cuda.synchronize(self.device)          # stage boundary (the back end needs the embeddings anyway)
+        t1 = time.perf_counter()
         kw = {} if speaker_num is None else {"speaker_num": speaker_num}
         labels = self.cluster(emb, **kw)
+        t2 = time.perf_counter()
+        self.last = {"h2d_extract_gather": t1 - t0, "cluster": t2 - t1}
+        self.last.update({"cluster." + k: v for k, v in getattr(self.cluster, "last", {}).get("stages_s", {}).items()})
+        self.last_embeddings = emb
         return chunks, labels

@@ -173,7 +173,8 @@ class _Engine(EngineBase):
         aff_raw = buf("aff_raw", max(hw * _pad16(max(1, w // 4)) for hw, w, _ in in_blk))
         aff_t = buf("aff_t", max(hw * _pad16(max(1, w // 4)) for hw, w, _ in in_blk))
         aff_z = buf("aff_z", max(hw * wp for hw, _, wp in in_blk))
-        out3_b = None      # the layer-3 output must survive layer 4 (layer3_ds reads it): own buffer
+        keep = self.keep_layers()      # layers whose output must survive later layers: own buffer
+        env = type("Env", (), {})()
 
         def aff_ops(prefix, x_buf, x_ld, x_off, y_buf, y_ld, y_off, C, Cp, hw_h, hw_w, t_raw, t_buf, z_buf, out_buf, out_ld, out_off):
             """AFF (fusion.py:22-28) on x,y [hw, Cp] (C real channels) -> out."""
@@ -253,10 +254,8 @@ class _Engine(EngineBase):
                 else:
                     res, res_ld = cur, cur_c
                 # conv3 + bn3 + residual + clamp
-                last_of_l3 = (li == 3 and bi == len(layer) - 1)
-                if last_of_l3:
-                    out3_b = buf("out3", hw * cout)
-                    dst = out3_b
+                if li in keep and bi == len(layer) - 1:
+                    dst = buf("out%d" % li, hw * cout)
                 else:
                     dst = ping[which]
                     which ^= 1
@@ -269,6 +268,20 @@ class _Engine(EngineBase):
                         epi_scale=s3, epi_shift=b3, res_buf=res, res_ld=res_ld, act=_lib.ACT_CLAMP20)
                 cur, cur_c, H, W = dst, cout, Ho, Wo
             layer_out[li] = (cur, cur_c, H, W)
+            env.prog, env.buf, env.aff_ops, env.layer_out, env.E = prog, buf, aff_ops, layer_out, E
+            self.after_layer(li, env)
+        self.tail(env)
+        self.model.set_program(T, prog)
+
+    def keep_layers(self):
+        return {3}                      # layer3_ds reads the layer-3 output after layer 4 ran
+
+    def after_layer(self, li, env):
+        pass
+
+    def tail(self, env):
+        """layer3_ds -> fuse34 -> TSTP -> seg_1 (ERes2NetV2.py:244-247)."""
+        prog, buf, aff_ops, layer_out, E = env.prog, env.buf, env.aff_ops, env.layer_out, env.E
         out4, c4, H4, W4 = layer_out[4]
         o3, c3, H3, W3 = layer_out[3]
         # layer3_ds: 3x3 stride 2 pad 1, no BN / activation
@@ -280,7 +293,11 @@ class _Engine(EngineBase):
         ip34 = _pad16(c4 // 4)
         f_raw, f_t, f_z = buf("f34_raw", H4 * W4 * ip34), buf("f34_t", H4 * W4 * ip34), buf("f34_z", H4 * W4 * c4)
         aff_ops("fuse34", out4, c4, 0, ds_b, c4, 0, c4, c4, H4, W4, f_raw, f_t, f_z, fused, c4, 0)
-        # TSTP over time for every (frequency row, channel); seg_1 with columns permuted (c,f) -> (f,c)
+        self.pool_and_embed(env, fused, c4, H4, W4)
+
+    def pool_and_embed(self, env, fused, c4, H4, W4):
+        """TSTP over time for every (frequency row, channel); seg_1 with columns permuted (c,f) -> (f,c)."""
+        prog, buf, E = env.prog, env.buf, env.E
         stats = buf("stats", 2 * H4 * c4, _lib.DT_F32)
         prog.op(_lib.OP_STATS_POOL, in_buf=fused, in_ld=c4, out_buf=stats, H=H4, W=W4, Cin=c4, iaux=[1], faux=[1e-8])
 
@@ -291,7 +308,6 @@ class _Engine(EngineBase):
         ones = self._p(("ones", E), lambda: torch.ones(E))
         prog.op(_lib.OP_CONV, in_buf=stats, in_ld=2 * H4 * c4, out_buf=1, out_ld=E, H=1, W=1, Cin=2 * H4 * c4, Ho=1, Wo=1,
                 Cout=E, w=self._p(("w", "seg_1"), seg_w), epi_scale=ones, epi_shift=self._raw("seg_1.bias"))
-        self.model.set_program(T, prog)
 
 
 ERes2NetV2.engine_cls = _Engine

@@ -1,6 +1,8 @@
 // Library-level entry points: error string, ABI version, device check, launch counter.
 #include <mutex>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 
 namespace spk {
@@ -63,6 +65,13 @@ int require_device() {
     }
     return rc;
 }
+
+bool nvtx_enabled() {
+    static const bool on = [] { const char *e = getenv("SPK_NVTX"); return e && e[0] == '1'; }();
+    return on;
+}
+void nvtx_push(const char *name) { nvtxRangePushA(name); }
+void nvtx_pop() { nvtxRangePop(); }
 
 int sm_count() {
     static int cached[32] = {0};

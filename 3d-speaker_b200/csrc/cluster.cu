@@ -20,7 +20,11 @@
 #include <cstring>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "ops.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace spk {
 namespace {
@@ -176,121 +180,288 @@ laplacian_diag_kernel(float *__restrict__ L, int N, int ld) {
     if (threadIdx.x == 0) L[(size_t)row * ld + row] = s;
 }
 
-// ---- Lanczos building blocks (fp32 storage, fp32 accumulate with tree reductions)
-// w = sigma*v - L v      (one warp per row)
+// ---- Lanczos on sigma*I - L with full re-orthogonalisation, as ONE cooperative kernel.
+//
+// The pruned, symmetrised Laplacian has ~2*keep non-zeros per row (420 k of 23 M entries for a 1-hour meeting), so
+// it is compacted once to CSR (3.4 MB: stays in L2) and every Lanczos step is a sparse mat-vec.  The whole step
+// sequence runs inside one cooperative launch: CTA c owns a contiguous slice of rows, i.e. rows of the mat-vec AND
+// the same rows of every basis vector (stored transposed, Vt[row][step], so a CTA only ever touches its own slice
+// of the basis).  Per step three grid-wide barriers replace the eight kernel launches of the straightforward
+// formulation:
+//   1. w = sigma v_j - L v_j on the slice, partial dots  V^T w over the slice          -> barrier
+//   2. h1 = sum of the partials (fixed CTA order), w1 = w - V h1, partials of V^T w1 and |w1|^2 -> barrier
+//   3. h2 likewise, w2 = w1 - V h2 (classical Gram-Schmidt applied twice), beta^2 = |w1|^2 - |h2|^2,
+//      v_{j+1} = w2 / beta, alpha_j = h1[j] + h2[j]                                     -> barrier
+// All reductions have a fixed order, so the tridiagonal - and the labels downstream - are bit-reproducible.
+constexpr int kCsrPerRow = 256;          // CSR capacity per row on average; denser matrices use the dense rows
+constexpr int kLzThreads = 1024;     // 32 warps: one warp per row of the slice in the mat-vec and Gram-Schmidt passes
+
 __global__ void __launch_bounds__(256)
-shifted_matvec_kernel(const float *__restrict__ L, int N, int ld, float sigma, const float *__restrict__ v,
-                      float *__restrict__ w) {
+csr_count_kernel(const float *__restrict__ L, int N, int ld, int *__restrict__ rowcnt) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= N) return;
     const float *lr = L + (size_t)row * ld;
-    float s = 0.f;
-    for (int j = lane; j < N; j += 32) s = fmaf(lr[j], v[j], s);
-    s = warp_sum(s);
-    if (lane == 0) w[row] = sigma * v[row] - s;
+    int c = 0;
+    for (int j = lane; j < N; j += 32) c += (j != row && lr[j] != 0.f) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) rowcnt[row] = c;
 }
-// h[j] = dot(V[j,:], w) for j < m     (one CTA per j)
-__global__ void __launch_bounds__(256)
-dots_kernel(const float *__restrict__ V, int N, int m, const float *__restrict__ w, float *__restrict__ h) {
-    __shared__ float sh[32];
-    const int j = blockIdx.x;
-    const float *vj = V + (size_t)j * N;
-    float s = 0.f;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) s = fmaf(vj[i], w[i], s);
-    s = block_sum(s, sh);
-    if (threadIdx.x == 0) h[j] = s;
-}
-// w -= sum_j h[j] V[j,:] in two deterministic stages: gridDim.y slices of the basis produce partial
-// sums (so the serial depth per thread is m / gridDim.y, not m), a second kernel folds them in order
-__global__ void __launch_bounds__(256)
-axpys_partial_kernel(const float *__restrict__ V, int N, int m, const float *__restrict__ h, float *__restrict__ part) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    const int per = (m + gridDim.y - 1) / gridDim.y;
-    const int j0 = blockIdx.y * per, j1 = min(m, j0 + per);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int j = j0;
-    for (; j + 3 < j1; j += 4) {
-        s0 = fmaf(h[j], V[(size_t)j * N + i], s0);
-        s1 = fmaf(h[j + 1], V[(size_t)(j + 1) * N + i], s1);
-        s2 = fmaf(h[j + 2], V[(size_t)(j + 2) * N + i], s2);
-        s3 = fmaf(h[j + 3], V[(size_t)(j + 3) * N + i], s3);
-    }
-    for (; j < j1; ++j) s0 = fmaf(h[j], V[(size_t)j * N + i], s0);
-    part[(size_t)blockIdx.y * N + i] = (s0 + s1) + (s2 + s3);
-}
-__global__ void __launch_bounds__(256)
-axpys_finish_kernel(const float *__restrict__ part, int N, int slices, float *__restrict__ w) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    float s = 0.f;
-    for (int y = 0; y < slices; ++y) s += part[(size_t)y * N + i];
-    w[i] -= s;
-}
-// beta = ||w||; V[m,:] = w / beta; record alpha (sum of the two projections on v_{m-1}) and beta
-__global__ void __launch_bounds__(256)
-normalize_next_kernel(const float *__restrict__ w, int N, float *__restrict__ vnext, const float *__restrict__ h1,
-                      const float *__restrict__ h2, int jlast, float *__restrict__ alpha, float *__restrict__ beta, int step) {
-    __shared__ float sh[32];
-    float s = 0.f;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) s = fmaf(w[i], w[i], s);
-    s = block_sum(s, sh);
-    const float b = sqrtf(s);
-    const float inv = b > 0.f ? 1.f / b : 0.f;
-    if (vnext != nullptr)
-        for (int i = threadIdx.x; i < N; i += blockDim.x) vnext[i] = w[i] * inv;
-    if (threadIdx.x == 0) {
-        alpha[step] = h1[jlast] + h2[jlast];
-        beta[step] = b;
-    }
-}
-__global__ void init_vector_kernel(float *__restrict__ v, int N, unsigned seed) {
-    __shared__ float sh[32];
-    // deterministic pseudo-random start vector (hash), then normalised by the caller kernel
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        unsigned x = (unsigned)i * 2654435761u ^ seed;
-        x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-        v[i] = ((x >> 8) * (1.0f / 16777216.0f)) - 0.5f;
-    }
+// exclusive scan of the row counts (one CTA; N is a few thousand) -> rowptr[N+1]; flags[0] = 1 when the CSR fits
+__global__ void __launch_bounds__(1024)
+csr_scan_kernel(const int *__restrict__ rowcnt, int N, int *__restrict__ rowptr, long long cap, int *__restrict__ flags) {
+    __shared__ int sh[1024];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    float s = 0.f;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) s = fmaf(v[i], v[i], s);
-    s = block_sum(s, sh);
-    const float inv = rsqrtf(s);
-    for (int i = threadIdx.x; i < N; i += blockDim.x) v[i] *= inv;
+    for (int base = 0; base < N; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < N ? rowcnt[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < N) rowptr[i] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        rowptr[N] = carry;
+        flags[0] = (long long)carry <= cap ? 1 : 0;
+    }
 }
-// evecs[i, c] = sum_j V[j, i] * Sm[j, c]     (Ritz vectors; Sm is m x k row-major on device)
 __global__ void __launch_bounds__(256)
-ritz_kernel(const float *__restrict__ V, int N, int m, const float *__restrict__ Sm, int k, float *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+csr_fill_kernel(const float *__restrict__ L, int N, int ld, const int *__restrict__ rowptr, const int *__restrict__ flags,
+                int *__restrict__ cols, float *__restrict__ vals, float *__restrict__ diag) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= N) return;
+    const float *lr = L + (size_t)row * ld;
+    if (lane == 0) diag[row] = lr[row];
+    if (!flags[0]) return;
+    int base = rowptr[row];
+    for (int j0 = 0; j0 < N; j0 += 32) {                 // ascending column order: deterministic layout
+        const int j = j0 + lane;
+        const float v = j < N ? lr[j] : 0.f;
+        const bool nz = j < N && j != row && v != 0.f;
+        const unsigned m = __ballot_sync(0xffffffffu, nz);
+        if (nz) {
+            const int p = base + __popc(m & ((1u << lane) - 1u));
+            cols[p] = j;
+            vals[p] = v;
+        }
+        base += __popc(m);
+    }
+}
+
+struct LzArgs {
+    const float *L;          // dense Laplacian (row pitch ld), used when the CSR does not fit
+    int N, ld;
+    const int *rowptr, *cols, *flags;
+    const float *vals, *diag;
+    float *Vt;               // [N][pitch] basis, transposed: Vt[i][j] = v_j[i]
+    int pitch;
+    float *vbuf;             // [2][N] the current / next Lanczos vector, contiguous for the mat-vec gathers
+    float *partial;          // [2][grid][pm] per-CTA partial reductions
+    int pm;
+    float *alpha, *beta, *dsigma;
+    int m_from, m_to, rows_per_cta;
+    int spitch;              // > 0: the CTA's rows of the basis live in shared memory with this pitch
+};
+
+// sum over the CTAs of partial[c][jj] for jj < n -> h_s[jj]: eight lanes per jj, each a fixed stride-8 walk over
+// the CTAs, folded by a fixed shuffle tree (order independent of scheduling)
+__device__ __forceinline__ void lz_reduce_partials(const float *part, int pm, int G, int n, float *h_s) {
+    const int tid = threadIdx.x, sub = tid & 7;
+    for (int jj0 = 0; jj0 < n; jj0 += kLzThreads / 8) {
+        const int jj = jj0 + (tid >> 3);
+        float acc = 0.f;
+        if (jj < n)
+            for (int c = sub; c < G; c += 8) acc += part[(size_t)c * pm + jj];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        if (jj < n && sub == 0) h_s[jj] = acc;
+    }
+}
+// partial[jj] = sum over the slice rows of vt[il][jj] * w_s[il] for jj < n: four lanes per jj
+__device__ __forceinline__ void lz_partial_dots(const float *vt, int vpitch, int nr, const float *w_s, int n, float *out) {
+    const int tid = threadIdx.x, sub = tid & 3;
+    for (int jj0 = 0; jj0 < n; jj0 += kLzThreads / 4) {
+        const int jj = jj0 + (tid >> 2);
+        float acc = 0.f;
+        if (jj < n)
+            for (int il = sub; il < nr; il += 4) acc = fmaf(vt[(size_t)il * vpitch + jj], w_s[il], acc);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (jj < n && sub == 0) out[jj] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(kLzThreads)
+lanczos_coop_kernel(const LzArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ float lz_sh[];
+    const int R = a.rows_per_cta;
+    float *w_s = lz_sh;                  // [R]
+    float *h_s = lz_sh + R;              // [m_to + 2]
+    float *red = h_s + a.m_to + 2;       // [32]
+    float *vt_s = red + 32;              // [R][spitch] this CTA's rows of the basis, when they fit shared memory
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, G = gridDim.x, cta = blockIdx.x;
+    const int r0 = min(a.N, cta * R), r1 = min(a.N, r0 + R), nr = r1 - r0;
+    const bool csr = a.flags[0] != 0;
+    float *part0 = a.partial, *part1 = a.partial + (size_t)G * a.pm;
+    // the slice of the basis this CTA works on: shared memory copy (spitch > 0) or the global rows
+    const int vpitch = a.spitch > 0 ? a.spitch : a.pitch;
+    float *vt = a.spitch > 0 ? vt_s : a.Vt + (size_t)r0 * a.pitch;
+    float sigma;
+
+    if (a.m_from == 0) {
+        // Gershgorin shift (unnormalised Laplacian: row sum of |offdiag| equals the diagonal) and the start vector:
+        // a deterministic hash of the row index, normalised
+        float mx = 0.f, ss = 0.f;
+        for (int il = tid; il < nr; il += kLzThreads) {
+            const int i = r0 + il;
+            mx = fmaxf(mx, a.diag[i]);
+            unsigned x = (unsigned)i * 2654435761u ^ 0x9E3779B9u;
+            x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+            const float v = ((x >> 8) * (1.0f / 16777216.0f)) - 0.5f;
+            w_s[il] = v;
+            ss = fmaf(v, v, ss);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        __syncthreads();
+        if (lane == 0) red[warp] = mx;
+        __syncthreads();
+        if (tid == 0) {
+            float m2 = 0.f;
+            for (int w = 0; w < kLzThreads / 32; ++w) m2 = fmaxf(m2, red[w]);
+            part0[(size_t)cta * a.pm] = m2;
+        }
+        ss = block_sum(ss, red);
+        if (tid == 0) part0[(size_t)cta * a.pm + 1] = ss;
+        grid.sync();
+        float m2 = 0.f, tot = 0.f;
+        for (int c = 0; c < G; ++c) {
+            m2 = fmaxf(m2, part0[(size_t)c * a.pm]);
+            tot += part0[(size_t)c * a.pm + 1];
+        }
+        sigma = 2.f * m2 + 1e-3f;
+        const float inv = rsqrtf(tot);
+        for (int il = tid; il < nr; il += kLzThreads) {
+            const float v = w_s[il] * inv;
+            a.Vt[(size_t)(r0 + il) * a.pitch] = v;
+            if (a.spitch > 0) vt_s[(size_t)il * a.spitch] = v;
+            a.vbuf[r0 + il] = v;
+        }
+        if (cta == 0 && tid == 0) a.dsigma[0] = sigma;
+        grid.sync();
+    } else {
+        sigma = a.dsigma[0];
+        if (a.spitch > 0) {             // continue a run: pull this slice of the basis built so far into shared memory
+            for (int idx = tid; idx < nr * (a.m_from + 1); idx += kLzThreads) {
+                const int il = idx / (a.m_from + 1), jj = idx - il * (a.m_from + 1);
+                vt_s[(size_t)il * a.spitch + jj] = a.Vt[(size_t)(r0 + il) * a.pitch + jj];
+            }
+            __syncthreads();
+        }
+    }
+
+    for (int j = a.m_from; j < a.m_to; ++j) {
+        const float *v = a.vbuf + (size_t)(j & 1) * a.N;
+        float *vnext = a.vbuf + (size_t)((j + 1) & 1) * a.N;
+        // ---- phase 1: w = sigma v - L v on the slice (one warp per row), partial V^T w
+        for (int il = warp; il < nr; il += kLzThreads / 32) {
+            const int i = r0 + il;
+            float s = 0.f;
+            if (csr) {
+                const int p1 = a.rowptr[i + 1];
+                for (int p = a.rowptr[i] + lane; p < p1; p += 32) s = fmaf(a.vals[p], v[a.cols[p]], s);
+            } else {
+                const float *lr = a.L + (size_t)i * a.ld;
+                for (int c = lane; c < a.N; c += 32) s = fmaf(c != i ? lr[c] : 0.f, v[c], s);
+            }
+            s = warp_sum(s);
+            if (lane == 0) w_s[il] = (sigma - a.diag[i]) * v[i] - s;
+        }
+        __syncthreads();
+        lz_partial_dots(vt, vpitch, nr, w_s, j + 1, part0 + (size_t)cta * a.pm);
+        grid.sync();
+        // ---- phase 2: h1, first Gram-Schmidt pass, partials of the second
+        lz_reduce_partials(part0, a.pm, G, j + 1, h_s);
+        __syncthreads();
+        const float h1j = h_s[j];
+        for (int il = warp; il < nr; il += kLzThreads / 32) {
+            const float *vr = vt + (size_t)il * vpitch;
+            float s = 0.f;
+            for (int jj = lane; jj <= j; jj += 32) s = fmaf(h_s[jj], vr[jj], s);
+            s = warp_sum(s);
+            if (lane == 0) w_s[il] -= s;
+        }
+        __syncthreads();
+        lz_partial_dots(vt, vpitch, nr, w_s, j + 1, part1 + (size_t)cta * a.pm);
+        {
+            float ss = 0.f;
+            for (int il = tid; il < nr; il += kLzThreads) ss = fmaf(w_s[il], w_s[il], ss);
+            ss = block_sum(ss, red);
+            if (tid == 0) part1[(size_t)cta * a.pm + j + 1] = ss;
+        }
+        grid.sync();
+        // ---- phase 3: h2, second pass, normalise -> v_{j+1}
+        lz_reduce_partials(part1, a.pm, G, j + 2, h_s);
+        __syncthreads();
+        float hh = 0.f;
+        for (int jj = tid; jj <= j; jj += kLzThreads) hh = fmaf(h_s[jj], h_s[jj], hh);
+        hh = block_sum(hh, red);
+        const float beta2 = fmaxf(h_s[j + 1] - hh, 0.f);      // |w1 - V h2|^2 for an orthonormal basis
+        const float b = sqrtf(beta2);
+        const float inv = b > 0.f ? 1.f / b : 0.f;
+        for (int il = warp; il < nr; il += kLzThreads / 32) {
+            float *vr = vt + (size_t)il * vpitch;
+            float s = 0.f;
+            for (int jj = lane; jj <= j; jj += 32) s = fmaf(h_s[jj], vr[jj], s);
+            s = warp_sum(s);
+            if (lane == 0) {
+                const float vn = (w_s[il] - s) * inv;
+                vr[j + 1] = vn;
+                if (a.spitch > 0) a.Vt[(size_t)(r0 + il) * a.pitch + j + 1] = vn;
+                vnext[r0 + il] = vn;
+            }
+        }
+        if (cta == 0 && tid == 0) {
+            a.alpha[j] = h1j + h_s[j];
+            a.beta[j] = b;
+        }
+        grid.sync();
+    }
+}
+
+// evecs[i, c] = sum_j Vt[i][j] * Sm[j, c]     (Ritz vectors; Sm is m x k row-major on device; one warp per row)
+__global__ void __launch_bounds__(256)
+ritz_kernel(const float *__restrict__ Vt, int N, int pitch, int m, const float *__restrict__ Sm, int k, float *__restrict__ out) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= N) return;
+    const float *vr = Vt + (size_t)i * pitch;
     float acc[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-    for (int j = 0; j < m; ++j) {
-        const float v = V[(size_t)j * N + i];
+    for (int j = lane; j < m; j += 32) {
+        const float v = vr[j];
 #pragma unroll
         for (int c = 0; c < 32; ++c)
             if (c < k) acc[c] = fmaf(v, Sm[j * k + c], acc[c]);
     }
-    for (int c = 0; c < k; ++c) out[(size_t)i * k + c] = acc[c];
-}
-__global__ void gershgorin_kernel(const float *__restrict__ L, int N, int ld, float *__restrict__ out) {
-    // sigma = max_i 2*L[i][i] (unnormalised Laplacian: row sum of |offdiag| equals the diagonal)
-    __shared__ float sh[32];
-    float mx = 0.f;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) mx = fmaxf(mx, L[(size_t)i * ld + i]);
-    // block max via the sum helper on a one-hot trick is wasteful; do a plain shared reduction
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) sh[warp] = mx;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float m2 = 0.f;
-        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) m2 = fmaxf(m2, sh[w]);
-        out[0] = 2.f * m2 + 1e-3f;
-    }
+    for (int c = 0; c < 32; ++c)
+        if (c < k) {
+            const float r = warp_sum(acc[c]);
+            if (lane == 0) out[(size_t)i * k + c] = r;
+        }
 }
 
 // ---- k-means (Lloyd).  The update is a fixed-order tree reduction per (cluster, dimension), so
@@ -645,6 +816,7 @@ extern "C" int64_t spk_affinity_workspace_bytes(int64_t N, int64_t D) {
 extern "C" int spk_affinity_laplacian(const float *X, int64_t N, int64_t D, int64_t keep, float *L, void *workspace,
                                       int64_t workspace_bytes, void *stream_) {
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    NvtxRange range("spk_affinity_laplacian");
     SPK_REQUIRE(X != nullptr && L != nullptr, "null buffer");
     SPK_REQUIRE(N >= 2 && D >= 1 && N < (1 << 24), "bad shape N=%lld D=%lld", (long long)N, (long long)D);
     SPK_REQUIRE(keep >= 1 && keep <= N, "keep=%lld out of range", (long long)keep);
@@ -682,24 +854,36 @@ extern "C" int spk_affinity_laplacian(const float *X, int64_t N, int64_t D, int6
 }
 
 namespace {
-constexpr int kAxpySlices = 16;
-struct EigPlan { int m_max; int64_t off_V, off_w, off_part, off_h1, off_h2, off_alpha, off_beta, off_sm, off_sigma, total; };
+struct EigPlan {
+    int m_max, pitch, grid, rows_per_cta, pm;
+    int64_t cap, off_V, off_vbuf, off_partial, off_alpha, off_beta, off_sm, off_sigma, off_rowcnt, off_rowptr, off_cols, off_vals,
+        off_diag, off_flags, total;
+};
 EigPlan eig_plan(int64_t N, int k) {
     EigPlan p;
     // Krylov budget: clustered eigenvalues at the edge of the bulk (and exact multiplicities, which a
     // single-vector Lanczos only separates through round-off) can need several hundred steps
     p.m_max = (int)std::min<int64_t>(N, std::max(48 * k, 1024));
+    p.pitch = (p.m_max + 1 + 31) & ~31;
+    p.grid = (int)std::max<int64_t>(1, std::min<int64_t>(sm_count(), (N + 7) / 8));      // one CTA per SM: co-resident
+    p.rows_per_cta = (int)((N + p.grid - 1) / p.grid);
+    p.pm = p.m_max + 2;
+    p.cap = std::min<int64_t>(N * N, (int64_t)kCsrPerRow * N);
     int64_t cur = 0;
     auto take = [&](int64_t bytes) { int64_t o = cur; cur += align_up(bytes, 256); return o; };
-    p.off_V = take((int64_t)(p.m_max + 1) * N * 4);
-    p.off_w = take(N * 4);
-    p.off_part = take((int64_t)kAxpySlices * N * 4);
-    p.off_h1 = take((int64_t)(p.m_max + 1) * 4);
-    p.off_h2 = take((int64_t)(p.m_max + 1) * 4);
+    p.off_V = take((int64_t)p.pitch * N * 4);
+    p.off_vbuf = take(2 * N * 4);
+    p.off_partial = take(2ll * p.grid * p.pm * 4);
     p.off_alpha = take((int64_t)(p.m_max + 1) * 4);
     p.off_beta = take((int64_t)(p.m_max + 1) * 4);
     p.off_sm = take((int64_t)p.m_max * 32 * 4);
     p.off_sigma = take(256);
+    p.off_rowcnt = take(N * 4);
+    p.off_rowptr = take((N + 1) * 4);
+    p.off_cols = take(p.cap * 4);
+    p.off_vals = take(p.cap * 4);
+    p.off_diag = take(N * 4);
+    p.off_flags = take(256);
     p.total = cur;
     return p;
 }
@@ -711,15 +895,17 @@ extern "C" int64_t spk_eig_workspace_bytes(int64_t N, int32_t k) {
 }
 
 namespace {
-struct EigBufs { float *V, *w, *part, *h1, *h2, *alpha, *beta, *Sm, *dsigma; };
+struct EigBufs { float *V, *vbuf, *partial, *alpha, *beta, *Sm, *dsigma, *vals, *diag; int *rowcnt, *rowptr, *cols, *flags; };
 EigBufs eig_bufs(void *workspace, const EigPlan &p) {
     char *ws = static_cast<char *>(workspace);
     EigBufs b;
-    b.V = reinterpret_cast<float *>(ws + p.off_V); b.w = reinterpret_cast<float *>(ws + p.off_w);
-    b.part = reinterpret_cast<float *>(ws + p.off_part);
-    b.h1 = reinterpret_cast<float *>(ws + p.off_h1); b.h2 = reinterpret_cast<float *>(ws + p.off_h2);
+    b.V = reinterpret_cast<float *>(ws + p.off_V); b.vbuf = reinterpret_cast<float *>(ws + p.off_vbuf);
+    b.partial = reinterpret_cast<float *>(ws + p.off_partial);
     b.alpha = reinterpret_cast<float *>(ws + p.off_alpha); b.beta = reinterpret_cast<float *>(ws + p.off_beta);
     b.Sm = reinterpret_cast<float *>(ws + p.off_sm); b.dsigma = reinterpret_cast<float *>(ws + p.off_sigma);
+    b.vals = reinterpret_cast<float *>(ws + p.off_vals); b.diag = reinterpret_cast<float *>(ws + p.off_diag);
+    b.rowcnt = reinterpret_cast<int *>(ws + p.off_rowcnt); b.rowptr = reinterpret_cast<int *>(ws + p.off_rowptr);
+    b.cols = reinterpret_cast<int *>(ws + p.off_cols); b.flags = reinterpret_cast<int *>(ws + p.off_flags);
     return b;
 }
 }  // namespace
@@ -731,6 +917,7 @@ extern "C" int spk_lanczos_extend(const float *L, int64_t N, int32_t k, int32_t 
                                   float *beta_host, float *sigma_host, void *workspace, int64_t workspace_bytes,
                                   void *stream_) {
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    NvtxRange range("spk_lanczos_extend");
     SPK_REQUIRE(L != nullptr && alpha_host != nullptr && beta_host != nullptr && sigma_host != nullptr, "null buffer");
     SPK_REQUIRE(N >= 2 && k >= 1 && k <= 32, "bad N=%lld k=%d", (long long)N, k);
     int rc = require_device();
@@ -744,33 +931,32 @@ extern "C" int spk_lanczos_extend(const float *L, int64_t N, int32_t k, int32_t 
     const int n = (int)N, ld = (int)align_up(N, 16);
     const EigBufs b = eig_bufs(workspace, p);
     if (m_from == 0) {
-        gershgorin_kernel<<<1, 256, 0, s>>>(L, n, ld, b.dsigma);
-        init_vector_kernel<<<1, 256, 0, s>>>(b.V, n, 0x9E3779B9u);
-        count_launch(2);
+        // compact the Laplacian once: row counts -> scan -> (column, value) runs in ascending column order
+        csr_count_kernel<<<(n + 7) / 8, 256, 0, s>>>(L, n, ld, b.rowcnt);
+        csr_scan_kernel<<<1, 1024, 0, s>>>(b.rowcnt, n, b.rowptr, (long long)p.cap, b.flags);
+        csr_fill_kernel<<<(n + 7) / 8, 256, 0, s>>>(L, n, ld, b.rowptr, b.flags, b.cols, b.vals, b.diag);
+        count_launch(3);
     }
-    SPK_CUDA_OK(cudaMemcpyAsync(sigma_host, b.dsigma, sizeof(float), cudaMemcpyDeviceToHost, s));
-    SPK_CUDA_OK(cudaStreamSynchronize(s));
-    const float sigma = *sigma_host;
-    const int gx = (n + 255) / 256;
-    for (int j = m_from; j < m_to; ++j) {
-        float *vj = b.V + (size_t)j * n;
-        shifted_matvec_kernel<<<(n + 7) / 8, 256, 0, s>>>(L, n, ld, sigma, vj, b.w);
-        // full re-orthogonalisation: classical Gram-Schmidt applied twice
-        const int slices = std::min(kAxpySlices, (j + 1 + 31) / 32);
-        dots_kernel<<<j + 1, 256, 0, s>>>(b.V, n, j + 1, b.w, b.h1);
-        axpys_partial_kernel<<<dim3(gx, slices), 256, 0, s>>>(b.V, n, j + 1, b.h1, b.part);
-        axpys_finish_kernel<<<gx, 256, 0, s>>>(b.part, n, slices, b.w);
-        dots_kernel<<<j + 1, 256, 0, s>>>(b.V, n, j + 1, b.w, b.h2);
-        axpys_partial_kernel<<<dim3(gx, slices), 256, 0, s>>>(b.V, n, j + 1, b.h2, b.part);
-        axpys_finish_kernel<<<gx, 256, 0, s>>>(b.part, n, slices, b.w);
-        normalize_next_kernel<<<1, 256, 0, s>>>(b.w, n, b.V + (size_t)(j + 1) * n, b.h1, b.h2, j, b.alpha, b.beta, j);
-        count_launch(8);
-    }
+    LzArgs a{};
+    a.L = L; a.N = n; a.ld = ld; a.rowptr = b.rowptr; a.cols = b.cols; a.flags = b.flags; a.vals = b.vals; a.diag = b.diag;
+    a.Vt = b.V; a.pitch = p.pitch; a.vbuf = b.vbuf; a.partial = b.partial; a.pm = p.pm;
+    a.alpha = b.alpha; a.beta = b.beta; a.dsigma = b.dsigma; a.m_from = m_from; a.m_to = m_to; a.rows_per_cta = p.rows_per_cta;
+    size_t sh = (size_t)(p.rows_per_cta + m_to + 2 + 32) * sizeof(float);
+    SPK_REQUIRE(sh <= 64 * 1024, "lanczos: %lld rows per CTA do not fit shared memory", (long long)p.rows_per_cta);
+    const int spitch = (m_to + 1) | 1;                     // odd pitch: the column walks of the dots stay conflict-free
+    const size_t slice = (size_t)p.rows_per_cta * spitch * sizeof(float);
+    a.spitch = sh + slice <= 200 * 1024 ? spitch : 0;      // else the basis rows are read from global memory (L2)
+    if (a.spitch > 0) sh += slice;
+    if (sh > 48 * 1024) SPK_CUDA_OK(cudaFuncSetAttribute(lanczos_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    void *kargs[] = {&a};
+    SPK_CUDA_OK(cudaLaunchCooperativeKernel((const void *)lanczos_coop_kernel, dim3(p.grid), dim3(kLzThreads), kargs, sh, s));
+    count_launch(1);
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) {
         set_error("lanczos launch failed: %s", cudaGetErrorString(le));
         return SPK_ERR_CUDA;
     }
+    SPK_CUDA_OK(cudaMemcpyAsync(sigma_host, b.dsigma, sizeof(float), cudaMemcpyDeviceToHost, s));
     SPK_CUDA_OK(cudaMemcpyAsync(alpha_host, b.alpha, m_to * sizeof(float), cudaMemcpyDeviceToHost, s));
     SPK_CUDA_OK(cudaMemcpyAsync(beta_host, b.beta, m_to * sizeof(float), cudaMemcpyDeviceToHost, s));
     SPK_CUDA_OK(cudaStreamSynchronize(s));
@@ -787,7 +973,7 @@ extern "C" int spk_lanczos_ritz(int64_t N, int32_t k, int32_t m, const float *S_
     SPK_REQUIRE(workspace_bytes >= p.total && m >= 1 && m <= p.m_max, "bad workspace or m=%d", m);
     const EigBufs b = eig_bufs(workspace, p);
     SPK_CUDA_OK(cudaMemcpyAsync(b.Sm, S_host, (size_t)m * k * sizeof(float), cudaMemcpyHostToDevice, s));
-    ritz_kernel<<<((int)N + 255) / 256, 256, 0, s>>>(b.V, (int)N, m, b.Sm, k, evecs);
+    ritz_kernel<<<((int)N + 7) / 8, 256, 0, s>>>(b.V, (int)N, p.pitch, m, b.Sm, k, evecs);
     int rc = check_launch("ritz_kernel");
     if (rc != SPK_OK) return rc;
     SPK_CUDA_OK(cudaStreamSynchronize(s));      // S_host may be a temporary

@@ -108,4 +108,18 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+// ---- NVTX ranges (header-only nvtx3; a no-op unless a profiler is attached).  SPK_NVTX=1 switches them on: one range
+// per library call and per fused op, so an nsys / ncu timeline reads as "fbank | forward(stem, conv, cam_local, ...) |
+// affinity | lanczos | kmeans" instead of anonymous kernels.
+bool nvtx_enabled();
+void nvtx_push(const char *name);
+void nvtx_pop();
+struct NvtxRange {
+    bool on;
+    explicit NvtxRange(const char *name) : on(nvtx_enabled()) { if (on) nvtx_push(name); }
+    ~NvtxRange() { if (on) nvtx_pop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+
 }  // namespace spk

@@ -178,8 +178,7 @@ fbank_kernel(const FbankArgs A) {
     int *sSlot = reinterpret_cast<int *>(sMelW + ((n_w + 3) & ~3));    // filter/start/woff [16*8] x 3, trip [8*8]
     float *sEf = reinterpret_cast<float *>(sSlot + 3 * kGroups * kMaxSlots + (kGroups / 2) * kMaxSlots);   // 16
     float *sGE = sEf + kFramesPerRound;                                // n_mels: repair threshold per unit frame energy
-    float *sColFix = sGE + kMaxMels;                                   // n_mels
-    float *sColMean = sColFix + kMaxMels;                              // n_mels
+    float *sColMean = sGE + kMaxMels;                                  // n_mels
     int *sRepair = reinterpret_cast<int *>(sColMean + kMaxMels);       // count + cap entries
     double *sRed = reinterpret_cast<double *>(sRepair + 2 + kRepairMax);   // 8 (8-byte aligned by construction)
 
@@ -194,10 +193,7 @@ fbank_kernel(const FbankArgs A) {
     }
     for (int i = tid; i < (kGroups / 2) * kMaxSlots; i += kThreads) sSlot[3 * kGroups * kMaxSlots + i] = tab->slot_trip[i];
     for (int i = tid; i < kPwRows * kPwPitch; i += kThreads) sPw[i] = 0.f;
-    for (int i = tid; i < kMaxMels; i += kThreads) {
-        sColFix[i] = 0.f;
-        sGE[i] = i < n_mels ? A.repair_theta * tab->gE[i] : 0.f;
-    }
+    for (int i = tid; i < kMaxMels; i += kThreads) sGE[i] = i < n_mels ? A.repair_theta * tab->gE[i] : 0.f;
     if (tid == 0) sRepair[0] = 0;
     __syncthreads();
 
@@ -334,7 +330,6 @@ fbank_kernel(const FbankArgs A) {
                     const float v = logf(fmaxf(e, kEps));
                     sStage[mf * stage_pitch + j] = v;
                     if (valid) {
-                        colsum[s] += v;
                         if (e < sGE[j] * ef) {
                             const int slot = atomicAdd(&sRepair[0], 1);
                             if (slot < A.repair_cap) sRepair[1 + slot] = (mf << 8) | j;
@@ -395,16 +390,22 @@ fbank_kernel(const FbankArgs A) {
                 im = block_sum(im, sRed);
                 e += (double)mw[t] * (re * re + im * im);
             }
-            if (tid == 0) {
-                const float v = (float)log(fmax(e, (double)kEps));
-                float *cell = &sStage[rf * stage_pitch + j];
-                sColFix[j] += v - *cell;
-                *cell = v;
-            }
+            if (tid == 0) sStage[rf * stage_pitch + j] = (float)log(fmax(e, (double)kEps));
         }
         if (n_rep > 0 || sRepair[0] != 0) {
             __syncthreads();
             if (tid == 0) sRepair[0] = 0;
+        }
+        // column sums for the CMN, taken from the tile AFTER the repair so that both CMN paths (this CTA's registers
+        // or cmn_kernel's re-read of the stored rows) add the same values in the same order: frames f, f+16, ...
+        // per lane, then a tree over the 16 frame lanes
+        if (A.mean_nor && f0 + mf < f_end) {
+#pragma unroll
+            for (int s = 0; s < kMaxSlots; ++s) {
+                if (s >= n_slots) break;
+                const int j = sSlot[mg * kMaxSlots + s];
+                if (j >= 0) colsum[s] += sStage[mf * stage_pitch + j];
+            }
         }
         // =============================================================== store the round's tile (contiguous rows)
         {
@@ -431,7 +432,7 @@ fbank_kernel(const FbankArgs A) {
     __syncthreads();
     if (!A.fused) return;      // frame-range CTAs: cmn_kernel does the normalisation
     // ---- utterance CMN (processor.py:156-157): second pass over this CTA's own rows (L2-resident)
-    for (int j = tid; j < n_mels; j += kThreads) sColMean[j] = (sColMean[j] + sColFix[j]) / (float)A.m;
+    for (int j = tid; j < n_mels; j += kThreads) sColMean[j] = sColMean[j] / (float)A.m;
     __syncthreads();
     for (int r = tid >> 4; r < A.m; r += kThreads / 16)
         for (int col = tid & 15; col < n_mels; col += 16) orow[r * n_mels + col] -= sColMean[col];
@@ -612,7 +613,7 @@ size_t smem_bytes(int n_mels, int n_w) {
     b += (416 + 512 + kBins + kFramesPerRound * kXpFloat2) * sizeof(float2);
     b += (size_t)(kPwRows * kPwPitch + kFramesPerRound * (n_mels + 1) + ((n_w + 3) & ~3)) * sizeof(float);
     b += (size_t)(3 * kGroups * kMaxSlots + (kGroups / 2) * kMaxSlots) * sizeof(int);
-    b += (size_t)(kFramesPerRound + 3 * kMaxMels) * sizeof(float);
+    b += (size_t)(kFramesPerRound + 2 * kMaxMels) * sizeof(float);
     b += (size_t)(2 + kRepairMax) * sizeof(int);
     b = (b + 7) & ~size_t(7);
     b += 8 * sizeof(double);
@@ -623,6 +624,7 @@ template <typename SampleT>
 int launch(const void *wav, const int64_t *starts, const int32_t *lens, const int32_t *phases, int64_t B,
            int64_t n_samples, int64_t stride,
            float *out, int n_mels, int mean_nor, cudaStream_t stream) {
+    NvtxRange range("spk_fbank");
     SPK_REQUIRE(B >= 0, "negative batch");
     SPK_REQUIRE(B == 0 || (wav != nullptr && out != nullptr), "null buffer");
     // kaldi.py:142: assert 2 <= window_size <= len(waveform)

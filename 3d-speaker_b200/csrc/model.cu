@@ -228,6 +228,8 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
         return SPK_ERR_WORKSPACE;
     }
     char *ws = static_cast<char *>(workspace);
+    NvtxRange whole("spk_model_forward");
+    static const char *kOpNames[] = {"?", "stem", "conv", "cam_gate", "stats_pool", "aff_blend", "cam_local", "se_scale", "asp_pool"};
 
     bool has_phase1 = false;
     for (const spk_op_t &o : p.ops) has_phase1 |= (o.phase != 0);
@@ -250,6 +252,7 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
         for (size_t oi = 0; oi < p.ops.size(); ++oi) {
             const spk_op_t &o = p.ops[oi];
             if ((o.phase != 0) != (pass == 1)) continue;
+            NvtxRange op_range(o.kind >= 1 && o.kind <= 8 ? kOpNames[o.kind] : kOpNames[0]);
             int rc = SPK_OK;
             switch (o.kind) {
                 case SPK_OP_STEM: {
@@ -320,8 +323,7 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                         rc = launch_cam_gate(cg, dt(o.in_buf), s);
                         if (rc != SPK_OK) break;
                     }
-                    static const bool slab_v2 = [] { const char *e = getenv("SPK_SLAB_V2"); return e && e[0] == '1'; }();
-                    if (m->precision == SPK_PREC_BF16 && !slab_v2 &&
+                    if (m->precision == SPK_PREC_BF16 &&
                         conv_slab3_supported(a, dt(o.in_buf), dt(o.out_buf), dt(o.res_buf))) {
                         const __nv_bfloat16 *wb = nullptr;
                         rc = param_bf16(m, o.w, &wb, s);

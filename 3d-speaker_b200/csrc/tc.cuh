@@ -135,5 +135,22 @@ __device__ __forceinline__ float2 unpack2(uint32_t v) {
     return make_float2(__low2float(t), __high2float(t));
 }
 
+// ---- shared by the TMA-fed GEMM and the generic gather kernel
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t bnrelu2(uint32_t x, uint32_t s, uint32_t b, bool relu) {
+    __nv_bfloat162 r = __hfma2(*reinterpret_cast<__nv_bfloat162 *>(&x), *reinterpret_cast<__nv_bfloat162 *>(&s),
+                               *reinterpret_cast<__nv_bfloat162 *>(&b));
+    if (relu) r = __hmax2(r, __floats2bfloat162_rn(0.f, 0.f));
+    return *reinterpret_cast<uint32_t *>(&r);
+}
+
 }  // namespace tc
 }  // namespace spk

@@ -121,6 +121,18 @@ def headline_cases():
     ]
 
 
+def eres2net_cases():
+    """ERes2Net v1: (name, variant, ctor kwargs of the b200spk mirror, batch, n_samples, weight seed).
+    base = speakerlab.models.eres2net.ERes2Net.ERes2Net(); large = the same with m_channels=64;
+    huge = speakerlab.models.eres2net.ERes2Net_huge.ERes2Net()."""
+    return [
+        ("base_t148", "base", dict(), 2, 24000, 401),
+        ("base_t298", "base", dict(), 1, 48000, 402),
+        ("large_t148", "large", dict(m_channels=64), 1, 24000, 403),
+        ("huge_t148", "huge", dict(m_channels=64, baseWidth=24, scale=3, expansion=4), 1, 24000, 404),
+    ]
+
+
 def cluster_cases():
     """(name, N, D, K, seed, ctor kwargs)"""
     return [
@@ -311,6 +323,40 @@ def mint_common(ver):
     print("common clustering goldens:", {k: int(v.max()) + 1 for k, v in out.items() if k.endswith(".labels")})
 
 
+def mint_eres2net(ver=None):
+    import torch
+    from oracle import synth
+    from speakerlab.models.eres2net.ERes2Net import ERes2Net as Base
+    from speakerlab.models.eres2net.ERes2Net_huge import ERes2Net as Huge
+    FBank, _, _ = import_reference()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    fb = FBank(80, 16000, mean_nor=True)
+    out = {"versions": ver or versions()}
+    layouts = json.load(open(os.path.join(OUT, "state_dict_layouts.json")))
+    for name, variant, kw, batch, n_samples, wseed in eres2net_cases():
+        torch.manual_seed(0)
+        if variant == "huge":
+            model = Huge(feat_dim=80, embedding_size=192).eval()
+        else:
+            model = Base(feat_dim=80, embedding_size=192, m_channels=kw.get("m_channels", 32)).eval()
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        layouts["eres2net_" + variant] = {k: list(v) for k, v in shapes.items()}
+        sd = synth.fill_state_dict(shapes, wseed, randomize_bn=True, gain=ERES_GAIN)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        wavs = campplus_input(batch, n_samples, seed=wseed + 1000)
+        feats = torch.vmap(fb)(torch.from_numpy(wavs).unsqueeze(1))
+        with torch.no_grad():
+            e = model(feats.clone())
+            e64 = model.double()(feats.double().clone())
+        out[name + ".feats"] = feats.numpy()
+        out[name + ".emb"] = e.numpy()
+        print(name, "params %.2f M" % (sum(int(np.prod(v)) for k, v in shapes.items() if "num_batches" not in k and "running" not in k) / 1e6),
+              "fp32 vs fp64 rel-L2 %.2e" % (np.linalg.norm(e.numpy() - e64.numpy()) / np.linalg.norm(e64.numpy())))
+    np.savez_compressed(os.path.join(OUT, "eres2net.npz"), **out)
+    with open(os.path.join(OUT, "state_dict_layouts.json"), "w") as f:
+        json.dump(layouts, f)
+
+
 def mint_headline(ver=None):
     import torch
     from oracle import synth
@@ -345,5 +391,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "headline":
         import_reference()
         mint_headline()
+    elif len(sys.argv) > 1 and sys.argv[1] == "eres2net":
+        import_reference()
+        mint_eres2net()
     else:
         main()

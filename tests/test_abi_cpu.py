@@ -89,6 +89,16 @@ def test_ecapa_state_dict_layout_is_the_reference_layout(golden_dir):
         assert all(list(sd[k].shape) == ref[k] for k in ref)
 
 
+def test_eres2net_v1_state_dict_layout_is_the_reference_layout(golden_dir):
+    import json
+    lay = json.load(open(os.path.join(golden_dir, "state_dict_layouts.json")))
+    for variant, model in (("base", b200spk.ERes2Net()), ("large", b200spk.ERes2Net(m_channels=64)), ("huge", b200spk.ERes2Net_huge())):
+        sd = model.state_dict()
+        ref = lay["eres2net_" + variant]
+        assert list(sd.keys()) == list(ref.keys())
+        assert all(list(sd[k].shape) == ref[k] for k in ref)
+
+
 def test_fbank_mirror_interface():
     fb = b200spk.FBank(80, 16000, mean_nor=True)
     assert (fb.n_mels, fb.sample_rate, fb.mean_nor) == (80, 16000, True)

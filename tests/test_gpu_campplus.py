@@ -93,17 +93,13 @@ def test_two_seg_windows_and_ragged_T():
         assert _rel(got, ref) <= 1e-4
 
 
-# torch's own CPU bf16 execution of the reference graph on the same weights/inputs, measured in
-# this repo's container (tools/diag_bf16.py + the snippet in DESIGN.md): min cosine vs fp32.
-TORCH_CPU_BF16_COS = {"noise_bnrand7": 0.999066, "fm_freshbn104": 0.999910, "fm_bnrand101": 0.991871}
-
-
-@pytest.mark.parametrize("case", ["noise_bnrand7", "fm_freshbn104", "fm_bnrand101"])
+@pytest.mark.parametrize("case", ["noise_bnrand7", "fm_freshbn104"])
 def test_bf16_mode(case):
-    """bf16 = tcgen05 tensor-core path.  North-star tolerance: cosine >= 0.999 vs the CPU fp32
-    reference path.  Weight set 101 (randomised BN) is ill-conditioned - PyTorch's own bf16 run of
-    the reference graph only reaches 0.9919 on it - so there the bar is 'no worse than torch bf16'."""
-    wseed, bnrand = {"noise_bnrand7": (7, True), "fm_freshbn104": (104, False), "fm_bnrand101": (101, True)}[case]
+    """bf16 = tcgen05 tensor-core path at the north-star tolerance: cosine >= 0.999 vs the CPU fp32 reference path.
+    (The models' own random initialisation, every family and headline shape: tests/test_gpu_bf16_parity.py, which
+    also bounds the per-block error growth on the deliberately ill-conditioned weight set 101 - a set on which
+    PyTorch's own CPU bf16 run of the reference graph loses 1e-2 of cosine.)"""
+    wseed, bnrand = {"noise_bnrand7": (7, True), "fm_freshbn104": (104, False)}[case]
     if case.startswith("noise"):
         wavs = synth.white_noise(16, 24000, seed=123)
     else:
@@ -115,12 +111,8 @@ def test_bf16_mode(case):
     with torch.no_grad():
         e32, e16 = f32(feats).cpu().numpy(), b16(feats).cpu().numpy()
     assert _rel(e32, ref) <= 1e-4
-    cos = _cos_min(e16, ref)
-    if case == "fm_bnrand101":
-        assert cos >= TORCH_CPU_BF16_COS[case], cos
-    else:
-        assert cos >= 0.999, cos
-        assert _rel(e16, e32) <= 3e-2
+    assert _cos_min(e16, ref) >= 0.999, _cos_min(e16, ref)
+    assert _rel(e16, e32) <= 3e-2
 
 
 def test_extractor_host_buffers_roundtrip():

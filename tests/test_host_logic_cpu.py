@@ -90,3 +90,81 @@ def test_mirrors_build_through_the_reference_builder(tmp_path):
         cfg = build_config.__globals__["Config"]({"embedding_model": {"obj": obj, "args": dict(args)}})
         m = build("embedding_model", cfg)
         assert isinstance(m, torch.nn.Module) and not m.training
+
+
+# --------------------------------------------------------------------------- turns / RTTM, ark/scp, trial metrics
+def test_compress_segments_matches_the_sequential_reference_rule():
+    from oracle import metrics_oracle, synth
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        regions, t = [], 0.0
+        for _ in range(rng.integers(1, 6)):                      # VAD regions separated by silences
+            t += float(rng.uniform(0.2, 3.0))
+            dur = float(rng.uniform(0.4, 30.0))
+            regions.append([round(t, 3), round(t + dur, 3)])
+            t += dur
+        chunks = [c for st, ed in regions for c in synth.chunk(st, ed)]
+        labels = np.repeat(rng.integers(0, 3, len(chunks) // 3 + 1), 3)[:len(chunks)]       # turns of >= 1 segment
+        ref = metrics_oracle.compressed_seg([[st, ed, int(c)] for (st, ed), c in zip(chunks, labels)])
+        got = b200spk.compress_segments(chunks, labels)
+        assert len(got) == len(ref)
+        assert np.allclose(np.array(got, dtype=np.float64), np.array(ref, dtype=np.float64), atol=1e-12)
+    assert b200spk.compress_segments([], []) == []
+
+
+def test_rttm_format(tmp_path):
+    turns = b200spk.write_rttm(str(tmp_path / "a.rttm"), [[0.0, 1.5], [0.75, 2.25], [1.5, 3.0]], [0, 0, 1], "rec1")
+    assert turns == [[0.0, 1.875, 0], [1.875, 3.0, 1]]
+    assert open(tmp_path / "a.rttm").read() == ("SPEAKER rec1 0 0.000 1.875 <NA> <NA> 1 <NA> <NA>\n"
+                                                "SPEAKER rec1 0 1.875 1.125 <NA> <NA> 2 <NA> <NA>\n")
+
+
+def test_ark_scp_round_trip(tmp_path):
+    rng = np.random.default_rng(1)
+    emb = rng.standard_normal((5, 192)).astype(np.float32)
+    keys = ["utt%02d" % i for i in range(5)]
+    ark, scp = str(tmp_path / "xvector_00.ark"), str(tmp_path / "xvector_00.scp")
+    with b200spk.ArkWriter(ark, scp) as w:
+        w.write_batch(keys[:4], emb[:4])
+        w(keys[4], emb[4])                                   # a plain vector entry
+    back = dict(b200spk.read_ark(ark))
+    assert list(back) == keys
+    assert all(back[k].shape == (1, 192) and np.array_equal(back[k][0], emb[i]) for i, k in enumerate(keys[:4]))
+    assert back[keys[4]].shape == (192,) and np.array_equal(back[keys[4]], emb[4])
+    by_scp = b200spk.read_scp(scp)
+    assert all(np.array_equal(by_scp[k], back[k]) for k in keys)
+    # byte layout of the first entry: key, space, \0B, 'FM ', \4 rows \4 cols
+    raw = open(ark, "rb").read(6 + 2 + 3 + 10)
+    assert raw == b"utt00 \0BFM \4\x01\x00\x00\x00\4\xc0\x00\x00\x00"
+
+
+def test_det_metrics_oracle_on_a_separable_toy():
+    from oracle import metrics_oracle
+    scores = np.array([0.1, 0.2, 0.3, 0.4, 0.6, 0.7, 0.8, 0.9])
+    labels = np.array([0, 0, 0, 1, 0, 1, 1, 1])
+    fnr, fpr = metrics_oracle.pmiss_pfa(scores, labels)
+    e, thr = metrics_oracle.eer(fnr, fpr, scores)
+    assert abs(e - 0.25) < 1e-12 and thr in (0.4, 0.6)
+    assert abs(metrics_oracle.c_norm(fnr, fpr, 0.5) - 0.25) < 1e-12
+
+
+def test_bulk_chunk_table_is_circle_pad_then_slice():
+    """IterWavList.load_wav / chunk_wav (infer_sv_batch.py:388-412): truncate to 90 s, circle-pad the recording to a
+    whole number of 10 s chunks, slice.  The table must address exactly those samples."""
+    fs, cs, cap = 16000, 160000, 90 * 16000
+    lengths = [cs * 3 + 5, 100, fs * 95, cs]
+    rng = np.random.default_rng(2)
+    wavs = [rng.standard_normal(n).astype(np.float32) for n in lengths]
+    buf = np.concatenate(wavs)
+    starts, periods, phases, pos = b200spk.chunk_table(lengths)
+    assert pos.tolist() == [0, 4, 5, 14, 15]
+    row = 0
+    for w in wavs:
+        w = w[:cap]
+        n = int(np.ceil(len(w) / cs))
+        padded = np.tile(w, int(np.ceil(n * cs / len(w))))[:n * cs]
+        for q in range(n):
+            idx = starts[row] + (phases[row] + np.arange(cs)) % periods[row]
+            assert np.array_equal(buf[idx], padded[q * cs:(q + 1) * cs])
+            row += 1
+    assert row == len(starts)

@@ -174,3 +174,14 @@ def test_common_clustering_oracle_matches_reference(golden_dir, case):
     if kw["cluster_type"] == "AHC":
         raw = cluster_oracle.ahc(X, kw.get("fix_cos_thr", 0.4))
         assert np.array_equal(cluster_oracle.match_labels(gold[name + ".raw_ahc"], raw), gold[name + ".raw_ahc"])
+
+
+@pytest.mark.parametrize("case", gen_golden.eres2net_cases(), ids=lambda c: c[0])
+def test_eres2net_v1_oracle_matches_reference(golden_dir, layouts, case):
+    from oracle import eres2net_oracle
+    gold = np.load(os.path.join(golden_dir, "eres2net.npz"))
+    name, variant, kw, batch, n_samples, wseed = case
+    sd = synth.fill_state_dict(layouts["eres2net_" + variant], wseed, randomize_bn=True, gain=gen_golden.ERES_GAIN)
+    got = eres2net_oracle.forward(sd, gold[name + ".feats"], scale=kw.get("scale", 2)).numpy()
+    ref = gold[name + ".emb"]
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-5

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import b200spk
-from b200spk import _lib, campplus, ecapa_tdnn, eres2netv2
+from b200spk import _lib, campplus, ecapa_tdnn, eres2net, eres2netv2
 from b200spk.program import conv_out
 
 
@@ -104,6 +104,23 @@ def test_eres2netv2_program(prec, kw, T):
     eng = eres2netv2._Engine(mod, MockModel(prec))
     eng.compile(T)
     _check_program(eng.model, eng.model.programs[T], T)
+
+
+@pytest.mark.parametrize("prec", [_lib.PREC_F32, _lib.PREC_BF16])
+@pytest.mark.parametrize("variant", ["base", "large", "huge"])
+@pytest.mark.parametrize("T", [148, 298])
+def test_eres2net_v1_program(prec, variant, T):
+    mod = {"base": b200spk.ERes2Net, "large": lambda: b200spk.ERes2Net(m_channels=64), "huge": b200spk.ERes2Net_huge}[variant]()
+    eng = eres2net._Engine(mod, MockModel(prec))
+    eng.compile(T)
+    prog = eng.model.programs[T]
+    _check_program(eng.model, prog, T)
+    # three stride-2 3x3 downsamples without BN / activation and three top-level fusions (ERes2Net.py:179-186)
+    ds = [o for o in prog.ops if o.kind == _lib.OP_CONV and o.KH == 3 and o.sh == 2 and o.epi_scale < 0]
+    assert len(ds) == 3
+    S = mod.scale
+    n_blend = sum(1 for o in prog.ops if o.kind == _lib.OP_AFF_BLEND)
+    assert n_blend == sum(mod.num_blocks) * (S - 1) + 3
 
 
 @pytest.mark.parametrize("prec", [_lib.PREC_F32, _lib.PREC_BF16])

@@ -561,6 +561,7 @@ int launch_conv_simt(const ConvArgs &a, int in_dtype, int out_dtype, int res_dty
         return SPK_ERR_UNSUPPORTED;
     }
     if (a.M == 0) return SPK_OK;
+    if (linear_supported(a, in_dtype, out_dtype)) return launch_linear(a, in_dtype, out_dtype, s);   // few rows, long K
     const int key = in_dtype * 100 + out_dtype * 10 + (a.res ? res_dtype : out_dtype);
     switch (key) {
         case 0:   return conv_simt_dispatch<float, float, float>(a, s);
@@ -620,6 +621,7 @@ int launch_stem(const StemArgs &a, int out_dtype, cudaStream_t s) {
 
 int launch_cam_gate(const CamGateArgs &a, int in_dtype, cudaStream_t s) {
     if (a.B == 0) return SPK_OK;
+    if (se_gate_cluster_supported(a, in_dtype)) return launch_se_gate_cluster(a, in_dtype, s);
     const int threads = 256;
     if (a.C % 4 != 0 || a.C / 4 > threads || a.in_ld % 4 != 0 || a.in_choff % 4 != 0) {
         set_error("cam_gate: C=%d must be a multiple of 4 and <= %d", a.C, threads * 4);
@@ -642,6 +644,7 @@ int launch_stats_pool(const StatsPoolArgs &a, int in_dtype, cudaStream_t s) {
         set_error("stats_pool: grid too large (G=%d, B=%d)", a.G, a.B);
         return SPK_ERR_UNSUPPORTED;
     }
+    if (stats_pool_sliced_supported(a)) return launch_stats_pool_sliced(a, in_dtype, s);     // long axes (10 s chunks)
     if (a.C % 2 == 0 && a.in_ld % 2 == 0 && a.in_choff % 2 == 0 && (long long)a.B * a.G < 0x7fffffffll &&
         (reinterpret_cast<uintptr_t>(a.x) & 7) == 0) {
         const unsigned blocks = (unsigned)((long long)a.B * a.G);

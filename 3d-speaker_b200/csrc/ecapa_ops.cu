@@ -107,6 +107,7 @@ int launch_asp_pool(const AspPoolArgs &a, int l_dtype, int x_dtype, cudaStream_t
         set_error("asp_pool: batch too large for one launch (%lld)", a.B);
         return SPK_ERR_UNSUPPORTED;
     }
+    if (asp_pool_online_supported(a)) return launch_asp_pool_online(a, l_dtype, x_dtype, s);
     dim3 grid((a.C + 127) / 128, (unsigned)a.B);
     if (l_dtype == SPK_DT_F32 && x_dtype == SPK_DT_F32) asp_pool_kernel<float, float><<<grid, 128, 0, s>>>(a);
     else if (l_dtype == SPK_DT_BF16 && x_dtype == SPK_DT_BF16) asp_pool_kernel<bf16, bf16><<<grid, 128, 0, s>>>(a);

@@ -102,6 +102,16 @@ struct AspPoolArgs {
 };
 int launch_asp_pool(const AspPoolArgs &a, int l_dtype, int x_dtype, cudaStream_t s);
 
+// small_ops.cu: cluster split-K linear layer, split-T squeeze-excitation gate, sliced / one-pass pooling for long axes
+bool linear_supported(const ConvArgs &a, int in_dtype, int out_dtype);
+int launch_linear(const ConvArgs &a, int in_dtype, int out_dtype, cudaStream_t s);
+bool se_gate_cluster_supported(const CamGateArgs &a, int in_dtype);
+int launch_se_gate_cluster(const CamGateArgs &a, int in_dtype, cudaStream_t s);
+bool stats_pool_sliced_supported(const StatsPoolArgs &a);
+int launch_stats_pool_sliced(const StatsPoolArgs &a, int in_dtype, cudaStream_t s);
+bool asp_pool_online_supported(const AspPoolArgs &a);
+int launch_asp_pool_online(const AspPoolArgs &a, int l_dtype, int x_dtype, cudaStream_t s);
+
 int launch_f32_to_bf16(const float *src, __nv_bfloat16 *dst, long long n, cudaStream_t s);
 int launch_widen(const void *src, int dtype, float *dst, long long n, cudaStream_t s);
 

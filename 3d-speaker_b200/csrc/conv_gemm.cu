@@ -41,7 +41,7 @@ using bf16 = __nv_bfloat16;
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 448;      // 0 TMA, 1 MMA, 2-5 transform A, 6-9 epilogue, 10-13 transform B
+constexpr int kThreads = 480;      // 0 TMA, 1 MMA, 2-5 transform A, 6-9 epilogue, 10-13 transform B, 14 TMA store / residual load
 constexpr int kXformThreads = 128;
 constexpr int kEpilogueThreads = 128;
 
@@ -80,9 +80,13 @@ template <int BLOCK_N, bool TEPI = false> struct Cfg {
     static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
     static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    // TEPI (TMA epilogue): one output tile [128 x BLOCK_N] bf16 is staged in shared memory, so the ring is shorter
-    static constexpr int kStgBytes = TEPI ? BLOCK_M * BLOCK_N * 2 : 0;
-    static constexpr int kStages = TEPI ? ((BLOCK_N >= 256) ? 3 : 4) : ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8));
+    // TEPI (TMA epilogue): output tiles leave in UNITS of 128 rows x <= 128 columns through two staging buffers, so
+    // the ring is shorter.  A unit is one or two 128B-swizzled blocks of 128 rows x 64 columns.
+    static constexpr int kUnitBlocks = BLOCK_N >= 128 ? 2 : 1;
+    static constexpr int kUnitBytes = TEPI ? kUnitBlocks * BLOCK_M * 128 : 0;
+    static constexpr int kUnitsPerTile = (BLOCK_N + 127) / 128;
+    static constexpr int kStgBytes = 2 * kUnitBytes;
+    static constexpr int kStages = TEPI ? ((BLOCK_N >= 256) ? 3 : (BLOCK_N >= 128 ? 4 : 6)) : ((BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8));
     static constexpr bool kATmem = BLOCK_N <= 128;          // room for the A ring next to the two accumulators
     static constexpr int kAColsPerStage = BLOCK_K / 2;       // two bf16 per 32-bit TMEM column
     static constexpr int kTmemNeed = 2 * BLOCK_N + (kATmem ? kStages * kAColsPerStage : 0);
@@ -113,9 +117,10 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
     auto empty_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + s); };
     auto accf_bar = [&](int b) { return bar0 + 8u * (3 * C::kStages + b); };
     auto acce_bar = [&](int b) { return bar0 + 8u * (3 * C::kStages + 2 + b); };
-    auto rfull_bar = [&]() { return bar0 + 8u * (3 * C::kStages + 4); };     // TEPI: residual tile landed in the staging buffer
-    auto sfree_bar = [&]() { return bar0 + 8u * (3 * C::kStages + 5); };     // TEPI: the TMA store has read the staging buffer
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + 3 * C::kStages + 8);
+    auto rfull_bar = [&](uint32_t b) { return bar0 + 8u * (3 * C::kStages + 4 + b); };     // TEPI: residual unit landed in staging buffer b
+    auto sfree_bar = [&](uint32_t b) { return bar0 + 8u * (3 * C::kStages + 6 + b); };     // TEPI: the TMA store has read staging buffer b
+    auto gfull_bar = [&](uint32_t b) { return bar0 + 8u * (3 * C::kStages + 8 + b); };     // TEPI: staging buffer b holds a finished unit
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + 3 * C::kStages + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool has_pro = pro_scale_bf != nullptr;
@@ -131,8 +136,11 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
             mbar_init(accf_bar(b), 1);
             mbar_init(acce_bar(b), kEpilogueThreads);
         }
-        mbar_init(rfull_bar(), 1);
-        mbar_init(sfree_bar(), 1);
+        for (uint32_t b = 0; b < 2; ++b) {
+            mbar_init(rfull_bar(b), 1);
+            mbar_init(sfree_bar(b), 1);
+            mbar_init(gfull_bar(b), kEpilogueThreads);
+        }
         if (TEPI) {
             prefetch_tmap(&ymap);
             prefetch_tmap(&rmap);
@@ -168,7 +176,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
         // =========================== TMA producer ===========================
         if (lane == 0) {
             int stage = 0, sidx = 0;
-            uint32_t phase = 0, pit = 0;
+            uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const long long mt = tile / n_tiles_n;
                 const int nt = (int)(tile - mt * n_tiles_n);
@@ -181,15 +189,6 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                     tma_load_2d(sa + C::kABytes, &wmap, kc * BLOCK_K, nt * BLOCK_N, land_bar(stage));
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
-                if (TEPI && a.res != nullptr) {
-                    // residual tile -> staging buffer, once the store of the previous tile has read it
-                    mbar_wait(sfree_bar(), (pit & 1u) ^ 1u);
-                    const int nblk = min(BLOCK_N / 64, (a.Cout - nt * BLOCK_N + 63) / 64);
-                    mbar_arrive_expect_tx(rfull_bar(), (uint32_t)nblk * (BLOCK_M * 128u));
-                    for (int j = 0; j < nblk; ++j)
-                        tma_load_2d(s_stg + (uint32_t)j * (BLOCK_M * 128u), &rmap, nt * BLOCK_N + 64 * j, (int)(mt * BLOCK_M), rfull_bar());
-                }
-                ++pit;
             }
         }
     } else if (warp == 1) {
@@ -232,7 +231,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                 if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp < 6 || warp >= 10) {
+    } else if (warp < 6 || (warp >= 10 && warp < 14)) {
         // =========================== transform (BN-ReLU prologue) ===========================
         // TMEM path: two groups of four warps (2-5 and 10-13) take alternate stages, so the latency of one stage's
         // load -> math -> tcgen05.st chain overlaps the next stage's
@@ -304,6 +303,53 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                 }
             }
         }
+    } else if (warp == 14) {
+        // =========================== TMA store / residual load (TMA epilogue only) ===========================
+        if (TEPI && elect_one()) {
+            struct Unit { long long tile; int h; };
+            auto units_of = [&](long long tile) { return min(C::kUnitsPerTile, (a.Cout - (int)(tile % n_tiles_n) * BLOCK_N + 127) / 128); };
+            auto next = [&](Unit &u) {
+                if (u.h + 1 < units_of(u.tile)) ++u.h;
+                else { u.h = 0; u.tile += gridDim.x; }
+            };
+            auto coords = [&](const Unit &u, int &row0, int &col0, int &nblk) {
+                const long long mt = u.tile / n_tiles_n;
+                const int nt = (int)(u.tile - mt * n_tiles_n);
+                row0 = (int)(mt * BLOCK_M);
+                col0 = nt * BLOCK_N + u.h * 128;
+                nblk = min(C::kUnitBlocks, (a.Cout - col0 + 63) / 64);
+            };
+            const bool has_res = a.res != nullptr;
+            auto load_res = [&](const Unit &u, uint32_t sb) {
+                int row0, col0, nblk;
+                coords(u, row0, col0, nblk);
+                mbar_arrive_expect_tx(rfull_bar(sb), (uint32_t)nblk * (BLOCK_M * 128u));
+                for (int j = 0; j < nblk; ++j)
+                    tma_load_2d(s_stg + sb * C::kUnitBytes + (uint32_t)j * (BLOCK_M * 128u), &rmap, col0 + 64 * j, row0, rfull_bar(sb));
+            };
+            Unit cur{(long long)blockIdx.x, 0}, pre = cur;
+            if (has_res)
+                for (uint32_t i = 0; i < 2 && pre.tile < n_tiles; ++i) {       // the residual runs two units ahead
+                    load_res(pre, i);
+                    next(pre);
+                }
+            for (uint32_t unit = 0; cur.tile < n_tiles; ++unit, next(cur)) {
+                const uint32_t sb = unit & 1u, sph = (unit >> 1) & 1u;
+                int row0, col0, nblk;
+                coords(cur, row0, col0, nblk);
+                mbar_wait(gfull_bar(sb), sph);
+                for (int j = 0; j < nblk; ++j)
+                    tma_store_2d(&ymap, col0 + 64 * j, row0, s_stg + sb * C::kUnitBytes + (uint32_t)j * (BLOCK_M * 128u));
+                bulk_commit();
+                bulk_wait_read0();          // the unit has been read out of shared memory
+                if (!has_res) mbar_arrive(sfree_bar(sb));
+                else if (pre.tile < n_tiles) {
+                    load_res(pre, sb);
+                    next(pre);
+                }
+            }
+            bulk_wait_all();                // the last stores have reached global memory
+        }
     } else {
         // =========================== epilogue ===========================
         const int q = warp & 3;                       // warps 6..9 -> lane quarters 2,3,0,1
@@ -312,7 +358,8 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
         TOut *y = static_cast<TOut *>(a.y);
         const TRes *res = static_cast<const TRes *>(a.res);
         const bool wide_st = sizeof(TOut) == 2 && (reinterpret_cast<uintptr_t>(a.y) & 31) == 0 && a.out_ld % 16 == 0 && a.out_choff % 16 == 0;
-        uint32_t it = 0;
+        uint32_t it = 0, unit = 0;
+        (void)unit;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const long long mt = tile / n_tiles_n;
             const int nt = (int)(tile - mt * n_tiles_n);
@@ -326,19 +373,26 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                 grow = a.gate + ((long long)b * a.gate_nwin + wo / a.gate_win) * a.Cout;
             }
             if constexpr (TEPI) {
-                // ---- TMA epilogue: the tile goes through a 128B-swizzled staging buffer ([BLOCK_N/64] blocks of
-                // 128 rows x 64 columns).  A residual tile was TMA-loaded into it by the producer and is updated in
-                // place; one thread then stores the blocks with TMA (rows past M / columns past Cout are clipped).
-                // Row-strided per-lane global accesses - 32 different lines per warp instruction - are what made the
-                // residual GEMMs of ERes2NetV2 run below 1 TB/s.
-                if (res != nullptr) mbar_wait(rfull_bar(), it & 1u);
-                else mbar_wait(sfree_bar(), (it & 1u) ^ 1u);
+                // ---- TMA epilogue: the tile leaves in units of <= 128 columns through two 128B-swizzled staging buffers
+                // (one or two blocks of 128 rows x 64 columns each).  The store warp TMA-loads a residual unit into the
+                // buffer beforehand (updated in place here) and TMA-stores the finished unit (rows past M / columns past
+                // Cout are clipped), so this warp group never waits on a store: the per-tile chain is the epilogue math
+                // alone.  (With one buffer and the store issued from here, every tile cost ~3.5 us however small:
+                // math -> store -> wait for the read -> residual load -> next tile.)  Row-strided per-lane global accesses
+                // - 32 different lines per warp instruction - are what made the residual GEMMs run below 1 TB/s before.
                 mbar_wait(accf_bar(buf), acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
-                const uint32_t srow = s_stg + (uint32_t)row * 128u, x7 = (uint32_t)(row & 7);
+                const uint32_t x7 = (uint32_t)(row & 7);
+                const int units = min(C::kUnitsPerTile, (a.Cout - n0 + 127) / 128);
+                for (int h = 0; h < units; ++h, ++unit) {
+                const uint32_t sb = unit & 1u, sph = (unit >> 1) & 1u;
+                if (res != nullptr) mbar_wait(rfull_bar(sb), sph);
+                else mbar_wait(sfree_bar(sb), sph ^ 1u);
+                const uint32_t srow = s_stg + sb * C::kUnitBytes + (uint32_t)row * 128u;
+                const int c_end = min(BLOCK_N, h * 128 + 128);
 #pragma unroll 1
-                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                for (int c0 = h * 128; c0 < c_end; c0 += 32) {
                     const int n = n0 + c0;
                     if (n >= a.Cout) break;
                     const bool second = n + 16 < a.Cout;
@@ -370,7 +424,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                         }
                     }
                     // this step's four 16-byte chunks of the row inside block c0 / 64
-                    const uint32_t blk = srow + (uint32_t)(c0 >> 6) * (BLOCK_M * 128u);
+                    const uint32_t blk = srow + (uint32_t)((c0 & 127) >> 6) * (BLOCK_M * 128u);
                     const uint32_t ch0 = (uint32_t)((c0 & 63) >> 3);
                     if (res != nullptr) {
 #pragma unroll
@@ -404,19 +458,13 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                               make_uint4(pack2(v[8 * e], v[8 * e + 1]), pack2(v[8 * e + 2], v[8 * e + 3]), pack2(v[8 * e + 4], v[8 * e + 5]),
                                          pack2(v[8 * e + 6], v[8 * e + 7])));
                 }
-                tc_fence_before();
-                mbar_arrive(acce_bar(buf));
-                fence_proxy_async();
-                epi_bar_sync();
-                if (warp == 6 && elect_one()) {
-                    const int nblk = min(BLOCK_N / 64, (a.Cout - n0 + 63) / 64);
-                    for (int j = 0; j < nblk; ++j)
-                        tma_store_2d(&ymap, n0 + 64 * j, (int)(mt * BLOCK_M), s_stg + (uint32_t)j * (BLOCK_M * 128u));
-                    bulk_commit();
-                    bulk_wait_read0();
-                    mbar_arrive(sfree_bar());
+                if (h == units - 1) {           // all TMEM reads of the tile are done: the accumulator may be overwritten
+                    tc_fence_before();
+                    mbar_arrive(acce_bar(buf));
                 }
-                __syncwarp();
+                fence_proxy_async();            // staging writes (generic proxy) -> TMA store (async proxy)
+                mbar_arrive(gfull_bar(sb));
+                }
                 continue;
             }
             mbar_wait(accf_bar(buf), acc_phase);
@@ -542,7 +590,6 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
             mbar_arrive(acce_bar(buf));
             if (warp == 6) GEMM_TS(it, 7);
         }
-        if (TEPI) bulk_wait_all();          // the stores of the last tile have left shared memory and reached global
     }
 
     tc_fence_before();
@@ -661,21 +708,24 @@ int launch_one(const ConvArgs &a, cudaStream_t s) {
 
 template <typename TOut, typename TRes>
 int launch_n(const ConvArgs &a, cudaStream_t s) {
-    if (a.Cout <= 32) return launch_one<32, TOut, TRes>(a, s);
-    if (a.Cout <= 64) return launch_one<64, TOut, TRes>(a, s);
     if constexpr (sizeof(TOut) == 2 && sizeof(TRes) == 2) {
         // bf16 tiles leave (and residual tiles arrive) through shared memory with TMA: faster than the register
         // epilogue for every GEMM of the three networks even with the shorter stage ring (CAM++ +4.6 %, ECAPA-TDNN
-        // +12 %, ERes2NetV2 +23 %).  SPK_GEMM_TEPI=0 selects the register epilogue for A/B runs.
+        // +12 %, ERes2NetV2 +23 % in its first, single-buffer form).  SPK_GEMM_TEPI=0 selects the register epilogue
+        // for A/B runs.
         static const int force = [] { const char *e = getenv("SPK_GEMM_TEPI"); return e ? atoi(e) : -1; }();
         const bool ok = a.gate == nullptr && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 &&
                         (a.res == nullptr || (reinterpret_cast<uintptr_t>(a.res) & 15) == 0);
         const bool want = force != 0;
         if (ok && want) {
+            if (a.Cout <= 32) return launch_one<32, TOut, TRes, true>(a, s);
+            if (a.Cout <= 64) return launch_one<64, TOut, TRes, true>(a, s);
             if (a.Cout <= 128) return launch_one<128, TOut, TRes, true>(a, s);
             return launch_one<256, TOut, TRes, true>(a, s);
         }
     }
+    if (a.Cout <= 32) return launch_one<32, TOut, TRes>(a, s);
+    if (a.Cout <= 64) return launch_one<64, TOut, TRes>(a, s);
     if (a.Cout <= 128) return launch_one<128, TOut, TRes>(a, s);
     return launch_one<256, TOut, TRes>(a, s);
 }

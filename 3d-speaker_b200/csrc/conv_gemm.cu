@@ -124,6 +124,12 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool has_pro = pro_scale_bf != nullptr;
+    // Without the tensor-memory prologue warps 10-13 have nothing to transform: they form a second epilogue group.
+    // One unit per tile (N <= 128): the groups take alternate tiles (= alternate accumulators and staging buffers);
+    // two units per tile (N = 256): group g takes the tile's column half g.  The epilogue - one TMEM round trip per 32
+    // columns and row - was the per-tile critical path of every GEMM with a short K loop.
+    const bool two_groups = !(has_pro && C::kATmem);
+    constexpr bool kSplitCols = C::kUnitsPerTile == 2;
 
     pdl_trigger();
     if (threadIdx.x == 0) {
@@ -134,7 +140,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(accf_bar(b), 1);
-            mbar_init(acce_bar(b), kEpilogueThreads);
+            mbar_init(acce_bar(b), kEpilogueThreads * ((kSplitCols && two_groups) ? 2 : 1));
         }
         for (uint32_t b = 0; b < 2; ++b) {
             mbar_init(rfull_bar(b), 1);
@@ -231,7 +237,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                 if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp < 6 || (warp >= 10 && warp < 14)) {
+    } else if (warp < 6 || (warp >= 10 && warp < 14 && !two_groups)) {
         // =========================== transform (BN-ReLU prologue) ===========================
         // TMEM path: two groups of four warps (2-5 and 10-13) take alternate stages, so the latency of one stage's
         // load -> math -> tcgen05.st chain overlaps the next stage's
@@ -306,11 +312,18 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
     } else if (warp == 14) {
         // =========================== TMA store / residual load (TMA epilogue only) ===========================
         if (TEPI && elect_one()) {
-            struct Unit { long long tile; int h; };
+            // units in issue order: tile by tile, column half by column half; staging buffer = column half (two units
+            // per tile) or tile parity (one unit per tile); barrier phase = that buffer's use count
+            struct Unit { long long tile; uint32_t it; int h; };
             auto units_of = [&](long long tile) { return min(C::kUnitsPerTile, (a.Cout - (int)(tile % n_tiles_n) * BLOCK_N + 127) / 128); };
             auto next = [&](Unit &u) {
                 if (u.h + 1 < units_of(u.tile)) ++u.h;
-                else { u.h = 0; u.tile += gridDim.x; }
+                else { u.h = 0; u.tile += gridDim.x; ++u.it; }
+            };
+            auto sb_of = [&](const Unit &u) { return kSplitCols ? (uint32_t)u.h : (u.it & 1u); };
+            auto next_same = [&](Unit &u) {
+                const uint32_t sb = sb_of(u);
+                do next(u); while (u.tile < n_tiles && sb_of(u) != sb);
             };
             auto coords = [&](const Unit &u, int &row0, int &col0, int &nblk) {
                 const long long mt = u.tile / n_tiles_n;
@@ -327,14 +340,16 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                 for (int j = 0; j < nblk; ++j)
                     tma_load_2d(s_stg + sb * C::kUnitBytes + (uint32_t)j * (BLOCK_M * 128u), &rmap, col0 + 64 * j, row0, rfull_bar(sb));
             };
-            Unit cur{(long long)blockIdx.x, 0}, pre = cur;
+            Unit cur{(long long)blockIdx.x, 0u, 0}, pre[2];
             if (has_res)
-                for (uint32_t i = 0; i < 2 && pre.tile < n_tiles; ++i) {       // the residual runs two units ahead
-                    load_res(pre, i);
-                    next(pre);
+                for (uint32_t sb = 0; sb < 2; ++sb) {       // the residual of a buffer's next use is loaded as soon as the buffer is free
+                    pre[sb] = cur;
+                    while (pre[sb].tile < n_tiles && sb_of(pre[sb]) != sb) next(pre[sb]);
+                    if (pre[sb].tile < n_tiles) load_res(pre[sb], sb);
                 }
-            for (uint32_t unit = 0; cur.tile < n_tiles; ++unit, next(cur)) {
-                const uint32_t sb = unit & 1u, sph = (unit >> 1) & 1u;
+            uint32_t uses[2] = {0u, 0u};
+            for (; cur.tile < n_tiles; next(cur)) {
+                const uint32_t sb = sb_of(cur), sph = uses[sb]++ & 1u;
                 int row0, col0, nblk;
                 coords(cur, row0, col0, nblk);
                 mbar_wait(gfull_bar(sb), sph);
@@ -343,9 +358,9 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                 bulk_commit();
                 bulk_wait_read0();          // the unit has been read out of shared memory
                 if (!has_res) mbar_arrive(sfree_bar(sb));
-                else if (pre.tile < n_tiles) {
-                    load_res(pre, sb);
-                    next(pre);
+                else {
+                    next_same(pre[sb]);
+                    if (pre[sb].tile < n_tiles) load_res(pre[sb], sb);
                 }
             }
             bulk_wait_all();                // the last stores have reached global memory
@@ -358,9 +373,11 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
         TOut *y = static_cast<TOut *>(a.y);
         const TRes *res = static_cast<const TRes *>(a.res);
         const bool wide_st = sizeof(TOut) == 2 && (reinterpret_cast<uintptr_t>(a.y) & 31) == 0 && a.out_ld % 16 == 0 && a.out_choff % 16 == 0;
-        uint32_t it = 0, unit = 0;
-        (void)unit;
+        const int grp = warp >= 10 ? 1 : 0;
+        uint32_t it = 0, uses0 = 0, uses1 = 0;       // uses of staging buffer 0 / 1 so far (N = 256: by either group)
+        (void)uses0; (void)uses1;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            if (!kSplitCols && two_groups && (int)(it & 1u) != grp) continue;      // the groups take alternate tiles
             const long long mt = tile / n_tiles_n;
             const int nt = (int)(tile - mt * n_tiles_n);
             const long long m = mt * BLOCK_M + row;
@@ -380,13 +397,17 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                 // alone.  (With one buffer and the store issued from here, every tile cost ~3.5 us however small:
                 // math -> store -> wait for the read -> residual load -> next tile.)  Row-strided per-lane global accesses
                 // - 32 different lines per warp instruction - are what made the residual GEMMs run below 1 TB/s before.
+                if (warp == 6) GEMM_TS(it, 6);
                 mbar_wait(accf_bar(buf), acc_phase);
                 tc_fence_after();
+                if (warp == 6) GEMM_TS(it, 7);
                 const uint32_t taddr = tmem_base + buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
                 const uint32_t x7 = (uint32_t)(row & 7);
                 const int units = min(C::kUnitsPerTile, (a.Cout - n0 + 127) / 128);
-                for (int h = 0; h < units; ++h, ++unit) {
-                const uint32_t sb = unit & 1u, sph = (unit >> 1) & 1u;
+                const int h_lo = kSplitCols ? grp : 0, h_hi = kSplitCols ? min(units, grp + 1) : units;
+                for (int h = h_lo; h < h_hi; ++h) {
+                const uint32_t sb = kSplitCols ? (uint32_t)h : (it & 1u);
+                const uint32_t sph = kSplitCols ? ((h == 0 ? uses0 : uses1) & 1u) : ((it >> 1) & 1u);
                 if (res != nullptr) mbar_wait(rfull_bar(sb), sph);
                 else mbar_wait(sfree_bar(sb), sph ^ 1u);
                 const uint32_t srow = s_stg + sb * C::kUnitBytes + (uint32_t)row * 128u;
@@ -458,13 +479,13 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                               make_uint4(pack2(v[8 * e], v[8 * e + 1]), pack2(v[8 * e + 2], v[8 * e + 3]), pack2(v[8 * e + 4], v[8 * e + 5]),
                                          pack2(v[8 * e + 6], v[8 * e + 7])));
                 }
-                if (h == units - 1) {           // all TMEM reads of the tile are done: the accumulator may be overwritten
-                    tc_fence_before();
-                    mbar_arrive(acce_bar(buf));
-                }
                 fence_proxy_async();            // staging writes (generic proxy) -> TMA store (async proxy)
                 mbar_arrive(gfull_bar(sb));
                 }
+                ++uses0;
+                if (units == 2) ++uses1;
+                tc_fence_before();              // this group's TMEM reads of the tile are done
+                mbar_arrive(acce_bar(buf));
                 continue;
             }
             mbar_wait(accf_bar(buf), acc_phase);
@@ -473,7 +494,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
             const uint32_t taddr = tmem_base + buf * BLOCK_N + ((uint32_t)(q * 32) << 16);
             // 32 accumulator columns per step: both TMEM loads and the scale/shift loads are in flight together
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            for (int c0 = kSplitCols ? grp * 128 : 0; c0 < (kSplitCols ? grp * 128 + 128 : BLOCK_N); c0 += 32) {
                 const int n = n0 + c0;
                 if (n >= a.Cout) break;
                 const bool second = n + 16 < a.Cout;         // Cout is a multiple of 16

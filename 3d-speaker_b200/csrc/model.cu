@@ -332,6 +332,14 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                             rc = launch_conv_slab3(a, s);
                         }
                     } else if (m->precision == SPK_PREC_BF16 &&
+                        conv_slab4_supported(a, dt(o.in_buf), dt(o.out_buf), dt(o.res_buf))) {
+                        const __nv_bfloat16 *wb = nullptr;
+                        rc = param_bf16(m, o.w, &wb, s);
+                        if (rc == SPK_OK) {
+                            a.w = wb;
+                            rc = launch_conv_slab4(a, s);
+                        }
+                    } else if (m->precision == SPK_PREC_BF16 &&
                         conv_slab_supported(a, dt(o.in_buf), dt(o.out_buf), dt(o.res_buf))) {
                         const __nv_bfloat16 *wb = nullptr;
                         rc = param_bf16(m, o.w, &wb, s);

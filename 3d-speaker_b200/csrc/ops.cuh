@@ -40,6 +40,9 @@ int launch_conv_slab(const ConvArgs &a, cudaStream_t s);
 // third generation of the same (conv_slab3.cu): TMA-staged 64B-swizzled slabs, lean MMA issue
 bool conv_slab3_supported(const ConvArgs &a, int in_dtype, int out_dtype, int res_dtype);
 int launch_conv_slab3(const ConvArgs &a, cudaStream_t s);
+// 3x3 stride-1 convs with up to 64 channels, rows of any width (conv_slab4.cu): column parts, 64/128-byte pixels
+bool conv_slab4_supported(const ConvArgs &a, int in_dtype, int out_dtype, int res_dtype);
+int launch_conv_slab4(const ConvArgs &a, cudaStream_t s);
 
 // fused CAM layer (cam_local.cu): dilated k=3 conv (128->32) + context gate + gating multiply
 bool cam_local_supported(const ConvArgs &a, int in_dtype, int out_dtype, int hidden, int seg_len);

@@ -126,6 +126,13 @@ CASES = [
     ("tdnn_kh10_kw5_s2", 3, 10, 148, 32, 128, 10, 5, (1, 2), (0, 2), (1, 1)),
     ("ragged_m_not_multiple_of_128", 1, 1, 131, 64, 64, 1, 1, (1, 1), (0, 0), (1, 1)),
     ("k_not_multiple_of_64", 2, 1, 150, 160, 48, 1, 1, (1, 1), (0, 0), (1, 1)),
+    # conv_slab4: Res2Net branch convs of ERes2NetV2 (3 s segments: column parts; 128-byte pixels; N = 48)
+    ("3x3_c64_w149_parts", 2, 13, 149, 64, 64, 3, 3, (1, 1), (1, 1), (1, 1)),
+    ("3x3_c48_w149_parts", 2, 9, 149, 48, 48, 3, 3, (1, 1), (1, 1), (1, 1)),
+    ("3x3_c32_w298_parts", 2, 11, 298, 32, 32, 3, 3, (1, 1), (1, 1), (1, 1)),
+    ("3x3_c64_w38", 3, 10, 38, 64, 64, 3, 3, (1, 1), (1, 1), (1, 1)),
+    ("3x3_c16_w75", 2, 7, 75, 16, 16, 3, 3, (1, 1), (1, 1), (1, 1)),
+    ("3x3_c32_w1000_parts", 1, 5, 1000, 32, 32, 3, 3, (1, 1), (1, 1), (1, 1)),
 ]
 
 
@@ -188,6 +195,49 @@ def test_conv_residual_relu(precision):
     torch.manual_seed(33)
     y, ref = run_conv(x, w, pad=(1, 1), epi=epi, residual=True, act=_lib.ACT_RELU, precision=precision)
     _check(y, ref, 1e-4 if precision == "fp32" else 1e-4)
+
+
+def test_slab4_residual_c64_parts():
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 9, 149, 64, generator=g)
+    w = torch.randn(64, 3, 3, 64, generator=g) / math.sqrt(576)
+    epi = (torch.rand(64, generator=g) + 0.5, 0.1 * torch.randn(64, generator=g))
+    torch.manual_seed(34)
+    y, ref = run_conv(x, w, pad=(1, 1), epi=epi, residual=True, act=_lib.ACT_CLAMP20, precision="bf16", chunk=2)
+    _check(y, ref, 1e-4)
+
+
+def test_slab4_channel_windows_are_clipped():
+    """A 48-channel conv reads a window of an 80-channel buffer and writes a window of a 96-channel buffer (the
+    Res2Net `cat` layout, ERes2NetV2.py:77-81): the 64-channel TMA boxes must not use the 16 foreign input channels
+    nor touch the neighbouring output channels."""
+    g = torch.Generator().manual_seed(6)
+    B, H, W, LDI, LDO, C, IN_OFF, OUT_OFF = 2, 12, 149, 80, 96, 48, 16, 48
+    x = torch.randn(B, H, W, LDI, generator=g)
+    wb = torch.randn(LDO, 1, 1, LDI, generator=g) / math.sqrt(LDI)
+    w = torch.randn(C, 3, 3, C, generator=g) / math.sqrt(9 * C)
+    model = Model(_lib.PREC_BF16, "cuda:0")
+    prog = Program(H * W * LDI, H * W * LDO)
+    xin = prog.buf("x", H * W * LDI, _lib.DT_BF16)
+    ybuf = prog.buf("y", H * W * LDO, _lib.DT_BF16)
+    prog.op(_lib.OP_CONV, in_buf=0, in_ld=LDI, out_buf=xin, out_ld=LDI, H=H, W=W, Cin=LDI, Ho=H, Wo=W, Cout=LDI,
+            w=model.param(torch.eye(LDI).reshape(LDI, 1, 1, LDI)))
+    prog.op(_lib.OP_CONV, in_buf=xin, in_ld=LDI, out_buf=ybuf, out_ld=LDO, H=H, W=W, Cin=LDI, Ho=H, Wo=W, Cout=LDO, w=model.param(wb))
+    prog.op(_lib.OP_CONV, in_buf=xin, in_ld=LDI, in_choff=IN_OFF, out_buf=ybuf, out_ld=LDO, out_choff=OUT_OFF, H=H, W=W, Cin=C,
+            Ho=H, Wo=W, Cout=C, KH=3, KW=3, ph=1, pw=1, w=model.param(w), act=_lib.ACT_RELU)
+    prog.op(_lib.OP_CONV, in_buf=ybuf, in_ld=LDO, out_buf=1, out_ld=LDO, H=H, W=W, Cin=LDO, Ho=H, Wo=W, Cout=LDO,
+            w=model.param(torch.eye(LDO).reshape(LDO, 1, 1, LDO)))
+    model.set_program(1, prog)
+    out = model.forward(1, x.reshape(B, -1).cuda().contiguous(), H * W * LDO, B).cpu().view(B, H, W, LDO).double()
+    model.close()
+    xr = _bf16_round(x)
+    bg = _bf16_round((xr.double() @ _bf16_round(wb).reshape(LDO, LDI).double().t()).float()).double()
+    conv = F.conv2d(xr[..., IN_OFF:IN_OFF + C].permute(0, 3, 1, 2).double(), _bf16_round(w).permute(0, 3, 1, 2).double(),
+                    padding=1).permute(0, 2, 3, 1)
+    ref = bg.clone()
+    ref[..., OUT_OFF:OUT_OFF + C] = _bf16_round(torch.relu(conv).float()).double()
+    err = (out - ref).abs()
+    assert bool((err <= 1e-4 * ref.abs().max() + 2.0 ** -7 * ref.abs()).all()), err.max().item()
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

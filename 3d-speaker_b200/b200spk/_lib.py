@@ -75,6 +75,7 @@ _SIGS = {
     "spk_last_error": (C.c_char_p, []),
     "spk_device_check": (C.c_int, [C.c_int]),
     "spk_launch_count": (C.c_int64, []),
+    "spk_add_launches": (None, [C.c_int64]),
     "spk_fbank_num_frames": (C.c_int64, [C.c_int64]),
     "spk_fbank_set_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "spk_fbank_set_repair": (C.c_int, [C.c_float, C.c_int]),

@@ -5,7 +5,9 @@ Folds BatchNorm (running stats) into per-channel scale/shift, repacks convolutio
 ``spk_model_add_param`` and registers one op list per frame count through
 ``spk_model_set_program``.  Activations are channels-last buffers in a caller-owned workspace.
 """
+import collections
 import ctypes as C
+import os
 
 import torch
 
@@ -50,6 +52,10 @@ class Model:
         self.handle = h
         self.programs = {}
         self._ws = {}
+        # CUDA-graph replay of small-batch forwards (the reference call sites batch 64 windows: ~125 launches of
+        # a few microseconds each, where host launch cost and inter-kernel gaps are most of the call)
+        self.graph_max_batch = int(os.environ.get("SPK_GRAPH_MAX_BATCH", "256"))
+        self._graphs = collections.OrderedDict()
 
     def close(self):
         if self.handle is not None and self.handle.value:
@@ -78,7 +84,7 @@ class Model:
         ws = self._ws.get(key)
         if ws is None:
             n = int(_lib.check(_lib.lib().spk_model_workspace_bytes(self.handle, int(T), int(chunk), int(fine))))
-            self._ws = {}            # keep one workspace alive
+            self._ws = {}            # keep one workspace alive (captured graphs hold their own reference)
             ws = torch.empty(max(n, 16), dtype=torch.uint8, device=self.device)
             self._ws[key] = ws
         return ws
@@ -92,13 +98,46 @@ class Model:
             return emb
         chunk = max(1, min(int(chunk), max(B, 1)))
         fine = chunk if fine <= 0 else max(1, min(int(fine), chunk))
-        ws = self.workspace(T, chunk, fine)
         self._last_chunk = (chunk, fine)
+        if B <= self.graph_max_batch and not torch.cuda.is_current_stream_capturing():
+            return self._forward_graph(T, feats, emb_dim, chunk, fine)
+        ws = self.workspace(T, chunk, fine)
+        self._launch(T, feats, emb, ws, chunk, fine)
+        return emb
+
+    def _launch(self, T, feats, emb, ws, chunk, fine):
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().spk_model_forward(self.handle, int(T), C.c_void_p(feats.data_ptr()), B,
+            _lib.check(_lib.lib().spk_model_forward(self.handle, int(T), C.c_void_p(feats.data_ptr()), feats.shape[0],
                                                     C.c_void_p(emb.data_ptr()), C.c_void_p(ws.data_ptr()),
                                                     ws.numel(), chunk, fine, _lib.current_stream_ptr()))
-        return emb
+
+    def _forward_graph(self, T, feats, emb_dim, chunk, fine):
+        """One captured graph per (T, batch): static input / output / workspace buffers, the forward's launches
+        (programmatic-dependent-launch edges included) replayed with one call."""
+        key = (int(T), tuple(feats.shape), int(emb_dim), chunk, fine)
+        ent = self._graphs.get(key)
+        if ent is None:
+            ws = self.workspace(T, chunk, fine)
+            sfeats = torch.empty_like(feats)
+            semb = torch.empty((feats.shape[0], emb_dim), dtype=torch.float32, device=feats.device)
+            sfeats.copy_(feats)
+            self._launch(T, sfeats, semb, ws, chunk, fine)          # eager once: attribute / tensor-map caches, warm-up
+            torch.cuda.current_stream(self.device).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.lib().spk_launch_count()
+            with torch.cuda.graph(graph):
+                self._launch(T, sfeats, semb, ws, chunk, fine)
+            ent = (graph, sfeats, semb, ws, int(_lib.lib().spk_launch_count() - n0))
+            self._graphs[key] = ent
+            while len(self._graphs) > 8:
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
+        graph, sfeats, semb, ws, n_launch = ent
+        sfeats.copy_(feats)
+        graph.replay()
+        _lib.lib().spk_add_launches(n_launch)       # the replay ran them; keep the library's launch counter truthful
+        return semb.clone()
 
     def read_buffer(self, T, name, n_segments):
         """Widened copy of a named workspace buffer as the last sub-batch of the last forward

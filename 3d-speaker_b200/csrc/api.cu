@@ -90,3 +90,4 @@ extern "C" int spk_abi_version(void) { return SPK_ABI_VERSION; }
 extern "C" const char *spk_last_error(void) { return spk::t_err; }
 extern "C" int spk_device_check(int dev) { return spk::check_dev(dev); }
 extern "C" int64_t spk_launch_count(void) { return spk::g_launches.load(); }
+extern "C" void spk_add_launches(int64_t n) { spk::g_launches.fetch_add(n, std::memory_order_relaxed); }

@@ -166,6 +166,8 @@ int     spk_model_read_buffer(spk_model_t *m, int64_t T, int32_t buf_id, int64_t
                               const void *workspace, float *dst, int64_t n, void *stream);
 /* kernels launched by spk_* calls since process start (bench.py's gpu_launches) */
 int64_t spk_launch_count(void);
+/* a host layer that replays captured launches (CUDA graph) adds them here so the counter stays truthful */
+void    spk_add_launches(int64_t n);
 
 /* ------------------------------------------------------------------ back end
  * Replaces SpectralCluster.__call__ (speakerlab/process/cluster.py:35-57).

@@ -54,7 +54,7 @@ class Model:
         self._ws = {}
         # CUDA-graph replay of small-batch forwards (the reference call sites batch 64 windows: ~125 launches of
         # a few microseconds each, where host launch cost and inter-kernel gaps are most of the call)
-        self.graph_max_batch = int(os.environ.get("SPK_GRAPH_MAX_BATCH", "256"))
+        self.graph_max_batch = int(os.environ.get("SPK_GRAPH_MAX_BATCH", "128"))
         self._graphs = collections.OrderedDict()
 
     def close(self):

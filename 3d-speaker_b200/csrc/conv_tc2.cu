@@ -59,6 +59,11 @@ template <int BLOCK_N, bool TEPI = false> struct Cfg {
     static constexpr int kSmemBytes = kStages * kStageBytes + kStgBytes + 1024 + 256;
 };
 
+// debug aid: per-stage role timestamps of CTA 0 (SPK_TC2_DBG=1), read back by spk_debug_tc2_timeline
+__device__ long long g_tc2_ts[256 * 8];
+__device__ int g_tc2_dbg;
+#define TC2_TS(idx, slot) do { if (dbg && (idx) < 256) g_tc2_ts[(idx) * 8 + (slot)] = clock64(); } while (0)
+
 struct GatherRegs {
     uint4 v[kRowsPerThread];
     uint32_t pad_mask;     // bit i: piece i is zero padding (prologue must not touch it)
@@ -86,10 +91,12 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kMmaWarp = kProducerWarps + 4;      // warps 0-7 producers, 8-11 epilogue, 12 MMA
+    const bool dbg = g_tc2_dbg != 0 && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kMmaWarp || warp == kProducerWarps);
+    int dbg_idx = 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::kStages; ++s) {
-            mbar_init(full_bar(s), kProducerThreads + 1);     // 256 gather arrivals + the TMA expect_tx arrive
+            mbar_init(full_bar(s), kProducerWarps + 1);       // one arrival per gather warp + the TMA expect_tx arrive
             mbar_init(empty_bar(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -123,13 +130,23 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
         const bf16 *x = static_cast<const bf16 *>(a.x);
         const bool has_pro = pro_scale_bf != nullptr;
 
-        // decoded rows of the tile whose loads are being issued
-        int pix0[kRowsPerThread], hi0[kRowsPerThread], wi0[kRowsPerThread];
+        // Decoded rows of the tile whose loads are being issued.  The gather warps are instruction-latency bound (two
+        // warps per scheduler, one dependent chain each), so everything that does not change from chunk to chunk is
+        // hoisted: per row the element offset of its (kh, kw) = (0, 0) pixel and two bit masks saying which kh / kw
+        // stay inside the image; per thread the (kh, kw, channel) position of its 16-byte column, advanced by 64
+        // channels per chunk without divisions.  A chunk then costs two shifts, an AND and one add per row.
+        long long base0[kRowsPerThread];
+        uint32_t hmask[kRowsPerThread], wmask[kRowsPerThread];
+        int pix0[kRowsPerThread], hi0[kRowsPerThread], wi0[kRowsPerThread];       // reflect / large-kernel path only
+        const bool masked = !a.pad_reflect && a.KH <= 32 && a.KW <= 32;
         auto decode = [&](long long tile) {
             const long long m0 = (tile / n_tiles_n) * BLOCK_M;
 #pragma unroll
             for (int i = 0; i < kRowsPerThread; ++i) {
                 const long long m = m0 + r0 + 32 * i;
+                hmask[i] = 0u;
+                wmask[i] = 0u;
+                base0[i] = 0;
                 if (m < a.M) {
                     const int b = (int)(m / HoWo);
                     const int r = (int)(m - (long long)b * HoWo);
@@ -137,6 +154,17 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
                     pix0[i] = b * a.H * a.W;
                     hi0[i] = ho * a.sh - a.ph;
                     wi0[i] = wo * a.sw - a.pw;
+                    if (masked) {
+                        for (int kh = 0; kh < a.KH; ++kh) {
+                            const int hi = hi0[i] + kh * a.dh;
+                            if (hi >= 0 && hi < a.H) hmask[i] |= 1u << kh;
+                        }
+                        for (int kw = 0; kw < a.KW; ++kw) {
+                            const int wi = wi0[i] + kw * a.dw;
+                            if (wi >= 0 && wi < a.W) wmask[i] |= 1u << kw;
+                        }
+                        base0[i] = ((long long)pix0[i] + (long long)hi0[i] * a.W + wi0[i]) * a.in_ld + a.in_choff;
+                    }
                 } else {
                     pix0[i] = 0;
                     hi0[i] = -(1 << 28);
@@ -144,30 +172,47 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
                 }
             }
         };
+        // (kh, kw, c) of this thread's column in the chunk being issued
+        int ckh = 0, ckw = 0, cc = 0;
+        auto col_reset = [&]() {
+            ckh = 0; ckw = 0; cc = j * 8;
+            while (cc >= a.Cin) { cc -= a.Cin; if (++ckw == a.KW) { ckw = 0; ++ckh; } }
+        };
+        auto col_advance = [&]() {
+            cc += BLOCK_K;
+            while (cc >= a.Cin) { cc -= a.Cin; if (++ckw == a.KW) { ckw = 0; ++ckh; } }
+        };
         auto issue = [&](int kc, GatherRegs &g) {
-            const int k = kc * BLOCK_K + j * 8;
             g.pad_mask = 0;
-            int kh = 0, kw = 0, c = 0;
-            const bool k_ok = k < a.K;
-            if (k_ok) {
-                const int tap = k / a.Cin;
-                c = k - tap * a.Cin;
-                kh = tap / a.KW;
-                kw = tap - kh * a.KW;
-            }
+            if (kc == 0) col_reset();
+            const bool k_ok = ckh < a.KH;
+            if (masked) {
+                const long long delta = ((long long)(ckh * a.dh) * a.W + ckw * a.dw) * a.in_ld + cc;
 #pragma unroll
-            for (int i = 0; i < kRowsPerThread; ++i) {
-                const int hi = hi0[i] + kh * a.dh;
-                int wi = wi0[i] + kw * a.dw;
-                if (a.pad_reflect) wi = wi < 0 ? -wi : (wi >= a.W ? 2 * (a.W - 1) - wi : wi);
-                if (k_ok && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
-                    const long long off = ((long long)pix0[i] + (long long)hi * a.W + wi) * a.in_ld + a.in_choff + c;
-                    g.v[i] = ldg16(x + off);
-                } else {
-                    g.v[i] = make_uint4(0u, 0u, 0u, 0u);
-                    g.pad_mask |= 1u << i;
+                for (int i = 0; i < kRowsPerThread; ++i) {
+                    if (k_ok && ((hmask[i] >> ckh) & (wmask[i] >> ckw) & 1u)) {
+                        g.v[i] = ldg16(x + base0[i] + delta);
+                    } else {
+                        g.v[i] = make_uint4(0u, 0u, 0u, 0u);
+                        g.pad_mask |= 1u << i;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kRowsPerThread; ++i) {
+                    const int hi = hi0[i] + ckh * a.dh;
+                    int wi = wi0[i] + ckw * a.dw;
+                    if (a.pad_reflect) wi = wi < 0 ? -wi : (wi >= a.W ? 2 * (a.W - 1) - wi : wi);
+                    if (k_ok && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W) {
+                        const long long off = ((long long)pix0[i] + (long long)hi * a.W + wi) * a.in_ld + a.in_choff + cc;
+                        g.v[i] = ldg16(x + off);
+                    } else {
+                        g.v[i] = make_uint4(0u, 0u, 0u, 0u);
+                        g.pad_mask |= 1u << i;
+                    }
                 }
             }
+            col_advance();
         };
         int stage = 0;
         uint32_t phase = 0;
@@ -189,7 +234,9 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
                     }
                 }
             }
+            TC2_TS(dbg_idx, 0);
             mbar_wait(empty_bar(stage), phase ^ 1u);
+            TC2_TS(dbg_idx, 1);
             const uint32_t sa = base + stage * C::kStageBytes;
             if (t == 0) {
                 const int nt = (int)(tile % n_tiles_n);
@@ -199,43 +246,89 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
 #pragma unroll
             for (int i = 0; i < kRowsPerThread; ++i) sts16(sa + sw_off + i * 4096, g.v[i]);
             fence_proxy_async();
-            mbar_arrive(full_bar(stage));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_bar(stage));        // 8 arrivals per stage instead of 256 on one barrier word
+            TC2_TS(dbg_idx, 2);
+            ++dbg_idx;
             if (++stage == C::kStages) {
                 stage = 0;
                 phase ^= 1u;
             }
         };
 
-        // software pipeline over the flattened (tile, kc) sequence, ping-ponging two register sets
-        GatherRegs ga, gb;
-        long long tile = blockIdx.x;
-        int kc = 0;
-        if (tile < n_tiles) {
-            decode(tile);
-            issue(0, ga);
+        long long itile = blockIdx.x, ftile = blockIdx.x;      // issue cursor, finish cursor
+        int ikc = 0, fkc = 0;
+        bool decoded = false;
+        if (!has_pro && masked) {
+            // ---- asynchronous gather: the 16-byte pieces go straight to the stage's swizzled slot with cp.async (zero
+            // padding: a plain store), kAhead chunks ahead of the one being completed; "complete" = this thread's copy
+            // group of that chunk has landed (cp.async.wait_group), then proxy fence + one arrival per warp.  Register
+            // staging cannot run this deep: the loads of all chunks in flight share a few counting scoreboards, so
+            // waiting for the oldest chunk waited for the newest one too (measured: 2 -> 4 register sets, no change).
+            constexpr int kAhead = C::kStages > 3 ? 3 : C::kStages - 1;
+            static_assert(kAhead < C::kStages, "the stage ring must hold the chunks in flight");
+            int istage = 0;
+            uint32_t iphase = 0;
+            auto issue_async = [&]() {
+                if (itile < n_tiles) {
+                    if (!decoded) { decode(itile); decoded = true; }
+                    if (ikc == 0) col_reset();
+                    const bool k_ok = ckh < a.KH;
+                    const long long delta = ((long long)(ckh * a.dh) * a.W + ckw * a.dw) * a.in_ld + cc;
+                    mbar_wait(empty_bar(istage), iphase ^ 1u);
+                    const uint32_t sa = base + istage * C::kStageBytes;
+                    if (t == 0) {
+                        const int nt = (int)(itile % n_tiles_n);
+                        mbar_arrive_expect_tx(full_bar(istage), C::kBBytes);
+                        tma_load_2d(sa + C::kABytes, &wmap, ikc * BLOCK_K, nt * BLOCK_N, full_bar(istage));
+                    }
+#pragma unroll
+                    for (int i = 0; i < kRowsPerThread; ++i) {
+                        const uint32_t dst = sa + sw_off + i * 4096;
+                        if (k_ok && ((hmask[i] >> ckh) & (wmask[i] >> ckw) & 1u))
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(x + base0[i] + delta) : "memory");
+                        else
+                            sts16(dst, make_uint4(0u, 0u, 0u, 0u));
+                    }
+                    col_advance();
+                    if (++ikc == nk) { ikc = 0; itile += gridDim.x; decoded = false; }
+                    if (++istage == C::kStages) { istage = 0; iphase ^= 1u; }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");      // always: keeps the group count uniform at the tail
+            };
+#pragma unroll
+            for (int d = 0; d < kAhead; ++d) issue_async();
+            while (ftile < n_tiles) {
+                issue_async();
+                asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(stage));
+                if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                if (++fkc == nk) { fkc = 0; ftile += gridDim.x; }
+            }
+        } else {
+        // ---- register-staged gather (BN-ReLU prologue, reflect padding): one chunk ahead
+        constexpr int kDepth = 2;
+        GatherRegs g[kDepth];
+        auto issue_next = [&](GatherRegs &dst) {
+            if (itile >= n_tiles) return;
+            if (!decoded) { decode(itile); decoded = true; }
+            issue(ikc, dst);
+            if (++ikc == nk) { ikc = 0; itile += gridDim.x; decoded = false; }
+        };
+#pragma unroll
+        for (int d = 0; d < kDepth - 1; ++d) issue_next(g[d]);
+        while (ftile < n_tiles) {
+#pragma unroll
+            for (int s = 0; s < kDepth; ++s) {
+                if (ftile < n_tiles) {
+                    issue_next(g[(s + kDepth - 1) % kDepth]);
+                    finish(ftile, fkc, g[s]);
+                    if (++fkc == nk) { fkc = 0; ftile += gridDim.x; }
+                }
+            }
         }
-        while (tile < n_tiles) {
-            // ---- ga holds (tile, kc); prefetch the successor into gb
-            long long ntile = tile;
-            int nkc = kc + 1;
-            if (nkc == nk) { nkc = 0; ntile = tile + gridDim.x; }
-            if (ntile < n_tiles) {
-                if (ntile != tile) decode(ntile);
-                issue(nkc, gb);
-            }
-            finish(tile, kc, ga);
-            tile = ntile; kc = nkc;
-            if (tile >= n_tiles) break;
-            // ---- gb holds (tile, kc); prefetch the successor into ga
-            ntile = tile;
-            nkc = kc + 1;
-            if (nkc == nk) { nkc = 0; ntile = tile + gridDim.x; }
-            if (ntile < n_tiles) {
-                if (ntile != tile) decode(ntile);
-                issue(nkc, ga);
-            }
-            finish(tile, kc, gb);
-            tile = ntile; kc = nkc;
         }
     } else if (warp == kMmaWarp) {
         // =========================== MMA issuer ===========================
@@ -248,8 +341,10 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
             for (int kc = 0; kc < nk; ++kc) {
+                TC2_TS(dbg_idx, 3);
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
+                TC2_TS(dbg_idx, 4);
                 if (lane == 0) {
                     const uint32_t sa = base + stage * C::kStageBytes;
                     const uint64_t ad = make_desc_sw128(sa), bd = make_desc_sw128(sa + C::kABytes);
@@ -260,6 +355,8 @@ conv_tc2_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const b
                     if (kc == nk - 1) umma_commit(accf_bar(buf));
                 }
                 __syncwarp();
+                TC2_TS(dbg_idx, 5);
+                ++dbg_idx;
                 if (++stage == C::kStages) {
                     stage = 0;
                     phase ^= 1u;
@@ -655,3 +752,9 @@ int launch_conv_tc(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t
 }
 
 }  // namespace spk
+
+// debug aids (not part of the ABI)
+extern "C" int spk_debug_tc2_enable(int on) { return cudaMemcpyToSymbol(spk::g_tc2_dbg, &on, sizeof(int)) == cudaSuccess ? 0 : -1; }
+extern "C" int spk_debug_tc2_timeline(long long *dst) {
+    return cudaMemcpyFromSymbol(dst, spk::g_tc2_ts, sizeof(long long) * 256 * 8) == cudaSuccess ? 0 : -1;
+}

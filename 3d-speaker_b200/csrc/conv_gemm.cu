@@ -18,6 +18,14 @@
 // A read, 96 -> 64 KB of shared-memory traffic per 128x128x64 stage.  For N = 256 the accumulators
 // fill TMEM and the tile is rewritten in place in shared memory instead.
 //
+// Convs that are not 1x1 stride 1 (the 3x3 convs of ERes2NetV2 on 96-208 channels, strided 1x1 shortcuts, the CAM++ tdnn
+// layer) run through the same kernel with the A tile fetched by TMA IM2COL loads: a tensor map over the [B, H, W, C]
+// activations whose pixel box is the set of filter base positions; one cp.async.bulk.tensor.4d...im2col per (filter
+// tap, 64-channel chunk) delivers the 128 consecutive output pixels of the tile (walking W, then H, then B with the
+// conv stride, out-of-image taps zero-filled) as the same 128B-swizzled K-major tile.  The K loop is taps x chunks;
+// a chunk that runs past Cin reads zeros (the map's channel axis ends at the conv's last input channel).  The
+// gather kernel this replaces was bound by its 16-byte loads at ~3 TB/s of L2 traffic (conv_tc2.cu).
+//
 // Warp roles (320 threads, one persistent CTA per SM): 0 TMA producer, 1 TMEM alloc + MMA issue,
 // 2-5 transform, 6-9 epilogue (folded BN, residual, activation, CAM gate; double-buffered TMEM
 // accumulator so the epilogue of tile i overlaps the mainloop of tile i+1).
@@ -64,6 +72,12 @@ __device__ __forceinline__ void umma_bf16_ta(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap *map, int c, int w, int h, int n, uint16_t off_w,
+                                                   uint16_t off_h, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h) : "memory");
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 // SW128 K-major descriptor from 32-bit halves (stepping K by 16 elements = +2 on the low half)
 __device__ __forceinline__ uint32_t sw128_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
@@ -103,7 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const bf16 *__restrict__ pro_shift_bf,
                  int n_tiles_n, long long n_tiles, const __grid_constant__ CUtensorMap amap,
                  const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap ymap,
-                 const __grid_constant__ CUtensorMap rmap, int dbg) {
+                 const __grid_constant__ CUtensorMap rmap, int dbg, int im2col) {
     using C = Cfg<BLOCK_N, TEPI>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -175,7 +189,8 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int nk = (a.K + BLOCK_K - 1) / BLOCK_K;
+    const int chunks = (a.Cin + BLOCK_K - 1) / BLOCK_K;                      // im2col: 64-channel chunks per filter tap
+    const int nk = im2col ? a.KH * a.KW * chunks : (a.K + BLOCK_K - 1) / BLOCK_K;
     pdl_wait();          // everything above read only parameters; the activations come from the previous kernel
 
     if (warp == 0) {
@@ -186,13 +201,31 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const long long mt = tile / n_tiles_n;
                 const int nt = (int)(tile - mt * n_tiles_n);
+                // im2col: base position (filter tap 0, 0) of the tile's first output pixel
+                int bw = 0, bh = 0, bn = 0, kh = 0, kw = 0, ch = 0;
+                if (im2col) {
+                    const long long m0 = mt * BLOCK_M;
+                    const int hw = a.Ho * a.Wo;
+                    bn = (int)(m0 / hw);
+                    const int r = (int)(m0 - (long long)bn * hw);
+                    const int p = r / a.Wo;
+                    bh = p * a.sh - a.ph;
+                    bw = (r - p * a.Wo) * a.sw - a.pw;
+                }
                 for (int kc = 0; kc < nk; ++kc, ++sidx) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     GEMM_TS(sidx, 0);
                     const uint32_t sa = base + stage * C::kStageBytes;
                     mbar_arrive_expect_tx(land_bar(stage), C::kStageBytes);
-                    tma_load_2d(sa, &amap, kc * BLOCK_K, (int)(mt * BLOCK_M), land_bar(stage));
-                    tma_load_2d(sa + C::kABytes, &wmap, kc * BLOCK_K, nt * BLOCK_N, land_bar(stage));
+                    if (im2col) {
+                        tma_load_im2col_4d(sa, &amap, a.in_choff + ch * BLOCK_K, bw, bh, bn, (uint16_t)(kw * a.dw), (uint16_t)(kh * a.dh),
+                                           land_bar(stage));
+                        tma_load_2d(sa + C::kABytes, &wmap, (kh * a.KW + kw) * a.Cin + ch * BLOCK_K, nt * BLOCK_N, land_bar(stage));
+                        if (++ch == chunks) { ch = 0; if (++kw == a.KW) { kw = 0; ++kh; } }
+                    } else {
+                        tma_load_2d(sa, &amap, kc * BLOCK_K, (int)(mt * BLOCK_M), land_bar(stage));
+                        tma_load_2d(sa + C::kABytes, &wmap, kc * BLOCK_K, nt * BLOCK_N, land_bar(stage));
+                    }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -655,6 +688,54 @@ int make_map(const void *ptr, long long rows, int cols, long long ld, int box_ro
     return SPK_OK;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const int *, const int *, cuuint32_t, cuuint32_t, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeIm2colFn encode_im2col_fn() {
+    static EncodeIm2colFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeIm2colFn>(p);
+    }();
+    return fn;
+}
+
+// IM2COL map over the channels-last activations [B][H][W][ld] (channel axis ending at the conv's last input channel):
+// pixel box = filter base positions [-pad, size + pad - (k - 1) dil), traversal stride = conv stride, 64 channels x 128
+// pixels per load, 128B swizzle
+int make_im2col_map(const ConvArgs &a, CUtensorMap *out) {
+    EncodeIm2colFn fn = encode_im2col_fn();
+    if (fn == nullptr) {
+        set_error("cuTensorMapEncodeIm2col is not available from the driver");
+        return SPK_ERR_CUDA;
+    }
+    const cuuint64_t dims[4] = {(cuuint64_t)(a.in_choff + a.Cin), (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)a.in_ld * 2, (cuuint64_t)a.W * a.in_ld * 2, (cuuint64_t)a.H * a.W * a.in_ld * 2};
+    const int lower[2] = {-a.pw, -a.ph};
+    const int upper[2] = {a.pw - (a.KW - 1) * a.dw, a.ph - (a.KH - 1) * a.dh};
+    const cuuint32_t estr[4] = {1u, (cuuint32_t)a.sw, (cuuint32_t)a.sh, 1u};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(a.x), dims, strides, lower, upper, (cuuint32_t)BLOCK_K,
+                    (cuuint32_t)BLOCK_M, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeIm2col failed (%d): [%d][%d][%d][%d] k%dx%d s%d,%d p%d,%d d%d,%d", (int)r, a.B, a.H, a.W, a.in_ld, a.KH,
+                  a.KW, a.sh, a.sw, a.ph, a.pw, a.dh, a.dw);
+        return SPK_ERR_CUDA;
+    }
+    // small-tensor workaround the CUTLASS host code applies for drivers up to 13.1 (cute/atom/copy_traits_sm90_im2col.hpp)
+    int drv = 0;
+    if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && (long long)a.B * a.H * a.W * a.in_ld * 2 < 131072)
+        reinterpret_cast<uint64_t *>(out)[1] &= ~(1ull << 21);
+    return SPK_OK;
+}
+
+bool is_plain_gemm(const ConvArgs &a) {
+    return a.KH == 1 && a.KW == 1 && a.sh == 1 && a.sw == 1 && a.ph == 0 && a.pw == 0 && a.Ho == a.H && a.Wo == a.W;
+}
+
 int bf16_vector(const float *src, int n, const bf16 **out, cudaStream_t s) {
     static std::mutex mu;
     static std::map<const float *, bf16 *> cache;
@@ -686,7 +767,8 @@ int launch_one(const ConvArgs &a, cudaStream_t s) {
         return SPK_ERR_CUDA;
     }
     CUtensorMap amap, wmap;
-    int rc = make_map(static_cast<const bf16 *>(a.x) + a.in_choff, a.M, a.Cin, a.in_ld, BLOCK_M, &amap);
+    const int im2col = is_plain_gemm(a) ? 0 : 1;
+    int rc = im2col ? make_im2col_map(a, &amap) : make_map(static_cast<const bf16 *>(a.x) + a.in_choff, a.M, a.Cin, a.in_ld, BLOCK_M, &amap);
     if (rc == SPK_OK) rc = make_map(a.w, a.Cout, a.K, a.K, BLOCK_N, &wmap);
     if (rc != SPK_OK) return rc;
     CUtensorMap ymap = amap, rmap = amap;        // placeholders unless the TMA epilogue is used
@@ -714,12 +796,12 @@ int launch_one(const ConvArgs &a, cudaStream_t s) {
     const long long grid = std::min<long long>(tiles, sm_count());
     static const int dbg_k = getenv("SPK_GEMM_DBG") ? atoi(getenv("SPK_GEMM_DBG")) : 0;      // timeline of launches with this K
     const int dbg = dbg_k != 0 && dbg_k == a.K;
-    const int smem_bytes = C::kSmemBytes + 2 * ((a.K + BLOCK_K - 1) / BLOCK_K) * 128;      // + prologue scale/shift
+    const int smem_bytes = C::kSmemBytes + (a.pro_scale != nullptr ? 2 * ((a.K + BLOCK_K - 1) / BLOCK_K) * 128 : 0);      // + prologue scale/shift
     if (smem_bytes > 227 * 1024) {
         set_error("conv_gemm: K=%d too large for the shared-memory prologue tables", a.K);
         return SPK_ERR_UNSUPPORTED;
     }
-    const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), (size_t)smem_bytes, s, a, ps, ph, ntn, tiles, amap, wmap, ymap, rmap, dbg);
+    const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), (size_t)smem_bytes, s, a, ps, ph, ntn, tiles, amap, wmap, ymap, rmap, dbg, im2col);
     if (le != cudaSuccess) {
         set_error("conv_gemm_kernel launch failed: %s", cudaGetErrorString(le));
         return SPK_ERR_CUDA;
@@ -755,9 +837,17 @@ int launch_n(const ConvArgs &a, cudaStream_t s) {
 
 bool conv_gemm_supported(const ConvArgs &a, int in_dtype) {
     if (!conv_tc_supported(a, in_dtype)) return false;
-    if (a.KH != 1 || a.KW != 1 || a.sh != 1 || a.sw != 1 || a.ph != 0 || a.pw != 0) return false;
-    if (a.Ho != a.H || a.Wo != a.W) return false;
     if ((reinterpret_cast<uintptr_t>(a.x) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.w) & 15) != 0) return false;
+    if (is_plain_gemm(a)) return true;
+    // everything else: TMA im2col loads (zero padding only, no per-channel prologue in front of the padding)
+    static const bool off = [] { const char *e = getenv("SPK_NO_IM2COL"); return e && e[0] == '1'; }();
+    if (off || a.pro_scale != nullptr || a.pad_reflect) return false;
+    if (a.Cin % 8 != 0 || a.sh > 8 || a.sw > 8 || a.in_ld % 8 != 0 || a.in_choff % 8 != 0) return false;
+    const int lw = -a.pw, lh = -a.ph, uw = a.pw - (a.KW - 1) * a.dw, uh = a.ph - (a.KH - 1) * a.dh;
+    if (lw < -128 || lh < -128 || uw < -128 || uh < -128 || uw > 127 || uh > 127) return false;
+    if ((a.KW - 1) * a.dw > 255 || (a.KH - 1) * a.dh > 255) return false;
+    if (a.W + uw - lw < 1 || a.H + uh - lh < 1) return false;            // the pixel box must not be empty
+    if (a.Wo != (a.W + uw - lw - 1) / a.sw + 1 || a.Ho != (a.H + uh - lh - 1) / a.sh + 1) return false;
     return true;
 }
 

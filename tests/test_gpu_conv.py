@@ -133,6 +133,13 @@ CASES = [
     ("3x3_c64_w38", 3, 10, 38, 64, 64, 3, 3, (1, 1), (1, 1), (1, 1)),
     ("3x3_c16_w75", 2, 7, 75, 16, 16, 3, 3, (1, 1), (1, 1), (1, 1)),
     ("3x3_c32_w1000_parts", 1, 5, 1000, 32, 32, 3, 3, (1, 1), (1, 1), (1, 1)),
+    # TMA im2col path of conv_gemm: wide 3x3 convs (partial last 64-channel chunk), strided 1x1 / 3x3, tiles crossing images
+    ("im2col_3x3_c112", 3, 20, 75, 112, 112, 3, 3, (1, 1), (1, 1), (1, 1)),
+    ("im2col_3x3_c208", 2, 10, 38, 208, 208, 3, 3, (1, 1), (1, 1), (1, 1)),
+    ("im2col_1x1_stride2", 3, 40, 149, 128, 256, 1, 1, (2, 2), (0, 0), (1, 1)),
+    ("im2col_3x3_stride2", 2, 20, 75, 64, 128, 3, 3, (2, 2), (1, 1), (1, 1)),
+    ("im2col_small_images", 40, 3, 5, 64, 64, 3, 3, (1, 1), (1, 1), (1, 1)),
+    ("im2col_k3_dil3_1d", 4, 1, 200, 96, 96, 1, 3, (1, 1), (0, 3), (1, 3)),
 ]
 
 

@@ -841,7 +841,8 @@ bool conv_gemm_supported(const ConvArgs &a, int in_dtype) {
     if (is_plain_gemm(a)) return true;
     // everything else: TMA im2col loads (zero padding only, no per-channel prologue in front of the padding)
     static const bool off = [] { const char *e = getenv("SPK_NO_IM2COL"); return e && e[0] == '1'; }();
-    if (off || a.pro_scale != nullptr || a.pad_reflect) return false;
+    if (off || a.pro_scale != nullptr) return false;
+    if (a.pad_reflect && !reflect_edge_fix_supported(a)) return false;      // zero-padded conv, then the edge fix
     if (a.Cin % 8 != 0 || a.sh > 8 || a.sw > 8 || a.in_ld % 8 != 0 || a.in_choff % 8 != 0) return false;
     const int lw = -a.pw, lh = -a.ph, uw = a.pw - (a.KW - 1) * a.dw, uh = a.ph - (a.KH - 1) * a.dh;
     if (lw < -128 || lh < -128 || uw < -128 || uh < -128 || uw > 127 || uh > 127) return false;
@@ -851,7 +852,15 @@ bool conv_gemm_supported(const ConvArgs &a, int in_dtype) {
     return true;
 }
 
+int launch_conv_gemm_main(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s);
+
 int launch_conv_gemm(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s) {
+    const int rc = launch_conv_gemm_main(a, out_dtype, res_dtype, s);
+    if (rc != SPK_OK || !a.pad_reflect || a.M == 0) return rc;
+    return launch_reflect_edge_fix(a, out_dtype, s);
+}
+
+int launch_conv_gemm_main(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s) {
     if (a.M == 0) return SPK_OK;
     const bool res_bf16 = a.res == nullptr ? (out_dtype == SPK_DT_BF16) : (res_dtype == SPK_DT_BF16);
     if (out_dtype == SPK_DT_BF16) {

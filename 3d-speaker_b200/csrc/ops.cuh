@@ -108,6 +108,8 @@ int launch_asp_pool(const AspPoolArgs &a, int l_dtype, int x_dtype, cudaStream_t
 // small_ops.cu: cluster split-K linear layer, split-T squeeze-excitation gate, sliced / one-pass pooling for long axes
 bool linear_supported(const ConvArgs &a, int in_dtype, int out_dtype);
 int launch_linear(const ConvArgs &a, int in_dtype, int out_dtype, cudaStream_t s);
+bool reflect_edge_fix_supported(const ConvArgs &a);           // 1-D 'same' conv with reflect padding: zero-padded conv + edge fix
+int launch_reflect_edge_fix(const ConvArgs &a, int out_dtype, cudaStream_t s);     // a.w: bf16 [Cout][KW][Cin]
 bool se_gate_cluster_supported(const CamGateArgs &a, int in_dtype);
 int launch_se_gate_cluster(const CamGateArgs &a, int in_dtype, cudaStream_t s);
 bool stats_pool_sliced_supported(const StatsPoolArgs &a);

@@ -61,9 +61,11 @@ linear_splitk_kernel(const ConvArgs a, int kper) {
     const bool a_ok = lm < a.M, b_ok = n0 + lrow < a.Cout;
     const int ty = tid >> 4, tx = tid & 15;
     float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-    for (int k0 = kbeg; k0 < kend; k0 += LBK) {
+    // the next step's global loads are issued before the current step's 32 x 4 FMAs (register double buffering)
+    auto fetch = [&](int k0, float (&av)[4], float (&bv)[4]) {
         const int k = k0 + k4;
-        float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { av[i] = 0.f; bv[i] = 0.f; }
         if (a_ok && k < kend) {
             ld4<TIn>(xrow + k, av);
             if (a.pro_scale != nullptr) {
@@ -78,6 +80,10 @@ linear_splitk_kernel(const ConvArgs a, int kper) {
             const float4 t = __ldg(reinterpret_cast<const float4 *>(wrow + k));
             bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
         }
+    };
+    float av[4], bv[4], an[4], bn[4];
+    if (kbeg < kend) fetch(kbeg, av, bv);
+    for (int k0 = kbeg; k0 < kend; k0 += LBK) {
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -85,6 +91,7 @@ linear_splitk_kernel(const ConvArgs a, int kper) {
             Bs[k4 + i][lrow] = bv[i];
         }
         __syncthreads();
+        if (k0 + LBK < kend) fetch(k0 + LBK, an, bn);
 #pragma unroll
         for (int kk = 0; kk < LBK; ++kk) {
             const float2 a2 = *reinterpret_cast<const float2 *>(&As[kk][ty * 2]);
@@ -94,6 +101,8 @@ linear_splitk_kernel(const ConvArgs a, int kper) {
             acc[1][0] = fmaf(a2.y, b2.x, acc[1][0]);
             acc[1][1] = fmaf(a2.y, b2.y, acc[1][1]);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { av[i] = an[i]; bv[i] = bn[i]; }
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i)
@@ -322,6 +331,73 @@ asp_pool_online_kernel(const AspPoolArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ reflect-padding edge fix
+// A 1-D 'same' conv with F.pad(mode='reflect') (ECAPA-TDNN's Conv1d, ECAPA_TDNN.py:49-77) differs from the zero-padded
+// conv only at the pw positions next to each end of a segment.  The tensor-core path runs the zero-padded conv with TMA
+// im2col loads; this kernel then recomputes those 2 pw positions per segment with mirrored taps and the full epilogue.
+// grid (B, 2 ends), thread = output channel: the (KW - 1) dw + 1 input rows an end needs are staged in shared memory
+// (every thread reads the same element: broadcast), each thread walks its own weight row once for all edge positions.
+constexpr int kFixMaxEdge = 8;
+
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+reflect_edge_fix_kernel(const ConvArgs a) {
+    extern __shared__ float xs[];                       // [rows][Cin]
+    const int b = blockIdx.x, right = blockIdx.y;
+    const int E = a.pw, span = (a.KW - 1) * a.dw + 1;    // edge positions per end, input rows they touch
+    const int row0 = right ? a.W - span : 0;
+    const bf16 *x = static_cast<const bf16 *>(a.x) + ((long long)b * a.W + row0) * a.in_ld + a.in_choff;
+    for (int idx = threadIdx.x; idx < span * a.Cin; idx += blockDim.x) {
+        const int r = idx / a.Cin, c = idx - r * a.Cin;
+        xs[idx] = __bfloat162float(x[(long long)r * a.in_ld + c]);
+    }
+    __syncthreads();
+    const bf16 *w = static_cast<const bf16 *>(a.w);      // [Cout][KW][Cin]
+    TOut *y = static_cast<TOut *>(a.y);
+    for (int n = threadIdx.x; n < a.Cout; n += blockDim.x) {
+        float acc[kFixMaxEdge];
+#pragma unroll
+        for (int e = 0; e < kFixMaxEdge; ++e) acc[e] = 0.f;
+        for (int j = 0; j < a.KW; ++j) {
+            int rows[kFixMaxEdge];                        // staged row read by edge position e through tap j
+#pragma unroll
+            for (int e = 0; e < kFixMaxEdge; ++e) {
+                const int t = right ? a.W - E + e : e;
+                int wi = t - a.pw + j * a.dw;
+                wi = wi < 0 ? -wi : (wi >= a.W ? 2 * (a.W - 1) - wi : wi);
+                rows[e] = (wi - row0) * a.Cin;
+            }
+            const bf16 *wr = w + ((long long)n * a.KW + j) * a.Cin;
+            for (int c = 0; c < a.Cin; c += 8) {
+                const uint4 raw = *reinterpret_cast<const uint4 *>(wr + c);
+                const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w4[q]);
+                    const float w0 = __low2float(h), w1 = __high2float(h);
+#pragma unroll
+                    for (int e = 0; e < kFixMaxEdge; ++e) {
+                        if (e < E) {
+                            acc[e] = fmaf(w0, xs[rows[e] + c + 2 * q], acc[e]);
+                            acc[e] = fmaf(w1, xs[rows[e] + c + 2 * q + 1], acc[e]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < kFixMaxEdge; ++e) {
+            if (e >= E) break;
+            const int t = right ? a.W - E + e : e;
+            float v = acc[e];
+            if (a.epi_scale != nullptr) v = fmaf(v, __ldg(a.epi_scale + n), __ldg(a.epi_shift + n));
+            v = apply_act(v, a.act);
+            if (a.post_scale != nullptr) v = apply_act(fmaf(v, __ldg(a.post_scale + n), __ldg(a.post_shift + n)), a.post_act);
+            y[((long long)b * a.W + t) * a.out_ld + a.out_choff + n] = from_f32<TOut>(v);
+        }
+    }
+}
+
 template <typename K, typename... Args>
 cudaError_t launch_cluster(K kern, dim3 grid, dim3 block, size_t smem, dim3 cluster, cudaStream_t s, Args... args) {
     cudaLaunchConfig_t cfg = {};
@@ -367,6 +443,22 @@ int launch_linear(const ConvArgs &a, int in_dtype, int out_dtype, cudaStream_t s
     if (in_dtype == SPK_DT_F32 && out_dtype == SPK_DT_BF16) return linear_dispatch<float, bf16>(a, s);
     if (in_dtype == SPK_DT_BF16 && out_dtype == SPK_DT_F32) return linear_dispatch<bf16, float>(a, s);
     return linear_dispatch<bf16, bf16>(a, s);
+}
+
+bool reflect_edge_fix_supported(const ConvArgs &a) {
+    if (!a.pad_reflect || a.H != 1 || a.KH != 1 || a.sw != 1 || a.Wo != a.W || a.B > 65535) return false;
+    if (a.pw != a.dw * (a.KW - 1) / 2 || a.pw < 1 || a.pw > kFixMaxEdge || (a.KW - 1) * a.dw + 1 > a.W || 2 * a.pw > a.W) return false;
+    if (a.gate != nullptr || a.res != nullptr || a.pro_scale != nullptr || a.Cin % 8 != 0) return false;
+    return (size_t)((a.KW - 1) * a.dw + 1) * a.Cin * sizeof(float) <= 48 * 1024;
+}
+
+int launch_reflect_edge_fix(const ConvArgs &a, int out_dtype, cudaStream_t s) {
+    if (a.B == 0) return SPK_OK;
+    const size_t sh = (size_t)((a.KW - 1) * a.dw + 1) * a.Cin * sizeof(float);
+    const dim3 grid((unsigned)a.B, 2);
+    if (out_dtype == SPK_DT_BF16) reflect_edge_fix_kernel<bf16><<<grid, 256, sh, s>>>(a);
+    else reflect_edge_fix_kernel<float><<<grid, 256, sh, s>>>(a);
+    return check_launch("reflect_edge_fix_kernel");
 }
 
 bool se_gate_cluster_supported(const CamGateArgs &a, int in_dtype) {

@@ -214,6 +214,36 @@ def test_slab4_residual_c64_parts():
     _check(y, ref, 1e-4)
 
 
+@pytest.mark.parametrize("Cin,Cout,K,dil,T", [(128, 128, 3, 3, 200), (128, 128, 3, 4, 998), (80, 256, 5, 1, 148), (128, 128, 3, 2, 131)])
+def test_reflect_padded_conv1d_im2col_plus_edge_fix(Cin, Cout, K, dil, T):
+    """ECAPA TDNNBlock (ECAPA_TDNN.py:49-77): Conv1d with reflect padding -> ReLU -> BN.  The tensor-core path runs the
+    zero-padded conv with TMA im2col loads and recomputes the positions next to the segment ends with mirrored taps."""
+    g = torch.Generator().manual_seed(9)
+    B, pad = 5, dil * (K - 1) // 2
+    x = torch.randn(B, 1, T, Cin, generator=g)
+    w = torch.randn(Cout, 1, K, Cin, generator=g) / math.sqrt(K * Cin)
+    ps, pb = torch.rand(Cout, generator=g) + 0.5, 0.1 * torch.randn(Cout, generator=g)
+    model = Model(_lib.PREC_BF16, "cuda:0")
+    prog = Program(T * Cin, T * Cout)
+    xin = prog.buf("x", T * Cin, _lib.DT_BF16)
+    ybuf = prog.buf("y", T * Cout, _lib.DT_BF16)
+    prog.op(_lib.OP_CONV, in_buf=0, in_ld=Cin, out_buf=xin, out_ld=Cin, H=1, W=T, Cin=Cin, Ho=1, Wo=T, Cout=Cin,
+            w=model.param(torch.eye(Cin).reshape(Cin, 1, 1, Cin)))
+    prog.op(_lib.OP_CONV, in_buf=xin, in_ld=Cin, out_buf=ybuf, out_ld=Cout, H=1, W=T, Cin=Cin, Ho=1, Wo=T, Cout=Cout, KH=1, KW=K,
+            pw=pad, dw=dil, w=model.param(w), act=_lib.ACT_RELU, aux=[model.param(ps), model.param(pb)], iaux=[_lib.ACT_NONE, 1, 0])
+    prog.op(_lib.OP_CONV, in_buf=ybuf, in_ld=Cout, out_buf=1, out_ld=Cout, H=1, W=T, Cin=Cout, Ho=1, Wo=T, Cout=Cout,
+            w=model.param(torch.eye(Cout).reshape(Cout, 1, 1, Cout)))
+    model.set_program(1, prog)
+    y = model.forward(1, x.reshape(B, -1).cuda().contiguous(), T * Cout, B).cpu().view(B, T, Cout).double()
+    model.close()
+    xr = _bf16_round(x)[:, 0].permute(0, 2, 1).double()                      # [B, Cin, T]
+    wr = _bf16_round(w)[:, 0].permute(0, 2, 1).double()                      # [Cout, Cin, K]
+    ref = F.conv1d(F.pad(xr, (pad, pad), mode="reflect"), wr, dilation=dil).permute(0, 2, 1)
+    ref = _bf16_round((torch.relu(ref) * ps.double() + pb.double()).float()).double()
+    err = (y - ref).abs()
+    assert bool((err <= 1e-4 * ref.abs().max() + 2.0 ** -7 * ref.abs()).all()), (err.max().item(), err.argmax().item())
+
+
 def test_slab4_channel_windows_are_clipped():
     """A 48-channel conv reads a window of an 80-channel buffer and writes a window of a 96-channel buffer (the
     Res2Net `cat` layout, ERes2NetV2.py:77-81): the 64-channel TMA boxes must not use the 16 foreign input channels

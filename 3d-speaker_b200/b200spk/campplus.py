@@ -107,11 +107,13 @@ class CAMPPlus(EngineModule):
 
 class _Engine(EngineBase):
     def default_chunks(self, T):
-        """(coarse, fine) sub-batch sizes.  Measured on B200 (bench.py sweeps): launch
-        count and pipeline fill matter more than L2 residency of the 2-D front, so both are large;
-        they only bound the workspace (about 0.6 MB coarse + 1.9 MB fine per segment in bf16)."""
+        """(coarse, fine) sub-batch sizes.  Measured on B200 (tools/sweep_chunks.py): launch
+        count and pipeline fill matter more than L2 residency of the 2-D front - every kernel of the D-TDNN part
+        pays ~10 us of ramp and tail, ~20 % of a 2048-segment launch - so both are large (16,384 windows: 2048/1024
+        255 k emb/s, 8192/2048 275 k, 16384/4096 279 k); they only bound the workspace (about 0.6 MB coarse + 1.9 MB
+        fine per segment in bf16: 8.8 GB at 8192/2048, allocated for the batch actually seen)."""
         scale = max(1, T // 148)
-        return max(64, 2048 // scale), max(32, 1024 // scale)
+        return max(64, 8192 // scale), max(32, 2048 // scale)
 
     def compile(self, T):
         mod, AD = self.m, self.model.act_dtype

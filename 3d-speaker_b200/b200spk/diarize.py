@@ -97,7 +97,7 @@ class Diarizer:
     """feature_extractor: b200spk.FBank; embedding_model: any b200spk network (on `device`);
     cluster: b200spk.SpectralCluster, AHCluster or CommonClustering (any callable taking the [N, E] embeddings)."""
 
-    def __init__(self, feature_extractor, embedding_model, cluster, device="cuda:0", batchsize=2048,
+    def __init__(self, feature_extractor, embedding_model, cluster, device="cuda:0", batchsize=8192,
                  seg_dur=1.5, seg_shift=0.75, group=None):
         self.fe, self.model, self.cluster = feature_extractor, embedding_model, cluster
         self.device = torch.device(device)

@@ -10,7 +10,8 @@ class EmbeddingExtractor:
     def __init__(self, feature_extractor, embedding_model, device="cuda:0", batchsize=64, reuse_output=False, head=512):
         """``reuse_output``: return a cached pinned host buffer (allocating pinned memory costs milliseconds per call);
         the result is then only valid until the next call.  ``head``: size of the first sub-batch - nothing overlaps
-        the first host-to-device copy, so it is kept short; the remaining batches use ``batchsize``."""
+        the first host-to-device copy, so it is kept short; the following batches grow by 4x per step (the copy of
+        batch i+1 hides behind the compute of batch i only if it is not much larger) until they reach ``batchsize``."""
         self.feature_extractor = feature_extractor
         self.embedding_model = embedding_model
         self.device = torch.device(device)
@@ -35,10 +36,11 @@ class EmbeddingExtractor:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(dev)
         cs = self._copy_stream
-        first = min(self.batchsize, self.head) if (self.head and N > self.batchsize) else self.batchsize
-        bounds = [0, min(first, N)]
+        size = min(self.batchsize, self.head) if (self.head and N > self.batchsize) else self.batchsize
+        bounds = [0, min(size, N)]
         while bounds[-1] < N:
-            bounds.append(min(bounds[-1] + self.batchsize, N))
+            size = min(self.batchsize, size * 4)
+            bounds.append(min(bounds[-1] + size, N))
         starts = bounds[:-1]
         ends = dict(zip(bounds[:-1], bounds[1:]))
 

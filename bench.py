@@ -626,7 +626,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--segments", type=int, default=16384, help="1.5 s windows per GPU per step")
-    ap.add_argument("--batch", type=int, default=2048, help="windows per fbank/forward call")
+    ap.add_argument("--batch", type=int, default=8192, help="windows per fbank/forward call")
     ap.add_argument("--chunk", type=int, default=0, help="coarse sub-batch (D-TDNN part), 0 = auto")
     ap.add_argument("--fine", type=int, default=0, help="fine sub-batch (2-D front), 0 = auto")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
@@ -653,7 +653,7 @@ def main():
 
     chunk = None
     if args.chunk or args.fine:
-        chunk = (args.chunk or 2048, args.fine or min(args.chunk or 2048, 1024))
+        chunk = (args.chunk or 8192, args.fine or min(args.chunk or 8192, 2048))
     model = b200spk.CAMPPlus(embedding_size=EMB, precision=args.precision, chunk=chunk)
     tsd, _ = make_weights(model)
     model.load_state_dict(tsd)

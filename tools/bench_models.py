@@ -39,12 +39,13 @@ def run(name, model, T, n_seg, gflop_per_seg, batch, reps=3):
 
 
 CH = int(os.environ.get("CHUNK", "0")) or None      # engine sub-batch override for experiments
+BS = float(os.environ.get("BATCH_SCALE", "1"))      # batch-size multiplier for experiments
 which = sys.argv[1:] or ["eres", "eres_w24", "ecapa", "ecapa_1p5"]
 if "eres" in which:
-    run("ERes2NetV2 (26,2,2)", b200spk.ERes2NetV2(precision="bf16", chunk=CH), 298, 1024, 24.934, 256)
+    run("ERes2NetV2 (26,2,2)", b200spk.ERes2NetV2(precision="bf16", chunk=CH), 298, int(1024 * max(BS, 1)), 24.934, int(256 * BS))
 if "eres_w24" in which:
-    run("ERes2NetV2 w24s4ep4", b200spk.ERes2NetV2(baseWidth=24, scale=4, expansion=4, precision="bf16", chunk=CH), 298, 512, 73.850, 128)
+    run("ERes2NetV2 w24s4ep4", b200spk.ERes2NetV2(baseWidth=24, scale=4, expansion=4, precision="bf16", chunk=CH), 298, int(512 * max(BS, 1)), 73.850, int(128 * BS))
 if "ecapa" in which:
-    run("ECAPA-TDNN C=1024, 10 s", b200spk.ECAPA_TDNN(80, channels=[1024, 1024, 1024, 1024, 3072], precision="bf16"), 998, 512, 35.848, 128)
+    run("ECAPA-TDNN C=1024, 10 s", b200spk.ECAPA_TDNN(80, channels=[1024, 1024, 1024, 1024, 3072], precision="bf16"), 998, int(512 * max(BS, 1)), 35.848, int(128 * BS))
 if "ecapa_1p5" in which:
     run("ECAPA-TDNN C=1024, 1.5 s", b200spk.ECAPA_TDNN(80, channels=[1024, 1024, 1024, 1024, 3072], precision="bf16"), 148, 4096, 5.552 * 35.848 / 37.416, 512)

@@ -77,6 +77,14 @@ int param_bf16(spk_model *m, int id, const __nv_bfloat16 **out, cudaStream_t s) 
     return SPK_OK;
 }
 
+// SPK_TRACE_DISPATCH=1: one stderr line per conv op saying which kernel family took it (docs / debugging)
+void trace_dispatch(const char *which, const ConvArgs &a) {
+    static const bool on = [] { const char *e = getenv("SPK_TRACE_DISPATCH"); return e && e[0] == '1'; }();
+    if (on)
+        fprintf(stderr, "[spk dispatch] %-10s %dx%dx%d k%dx%d s%d,%d d%d,%d -> %dx%dx%d pro=%d res=%d reflect=%d\n", which, a.H, a.W, a.Cin, a.KH,
+                a.KW, a.sh, a.sw, a.dh, a.dw, a.Ho, a.Wo, a.Cout, a.pro_scale != nullptr, a.res != nullptr, a.pad_reflect);
+}
+
 int validate(const spk_model *m, const spk_program &p) {
     const int nb = (int)p.bufs.size(), np = (int)m->params.size();
     auto buf_ok = [&](int b, bool allow_none) { return (allow_none && b < 0) || (b >= 0 && b < nb); };
@@ -329,6 +337,7 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                         rc = param_bf16(m, o.w, &wb, s);
                         if (rc == SPK_OK) {
                             a.w = wb;
+                            trace_dispatch("slab3", a);
                             rc = launch_conv_slab3(a, s);
                         }
                     } else if (m->precision == SPK_PREC_BF16 &&
@@ -337,6 +346,7 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                         rc = param_bf16(m, o.w, &wb, s);
                         if (rc == SPK_OK) {
                             a.w = wb;
+                            trace_dispatch("slab4", a);
                             rc = launch_conv_slab4(a, s);
                         }
                     } else if (m->precision == SPK_PREC_BF16 &&
@@ -345,6 +355,7 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                         rc = param_bf16(m, o.w, &wb, s);
                         if (rc == SPK_OK) {
                             a.w = wb;
+                            trace_dispatch("slab2", a);
                             rc = launch_conv_slab(a, s);
                         }
                     } else if (m->precision == SPK_PREC_BF16 && conv_gemm_supported(a, dt(o.in_buf))) {
@@ -352,6 +363,7 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                         rc = param_bf16(m, o.w, &wb, s);
                         if (rc == SPK_OK) {
                             a.w = wb;
+                            trace_dispatch(a.KH * a.KW == 1 && a.sh == 1 && a.sw == 1 ? "gemm" : "gemm_im2col", a);
                             rc = launch_conv_gemm(a, dt(o.out_buf), dt(o.res_buf), s);
                         }
                     } else if (m->precision == SPK_PREC_BF16 && conv_tc_supported(a, dt(o.in_buf))) {
@@ -359,10 +371,12 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                         rc = param_bf16(m, o.w, &wb, s);
                         if (rc == SPK_OK) {
                             a.w = wb;
+                            trace_dispatch("tc2_gather", a);
                             rc = launch_conv_tc(a, dt(o.out_buf), dt(o.res_buf), s);
                         }
                     } else {
                         a.w = param(m, o.w);
+                        trace_dispatch("simt", a);
                         rc = launch_conv_simt(a, dt(o.in_buf), dt(o.out_buf), dt(o.res_buf), s);
                     }
                     break;

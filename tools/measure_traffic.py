@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 
-def main(path, segments):
+def main(path, segments, tag="r02_traffic", title="CAM++ forward call (%d x 1.5 s segments, bf16)", model_args=""):
     rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 10]
     hdr = rows[0]
     ik, im, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
@@ -49,12 +49,12 @@ def main(path, segments):
            "dram_bytes_per_segment": (tot_r + tot_w) / segments, "kernel_time_ms_serialised": tot_t / 1e6,
            "launches": sum(e[0] for e in per.values()), "source_hash": bench.source_hash(),
            "command": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none "
-                      "python tools/run_forward.py --segments %d --iters 1" % segments,
+                      "python tools/run_forward.py %s--segments %d --iters 1" % (model_args, segments),
            "per_kernel": {k: {"launches": e[0], "read_MB": e[1] / 1e6, "write_MB": e[2] / 1e6, "ms": e[3] / 1e6}
                           for k, e in sorted(per.items(), key=lambda kv: -(kv[1][1] + kv[1][2]))}}
-    json.dump(out, open(os.path.join(ROOT, "profiles", "r02_traffic.json"), "w"), indent=1)
-    with open(os.path.join(ROOT, "profiles", "r02_traffic.md"), "w") as f:
-        f.write("# DRAM traffic of one CAM++ forward call (%d x 1.5 s segments, bf16), ncu dram__bytes\n\n" % segments)
+    json.dump(out, open(os.path.join(ROOT, "profiles", tag + ".json"), "w"), indent=1)
+    with open(os.path.join(ROOT, "profiles", tag + ".md"), "w") as f:
+        f.write("# DRAM traffic and device time per kernel of one %s, ncu dram__bytes + gpu__time_duration\n\n" % (title % segments))
         f.write("`%s`\n\nTotal %.2f GB read + %.2f GB written = **%.2f MB per segment**, %d launches, %.2f ms of serialised kernel time; csrc hash %s.\n\n"
                 % (out["command"], tot_r / 1e9, tot_w / 1e9, out["dram_bytes_per_segment"] / 1e6, out["launches"], tot_t / 1e6, out["source_hash"]))
         f.write("| kernel | launches | read MB | write MB | ms | GB/s |\n|---|---|---|---|---|---|\n")
@@ -65,4 +65,8 @@ def main(path, segments):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 2048)
+    # python tools/measure_traffic.py csv segments [tag title model_args]
+    if len(sys.argv) > 3:
+        main(sys.argv[1], int(sys.argv[2]), sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else "")
+    else:
+        main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 2048)

@@ -15,7 +15,7 @@ ERR_NAMES = {-1: "SPK_ERR_INVALID", -2: "SPK_ERR_CUDA", -3: "SPK_ERR_UNSUPPORTED
              -4: "SPK_ERR_WORKSPACE", -5: "SPK_ERR_NO_DEVICE", -6: "SPK_ERR_KERNEL"}
 PREC_F32, PREC_BF16 = 0, 1
 DT_F32, DT_BF16 = 0, 1
-OP_STEM, OP_CONV, OP_CAM_GATE, OP_STATS_POOL, OP_AFF_BLEND, OP_CAM_LOCAL, OP_SE_SCALE, OP_ASP_POOL = 1, 2, 3, 4, 5, 6, 7, 8
+OP_STEM, OP_CONV, OP_CAM_GATE, OP_STATS_POOL, OP_AFF_BLEND, OP_CAM_LOCAL, OP_SE_SCALE, OP_ASP_POOL, OP_STEM_BLOCK = 1, 2, 3, 4, 5, 6, 7, 8, 9
 ACT_NONE, ACT_RELU, ACT_CLAMP20, ACT_SILU, ACT_TANH = 0, 1, 2, 3, 4
 
 

@@ -19,6 +19,8 @@ Op mapping (reference file:line -> fused op):
 """
 from collections import OrderedDict
 
+import os
+
 import torch
 from torch import nn
 
@@ -125,10 +127,14 @@ class _Engine(EngineBase):
         bb = prog.buf("fcm_b", h1 * T * C0, AD)
         bc = prog.buf("fcm_c", h1 * T * C0, AD)
         bd = prog.buf("fcm_d", h1 * T * C0, AD)
-        # stem
+        # stem.  In bf16 mode, for segments up to 254 frames, the stem is fused with layer1[0]'s conv1 and shortcut
+        # (SPK_OP_STEM_BLOCK): its output, the largest tensor of the network, is then never stored.
+        fuse_stem = (self.model.precision == _lib.PREC_BF16 and T <= 254 and F % 2 == 0 and T >= 8 and
+                     os.environ.get("SPK_NO_STEM_FUSE", "0") != "1" and "head.layer1.0.shortcut.0.weight" in self.sd)
         s, b = self._bn("head.bn1")
-        prog.op(_lib.OP_STEM, in_buf=0, out_buf=big, out_ld=C0, H=F, W=T, Cout=C0,
-                w=self._raw("head.conv1.weight"), epi_scale=s, epi_shift=b, act=_lib.ACT_RELU)
+        if not fuse_stem:
+            prog.op(_lib.OP_STEM, in_buf=0, out_buf=big, out_ld=C0, H=F, W=T, Cout=C0,
+                    w=self._raw("head.conv1.weight"), epi_scale=s, epi_shift=b, act=_lib.ACT_RELU)
 
         def conv3x3(src, dst, H, stride, wkey, bnkey, act, res=-1):
             Ho = conv_out(H, 3, stride, 1)
@@ -152,7 +158,17 @@ class _Engine(EngineBase):
             conv3x3(tmp, dst, Ho, 1, prefix + ".conv2.weight", prefix + ".bn2", _lib.ACT_RELU, res=res)
             return Ho
 
-        H = res_block("head.layer1.0", big, F, 2, bb, bc, bd)        # -> bd  [F/2]
+        if fuse_stem:
+            p10 = "head.layer1.0"
+            s1, b1 = self._bn(p10 + ".bn1")
+            ss, bs = self._bn(p10 + ".shortcut.1")
+            H = F // 2
+            prog.op(_lib.OP_STEM_BLOCK, in_buf=0, out_buf=bb, out_ld=C0, res_buf=bc, res_ld=C0, H=F, W=T, Ho=H, Wo=T, Cin=1, Cout=C0,
+                    w=self._raw("head.conv1.weight"), epi_scale=s, epi_shift=b, act=_lib.ACT_RELU,
+                    aux=[self._w2d(p10 + ".conv1.weight"), s1, b1, self._w2d(p10 + ".shortcut.0.weight")], iaux=[ss, bs])
+            conv3x3(bb, bd, H, 1, p10 + ".conv2.weight", p10 + ".bn2", _lib.ACT_RELU, res=bc)
+        else:
+            H = res_block("head.layer1.0", big, F, 2, bb, bc, bd)        # -> bd  [F/2]
         H = res_block("head.layer1.1", bd, H, 1, bb, -1, bc)         # -> bc
         H = res_block("head.layer2.0", bc, H, 2, bb, bd, big)        # -> big [F/4]
         H = res_block("head.layer2.1", big, H, 1, bb, -1, bd)        # -> bd

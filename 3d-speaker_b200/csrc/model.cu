@@ -119,6 +119,12 @@ int validate(const spk_model *m, const spk_program &p) {
             case SPK_OP_STATS_POOL:
             case SPK_OP_AFF_BLEND:
                 break;
+            case SPK_OP_STEM_BLOCK:
+                ok = ok && m->precision == SPK_PREC_BF16 && par_ok(o.w, false) && par_ok(o.epi_scale, false) && par_ok(o.epi_shift, false) &&
+                     par_ok(o.aux[0], false) && par_ok(o.aux[1], false) && par_ok(o.aux[2], false) && par_ok(o.aux[3], false) &&
+                     par_ok(o.iaux[0], false) && par_ok(o.iaux[1], false) && o.res_buf >= 0 && o.Cout == 32;
+                if (ok && (m->param_n[o.w] != 32 * 9 || m->param_n[o.aux[0]] != 32 * 9 * 32 || m->param_n[o.aux[3]] != 32 * 32)) ok = false;
+                break;
             case SPK_OP_SE_SCALE:
                 ok = ok && o.gate_buf >= 0;
                 break;
@@ -193,6 +199,12 @@ extern "C" int spk_model_set_program(spk_model_t *m, int64_t T, const spk_buf_t 
         // may stage their weights before waiting on the previous kernel
         const __nv_bfloat16 *tmp = nullptr;
         for (const spk_op_t &o : p.ops) {
+            if (o.kind == SPK_OP_STEM_BLOCK) {
+                rc = param_bf16(m, o.aux[0], &tmp, nullptr);
+                if (rc == SPK_OK) rc = param_bf16(m, o.aux[3], &tmp, nullptr);
+                if (rc != SPK_OK) return rc;
+                continue;
+            }
             if (o.kind != SPK_OP_CONV && o.kind != SPK_OP_CAM_LOCAL) continue;
             rc = param_bf16(m, o.w, &tmp, nullptr);
             if (rc == SPK_OK && o.pro_scale >= 0) rc = param_bf16(m, o.pro_scale, &tmp, nullptr);
@@ -237,7 +249,7 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
     }
     char *ws = static_cast<char *>(workspace);
     NvtxRange whole("spk_model_forward");
-    static const char *kOpNames[] = {"?", "stem", "conv", "cam_gate", "stats_pool", "aff_blend", "cam_local", "se_scale", "asp_pool"};
+    static const char *kOpNames[] = {"?", "stem", "conv", "cam_gate", "stats_pool", "aff_blend", "cam_local", "se_scale", "asp_pool", "stem_block"};
 
     bool has_phase1 = false;
     for (const spk_op_t &o : p.ops) has_phase1 |= (o.phase != 0);
@@ -260,7 +272,7 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
         for (size_t oi = 0; oi < p.ops.size(); ++oi) {
             const spk_op_t &o = p.ops[oi];
             if ((o.phase != 0) != (pass == 1)) continue;
-            NvtxRange op_range(o.kind >= 1 && o.kind <= 8 ? kOpNames[o.kind] : kOpNames[0]);
+            NvtxRange op_range(o.kind >= 1 && o.kind <= 9 ? kOpNames[o.kind] : kOpNames[0]);
             int rc = SPK_OK;
             switch (o.kind) {
                 case SPK_OP_STEM: {
@@ -273,6 +285,27 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                     a.B = n; a.T = o.W; a.F = o.H; a.Cout = o.Cout;
                     a.out_ld = o.out_ld; a.out_choff = o.out_choff; a.act = o.act;
                     rc = launch_stem(a, dt(o.out_buf), s);
+                    break;
+                }
+                case SPK_OP_STEM_BLOCK: {
+                    StemBlockArgs a{};
+                    const __nv_bfloat16 *w1 = nullptr, *ws = nullptr;
+                    rc = param_bf16(m, o.aux[0], &w1, s);
+                    if (rc == SPK_OK) rc = param_bf16(m, o.aux[3], &ws, s);
+                    if (rc != SPK_OK) break;
+                    a.feats = static_cast<const float *>(ptr(o.in_buf));
+                    a.w0 = param(m, o.w); a.s0 = param(m, o.epi_scale); a.b0 = param(m, o.epi_shift);
+                    a.w1 = w1; a.s1 = param(m, o.aux[1]); a.b1 = param(m, o.aux[2]);
+                    a.ws = ws; a.ss = param(m, o.iaux[0]); a.bs = param(m, o.iaux[1]);
+                    a.y1 = ptr(o.out_buf); a.y2 = ptr(o.res_buf);
+                    a.B = n; a.T = o.W; a.F = o.H; a.Ho = o.Ho;
+                    a.y1_ld = o.out_ld; a.y1_choff = o.out_choff; a.y2_ld = o.res_ld; a.y2_choff = o.res_choff;
+                    if (dt(o.out_buf) != SPK_DT_BF16 || dt(o.res_buf) != SPK_DT_BF16 || !stem_block_supported(a)) {
+                        set_error("stem_block: unsupported shape or dtype (T=%d, F=%d)", a.T, a.F);
+                        rc = SPK_ERR_UNSUPPORTED;
+                        break;
+                    }
+                    rc = launch_stem_block(a, s);
                     break;
                 }
                 case SPK_OP_CONV:

@@ -59,6 +59,21 @@ struct StemArgs {
 };
 int launch_stem(const StemArgs &a, int out_dtype, cudaStream_t s);
 
+// stem conv + first FCM block entry in one kernel (conv_stem.cu): y1 = relu(bn1(conv3x3 s(2,1)(stem))), y2 = bn_s(conv1x1 s(2,1)(stem)),
+// stem = relu(bn0(conv3x3(feats))) never stored
+struct StemBlockArgs {
+    const float *feats;                 // [B,T,F]
+    const float *w0, *s0, *b0;          // stem [32][3][3] (kh over F, kw over T), folded BN
+    const __nv_bfloat16 *w1;            // conv1 [32][3][3][32]
+    const float *s1, *b1;
+    const __nv_bfloat16 *ws;            // shortcut [32][32]
+    const float *ss, *bs;
+    void *y1, *y2;                      // [B,F/2,T,ld] bf16
+    int B, T, F, Ho, y1_ld, y1_choff, y2_ld, y2_choff;
+};
+bool stem_block_supported(const StemBlockArgs &a);
+int launch_stem_block(const StemBlockArgs &a, cudaStream_t s);
+
 struct CamGateArgs {
     const void *x;        // [B,T,in_ld] (post BN-ReLU bottleneck)
     float *gate;          // [B,nwin,Cout]

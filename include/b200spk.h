@@ -114,6 +114,11 @@ enum {
     SPK_OP_CAM_LOCAL  = 6,  /* whole CAMLayer: dilated k=3 conv x context gate (layers.py:93-99); CONV fields +
                                aux = w1,b1,w2,b2, iaux = hidden, seg_len, id(w1^T), id(w2^T); gate_buf = scratch for the unfused path */
     SPK_OP_SE_SCALE   = 7,  /* out = in * gate[b, c] + res   (SEBlock + block residual, ECAPA_TDNN.py:222,345)    */
+    SPK_OP_STEM_BLOCK = 9,  /* bf16 only: STEM fused with the first BasicResBlock's conv1 (3x3 stride (2,1)) and 1x1 shortcut
+                               (DTDNN.py:39-48, layers.py:221-253), the stem output is never stored.  in_buf = feats, w /
+                               epi_scale / epi_shift = stem conv + BN; out_buf = conv1 output with aux[0] = conv1 weights,
+                               aux[1], aux[2] = its BN scale / shift (ReLU); res_buf (res_ld, res_choff) = shortcut OUTPUT with
+                               aux[3] = shortcut weights, iaux[0], iaux[1] = its BN scale / shift; H = F, W = T, Ho = F / 2 */
     SPK_OP_ASP_POOL   = 8   /* softmax over positions of in (logits), weighted mean/std of res (ECAPA_TDNN.py:279-285);
                                faux[0] = variance floor */
 };

@@ -94,7 +94,11 @@ def test_bf16_per_buffer_vs_fp32_on_gpu_random_init(fam):
     for k in a:
         if k == "gate":             # scratch of the unfused CAM path: the fused bf16 kernel never writes it
             continue
-        worst[k] = float(((a[k] - b[k]).norm() / a[k].norm()).item())
+        x, y = a[k], b[k]
+        if k == "fcm_a":            # the bf16 program fuses the stem into the first block (SPK_OP_STEM_BLOCK): only the part of
+            n = x.numel() // 4      # this buffer that layer2[0] re-uses for its output ([F/4, T, 32]) is written by both runs
+            x, y = x.view(B, -1)[:, :n // B], y.view(B, -1)[:, :n // B]
+        worst[k] = float(((x - y).norm() / x.norm()).item())
     assert max(worst.values()) <= 2e-2, worst
 
 

@@ -56,6 +56,16 @@ def _check_program(model, prog, T, F=80):
         elif op.kind == _lib.OP_STEM:
             assert model.sizes[op.w] == op.Cout * 9
             extent(op.out_buf, op.out_ld, op.out_choff, op.Cout, op.H, op.W)
+        elif op.kind == _lib.OP_STEM_BLOCK:
+            # stem fused with the first block's conv1 and shortcut: two outputs at half the frequency resolution
+            assert model.precision == _lib.PREC_BF16 and op.in_buf == 0 and op.Cout == 32 and op.Ho == op.H // 2 and op.Wo == op.W
+            assert model.sizes[op.w] == 32 * 9 and model.sizes[op.aux[0]] == 32 * 9 * 32 and model.sizes[op.aux[3]] == 32 * 32
+            for pid in (op.epi_scale, op.epi_shift, op.aux[1], op.aux[2], op.iaux[0], op.iaux[1]):
+                assert model.sizes[pid] == 32
+            extent(op.out_buf, op.out_ld, op.out_choff, 32, op.Ho, op.Wo)
+            extent(op.res_buf, op.res_ld, op.res_choff, 32, op.Ho, op.Wo)
+            assert bufs[op.out_buf].dtype == _lib.DT_BF16 and bufs[op.res_buf].dtype == _lib.DT_BF16
+            written.add(op.res_buf)
         elif op.kind == _lib.OP_AFF_BLEND:
             extent(op.in_buf, op.in_ld, op.in_choff, op.Cin, op.H, op.W)
             if op.res_buf >= 0:             # res_buf < 0: plain (dtype-converting) copy
@@ -92,7 +102,10 @@ def test_campplus_program(prec, T):
     eng.compile(T)
     prog = eng.model.programs[T]
     _check_program(eng.model, prog, T)
-    assert sum(1 for o in prog.ops if o.kind == _lib.OP_CONV) == 11 + 1 + 52 + 3 + 1     # FCM (8 + 2 shortcuts + conv2), tdnn, 52 bottlenecks, 3 transit, dense
+    fused = sum(1 for o in prog.ops if o.kind == _lib.OP_STEM_BLOCK)
+    assert fused == (1 if prec == _lib.PREC_BF16 and T <= 254 else 0)        # stem + layer1[0].conv1 + shortcut in one op
+    assert sum(1 for o in prog.ops if o.kind == _lib.OP_STEM) == 1 - fused
+    assert sum(1 for o in prog.ops if o.kind == _lib.OP_CONV) == 11 - 2 * fused + 1 + 52 + 3 + 1     # FCM (8 + 2 shortcuts + conv2), tdnn, 52 bottlenecks, 3 transit, dense
     assert sum(1 for o in prog.ops if o.kind == _lib.OP_CAM_LOCAL) == 52
 
 

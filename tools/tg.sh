@@ -1,5 +1,4 @@
-CHUNK=256 python tools/bench_models.py eres eres_w24 2>&1 | tail -2
-BATCH_SCALE=2 CHUNK=512 python tools/bench_models.py eres 2>&1 | tail -1
-BATCH_SCALE=2 CHUNK=256 python tools/bench_models.py eres_w24 ecapa 2>&1 | tail -2
-BATCH_SCALE=4 CHUNK=1024 python tools/bench_models.py eres 2>&1 | tail -1
-BATCH_SCALE=4 CHUNK=512 python tools/bench_models.py eres_w24 ecapa 2>&1 | tail -2
+timeout 300 python -m pytest tests/test_gpu_campplus.py -x -q 2>&1 | tail -5
+python tools/stem_timeline.py | sed -n 1,12p
+NSEG=16384 timeout 120 python tools/sweep_chunks.py 8192/2048
+SPK_NO_STEM_FUSE=1 NSEG=16384 timeout 120 python tools/sweep_chunks.py 8192/2048

@@ -96,8 +96,8 @@ def test_bf16_per_buffer_vs_fp32_on_gpu_random_init(fam):
             continue
         x, y = a[k], b[k]
         if k == "fcm_a":            # the bf16 program fuses the stem into the first block (SPK_OP_STEM_BLOCK): only the part of
-            n = x.numel() // 4      # this buffer that layer2[0] re-uses for its output ([F/4, T, 32]) is written by both runs
-            x, y = x.view(B, -1)[:, :n // B], y.view(B, -1)[:, :n // B]
+            n = x.numel() // 4      # this buffer that layer2[0] re-uses for its output ([B, F/4, T, 32], packed) is written by both
+            x, y = x.reshape(-1)[:n], y.reshape(-1)[:n]
         worst[k] = float(((x - y).norm() / x.norm()).item())
     assert max(worst.values()) <= 2e-2, worst
 
@@ -117,7 +117,12 @@ def test_bf16_stress_weights_error_growth_is_bounded():
     with torch.no_grad():
         e32, e16 = f32(feats), b16(feats)
     a, b = _buffers(f32, 148, 16), _buffers(b16, 148, 16)
-    rel = {k: float(((a[k] - b[k]).norm() / a[k].norm()).item()) for k in a if k != "gate"}
+    def _rel_buf(k):
+        x, y = a[k].reshape(-1), b[k].reshape(-1)
+        if k == "fcm_a":            # fused stem in the bf16 program: compare the part layer2[0] re-uses for its output
+            x, y = x[:x.numel() // 4], y[:y.numel() // 4]
+        return float(((x - y).norm() / x.norm()).item())
+    rel = {k: _rel_buf(k) for k in a if k != "gate"}
     bound = {"fcm_a": 1e-2, "fcm_out": 1.2e-2, "block1": 2.5e-2, "block2": 7e-2, "block3": 1.1e-1, "final": 1.2e-1, "stats": 1.1e-1}
     for k, v in bound.items():
         assert rel[k] <= v, (k, rel[k])

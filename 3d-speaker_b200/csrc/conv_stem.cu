@@ -41,6 +41,7 @@ constexpr int kC = 32;
 constexpr int kStemWarps = 8;
 constexpr int kStemThreads = kStemWarps * 32, kEpiThreads = 128;
 constexpr int kThreads = kStemThreads + 32 + kEpiThreads + 32;      // 448
+constexpr int kStemTries = 1;                                       // polls for a pending stem step in front of every conv tile
 constexpr int kMaxLd = 7;                                           // feature loads per stem thread and item
 constexpr uint32_t kIdesc = idesc_bf16(32);
 
@@ -56,6 +57,24 @@ __device__ long long g_stem_ts[64 * 8];
 __device__ int g_stem_dbg;
 #define STEM_TS(idx, slot) do { if (dbg && (idx) < 64) g_stem_ts[(idx) * 8 + (slot)] = clock64(); } while (0)
 
+// (lo, hi) -> bf16x2 with ReLU in the conversion
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// v -> bf16(v) | bf16(v - bf16(v)) << 16: the split-bf16 form of one feature value
+__device__ __forceinline__ uint32_t split_bf16(float v) {
+    const bf16 h = __float2bfloat16_rn(v);
+    const bf16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    return (uint32_t)__bfloat16_as_ushort(h) | ((uint32_t)__bfloat16_as_ushort(l) << 16);
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 __device__ __forceinline__ void stem_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kStemThreads) : "memory"); }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -65,14 +84,16 @@ stem_block_kernel(const StemBlockArgs a, const StemGeom g, long long n_items, co
     const uint32_t s0 = smem_u32(smem);
     const uint32_t s_w1 = s0 + g.off_w1, s_ws = s0 + g.off_ws, s_ss = s0 + g.off_ss, s_slab0 = s0 + g.off_slab, s_bar = s0 + g.off_bar;
     const uint32_t s_stg = s0 + g.off_stg, s_sa = s0 + g.off_sa, s_sb = s0 + g.off_sb;
-    float *feat = reinterpret_cast<float *>(smem + g.off_feat);          // 2 x [nbins][Tp2], columns 0 and T + 1 stay zero
+    uint32_t *feat = reinterpret_cast<uint32_t *>(smem + g.off_feat);    // 2 x [nbins][Tp2] split-bf16 values (hi | lo << 16), columns 0 and T + 1 stay zero
     auto sfull = [&](uint32_t i) { return s_bar + 8u * i; };
     auto sempty = [&](uint32_t i) { return s_bar + 8u * (2 + i); };
     auto afull = [&](uint32_t i) { return s_bar + 8u * (4 + i); };
     auto aempty = [&](uint32_t i) { return s_bar + 8u * (6 + i); };
-    const uint32_t gfull = s_bar + 8u * 8, gfree = s_bar + 8u * 9;
-    const uint32_t smma = s_bar + 8u * 10, aready = s_bar + 8u * 11;      // stem GEMM: the MMAs of a step retired / its A rows are staged
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + g.off_bar + 112);
+    auto gfull = [&](uint32_t o) { return s_bar + 8u * (8 + o); };        // staging buffer of output o (0 conv, 1 shortcut) is complete
+    auto gfree = [&](uint32_t o) { return s_bar + 8u * (14 + o); };       // its TMA store has read it
+    auto smma = [&](uint32_t i) { return s_bar + 8u * (10 + i); };        // stem GEMM: the MMAs of a step have retired
+    auto aready = [&](uint32_t i) { return s_bar + 8u * (12 + i); };      //            the A rows of a step are staged
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + g.off_bar + 136);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool dbg = g_stem_dbg != 0 && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (warp == 0 || warp == kStemWarps || warp == kStemWarps + 1 || warp == kStemWarps + 5);
     int di = 0;
@@ -87,10 +108,14 @@ stem_block_kernel(const StemBlockArgs a, const StemGeom g, long long n_items, co
             mbar_init(afull(i), 1);
             mbar_init(aempty(i), kEpiThreads);
         }
-        mbar_init(gfull, kEpiThreads);
-        mbar_init(gfree, 1);
-        mbar_init(smma, 1);
-        mbar_init(aready, kStemWarps);
+        for (uint32_t o = 0; o < 2; ++o) {
+            mbar_init(gfull(o), kEpiThreads);
+            mbar_init(gfree(o), 1);
+        }
+        for (uint32_t i = 0; i < 2; ++i) {
+            mbar_init(smma(i), 1);
+            mbar_init(aready(i), kStemWarps);
+        }
         tmap_prefetch(&y1map);
         tmap_prefetch(&y2map);
         fence_barrier_init();
@@ -132,7 +157,7 @@ stem_block_kernel(const StemBlockArgs a, const StemGeom g, long long n_items, co
         }
         for (uint32_t off = (uint32_t)threadIdx.x * 16u; off < 2u * g.slab_bytes; off += kThreads * 16u)
             sts16(s_slab0 + off, make_uint4(0u, 0u, 0u, 0u));
-        for (int i = threadIdx.x; i < 2 * g.nbins * g.Tp2; i += kThreads) feat[i] = 0.f;
+        for (int i = threadIdx.x; i < 2 * g.nbins * g.Tp2; i += kThreads) feat[i] = 0u;
     }
     fence_proxy_async();
     tc_fence_before();
@@ -147,11 +172,10 @@ stem_block_kernel(const StemBlockArgs a, const StemGeom g, long long n_items, co
         const int tid = threadIdx.x;
         const int tile = tid >> 7, r = tid & 127;          // this thread's A row / TMEM lane in a 256-pixel step
         const uint32_t arow = s_sa + (uint32_t)tile * 8192u + (uint32_t)r * 64u, ax = ((uint32_t)r >> 1) & 3u;
-        const uint32_t d_stem = tmem_base + 4u * acc_cols;           // two 32-column stem accumulators behind the conv ones
-        const uint32_t t_stem = d_stem + (uint32_t)tile * 32u + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t mph = 0;
+        const uint32_t t_stem = tmem_base + 4u * acc_cols + (uint32_t)tile * 32u + ((uint32_t)((warp & 3) * 32) << 16);
         const int n_feat = g.nbins * a.T;
         const int n_px = (g.rows_e + g.rows_o) * a.T;
+        const int n_steps = (n_px + kStemThreads - 1) / kStemThreads;
         const int tile_f = g.nbins * g.Tp2;
         // this thread's feature elements: (frame, bin) -> global offset, shared-memory offset, bin (the same for every item)
         int goff[kMaxLd], soff[kMaxLd];
@@ -174,98 +198,114 @@ stem_block_kernel(const StemBlockArgs a, const StemGeom g, long long n_items, co
                 pre[u] = (goff[u] >= 0 && f >= 0 && f < a.F) ? __ldg(fe + goff[u]) : 0.f;
             }
         };
-        auto stage = [&](float *dst) {
+        auto stage = [&](uint32_t *dst) {        // every feature value is split once here, not nine times in the im2col rows
 #pragma unroll
             for (int u = 0; u < kMaxLd; ++u)
-                if (goff[u] >= 0) dst[soff[u] & 0xFFFFF] = pre[u];
+                if (goff[u] >= 0) dst[soff[u] & 0xFFFFF] = split_bf16(pre[u]);
         };
-        uint32_t buf = 0, ph = 0, fb = 0;
+        // ---- one 256-pixel step of the stem GEMM, in two halves that are software-pipelined ACROSS steps (and items):
+        // build(step n + 1) runs before finish(step n), so the MMA round trip of a step hides behind the next step's rows.
+        //   build : im2col row of this thread's pixel (split bf16) -> A buffer (gs & 1), arrive
+        //   finish: wait for the step's MMAs, read the pixel's 32 channels from TMEM, ReLU, bf16 -> slab
+        struct Step { long long item; int s; uint32_t gs; };
+        auto build = [&](const Step &st, const uint32_t *ft) {
+            const int q = st.s * kStemThreads + tid;
+            if (q < n_px) {
+                const int j = (int)__umulhi((unsigned)q, g.t_magic);         // q / T  (exact for q < 2^16)
+                const int t = q - j * a.T;
+                const uint32_t *f0 = ft + j * g.Tp2 + t, *f1 = f0 + g.Tp2, *f2 = f1 + g.Tp2;
+                const uint32_t in[9] = {f0[0], f0[1], f0[2], f1[0], f1[1], f1[2], f2[0], f2[1], f2[2]};     // hi | lo << 16
+                // row = [hi0..8 | lo0..8 | hi0..8 | 1 | 1 | 0 0 0] as sixteen bf16 pairs, assembled with byte permutes
+                constexpr uint32_t LL = 0x5410, HH = 0x7632, LH = 0x7610;       // (a.lo, b.lo), (a.hi, b.hi), (a.lo, b.hi)
+                constexpr uint32_t one = 0x3F80;
+                const uint32_t h01 = prmt(in[0], in[1], LL), h23 = prmt(in[2], in[3], LL), h45 = prmt(in[4], in[5], LL), h67 = prmt(in[6], in[7], LL);
+                const uint32_t ar = arow + (st.gs & 1u) * 16384u;
+                sts16(ar + ((0u ^ ax) << 4), make_uint4(h01, h23, h45, h67));
+                sts16(ar + ((1u ^ ax) << 4), make_uint4(prmt(in[8], in[0], LH), prmt(in[1], in[2], HH), prmt(in[3], in[4], HH), prmt(in[5], in[6], HH)));
+                sts16(ar + ((2u ^ ax) << 4), make_uint4(prmt(in[7], in[8], HH), h01, h23, h45));
+                sts16(ar + ((3u ^ ax) << 4), make_uint4(h67, (in[8] & 0xFFFFu) | (one << 16), one, 0u));
+            }
+            tc_fence_before();              // this thread's TMEM reads of step gs - 2 (same accumulator) are done
+            fence_proxy_async();            // A rows (generic proxy) -> tcgen05.mma (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(aready(st.gs & 1u));      // the MMA warp issues the step's four MMAs between conv tiles
+        };
+        uint32_t buf = 0, ph = 0;           // slab buffer / phase of the item being FINISHED
+        auto finish = [&](const Step &st) {
+            const int band = (int)(st.item % g.n_bands);
+            const int xr0 = 2 * band * g.R - 1;              // stem row of slab row j = 0
+            if (st.s == 0) {
+                STEM_TS(di, 0);
+                mbar_wait(sempty(buf), ph ^ 1u);
+                STEM_TS(di, 1);
+            }
+            const uint32_t sb = s_slab0 + buf * g.slab_bytes;
+            mbar_wait(smma(st.gs & 1u), (st.gs >> 1) & 1u);
+            tc_fence_after();
+            uint32_t v[32];
+            {
+                uint32_t (&v0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[0]);
+                uint32_t (&v1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[16]);
+                const uint32_t ta = t_stem + (st.gs & 1u) * 64u;
+                tmem_ld16(ta, v0);
+                tmem_ld16(ta + 16, v1);
+                tmem_ld_wait();
+            }
+            const int q = st.s * kStemThreads + tid;
+            if (q < n_px) {
+                const int j = (int)__umulhi((unsigned)q, g.t_magic);
+                const int t = q - j * a.T;
+                const int xr = xr0 + j;
+                const uint32_t p = (uint32_t)((j >> 1) * g.Wp + t + 1);
+                const uint32_t prow = sb + ((j & 1) ? sub_o : 0u) + p * 64u, x = (p >> 1) & 3u;
+                const bool valid = xr >= 0 && xr < a.F;          // else: conv zero padding above / below the image
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (valid) {
+                        auto f = [&](int i) { return __uint_as_float(v[e * 8 + i]); };
+                        o = make_uint4(pack2_relu(f(0), f(1)), pack2_relu(f(2), f(3)), pack2_relu(f(4), f(5)), pack2_relu(f(6), f(7)));
+                    }
+                    sts16(prow + (((uint32_t)e ^ x) << 4), o);
+                }
+            }
+            if (st.s == n_steps - 1) {
+                fence_proxy_async();            // slab writes (generic proxy) -> tcgen05.mma reads (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sfull(buf));
+                STEM_TS(di, 2);
+                ++di;
+                if (++buf == 2u) { buf = 0; ph ^= 1u; }
+            }
+        };
         const long long step = gridDim.x;
+        uint32_t fb = 0, gs = 0;
+        Step prev{0, 0, 0};
+        bool have_prev = false;
         if ((long long)blockIdx.x < n_items) {
             prefetch(blockIdx.x);
             stage(feat);
             if (blockIdx.x + step < n_items) prefetch(blockIdx.x + step);
         }
-        stem_bar_sync();
         for (long long item = blockIdx.x; item < n_items; item += step) {
-            const int band = (int)(item % g.n_bands);
-            const int xr0 = 2 * band * g.R - 1;              // stem row of slab row j = 0
-            const float *ft = feat + fb * tile_f;
-            STEM_TS(di, 0);
-            mbar_wait(sempty(buf), ph ^ 1u);
-            STEM_TS(di, 1);
-            const uint32_t sb = s_slab0 + buf * g.slab_bytes;
-            const uint32_t hi64 = desc_hi(512u, kLayoutSw64);
-            for (int q0 = 0; q0 < n_px; q0 += kStemThreads) {
-                const int q = q0 + tid;
-                const bool inb = q < n_px;
-                const int j = (int)__umulhi((unsigned)q, g.t_magic);         // q / T  (exact for q < 2^16)
-                const int t = q - j * a.T;
-                const int xr = xr0 + j;
-                if (inb) {
-                    // im2col row of this pixel, split bf16: hi = bf16(x), lo = bf16(x - hi)
-                    const float *f0 = ft + j * g.Tp2 + t, *f1 = f0 + g.Tp2, *f2 = f1 + g.Tp2;
-                    const float in[9] = {f0[0], f0[1], f0[2], f1[0], f1[1], f1[2], f2[0], f2[1], f2[2]};
-                    uint16_t h[9], l[9];
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) {
-                        const bf16 bh = __float2bfloat16_rn(in[k]);
-                        const bf16 bl = __float2bfloat16_rn(in[k] - __bfloat162float(bh));
-                        h[k] = __bfloat16_as_ushort(bh);
-                        l[k] = __bfloat16_as_ushort(bl);
-                    }
-                    auto pk = [](uint16_t lo16, uint16_t hi16) { return (uint32_t)lo16 | ((uint32_t)hi16 << 16); };
-                    constexpr uint16_t one = 0x3F80;
-                    sts16(arow + ((0u ^ ax) << 4), make_uint4(pk(h[0], h[1]), pk(h[2], h[3]), pk(h[4], h[5]), pk(h[6], h[7])));
-                    sts16(arow + ((1u ^ ax) << 4), make_uint4(pk(h[8], l[0]), pk(l[1], l[2]), pk(l[3], l[4]), pk(l[5], l[6])));
-                    sts16(arow + ((2u ^ ax) << 4), make_uint4(pk(l[7], l[8]), pk(h[0], h[1]), pk(h[2], h[3]), pk(h[4], h[5])));
-                    sts16(arow + ((3u ^ ax) << 4), make_uint4(pk(h[6], h[7]), pk(h[8], one), pk(one, 0), 0u));
-                }
-                tc_fence_before();              // this thread's TMEM reads of the previous step are done
-                fence_proxy_async();            // A rows (generic proxy) -> tcgen05.mma (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(aready);          // the MMA warp issues the step's four MMAs between conv tiles
-                mbar_wait(smma, mph);
-                mph ^= 1u;
-                tc_fence_after();
-                uint32_t v[32];
-                {
-                    uint32_t (&v0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[0]);
-                    uint32_t (&v1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&v[16]);
-                    tmem_ld16(t_stem, v0);
-                    tmem_ld16(t_stem + 16, v1);
-                    tmem_ld_wait();
-                }
-                if (inb) {
-                    const uint32_t p = (uint32_t)((j >> 1) * g.Wp + t + 1);
-                    const uint32_t prow = sb + ((j & 1) ? sub_o : 0u) + p * 64u, x = (p >> 1) & 3u;
-                    const bool valid = xr >= 0 && xr < a.F;          // else: conv zero padding above / below the image
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                        if (valid) {
-                            auto rl = [&](int i) { return fmaxf(__uint_as_float(v[e * 8 + i]), 0.f); };
-                            o = make_uint4(pack2(rl(0), rl(1)), pack2(rl(2), rl(3)), pack2(rl(4), rl(5)), pack2(rl(6), rl(7)));
-                        }
-                        sts16(prow + (((uint32_t)e ^ x) << 4), o);
-                    }
-                }
-            }
-            fence_proxy_async();            // slab writes (generic proxy) -> tcgen05.mma reads (async proxy)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sfull(buf));
-            STEM_TS(di, 2);
-            ++di;
-            // the next item's tile (in registers since the previous iteration) -> the other feature buffer, whose last
-            // readers passed the barrier at the end of the previous iteration; then the loads of the item after that
+            // entering an item: its tile was staged one item ago; after the barrier nobody reads the other tile any more,
+            // so the next item's tile (in registers) goes there and the loads of the item after that are issued
+            stem_bar_sync();
+            const uint32_t *ft = feat + fb * tile_f;
             if (item + step < n_items) {
                 stage(feat + (fb ^ 1u) * tile_f);
                 if (item + 2 * step < n_items) prefetch(item + 2 * step);
             }
-            stem_bar_sync();
+            for (int sidx = 0; sidx < n_steps; ++sidx, ++gs) {
+                const Step cur{item, sidx, gs};
+                build(cur, ft);
+                if (have_prev) finish(prev);
+                prev = cur;
+                have_prev = true;
+            }
             fb ^= 1u;
-            if (++buf == 2u) { buf = 0; ph ^= 1u; }
         }
+        if (have_prev) finish(prev);
     } else if (warp == kStemWarps) {
         // =========================== MMA issuer ===========================
         const uint32_t hi = desc_hi(512u, kLayoutSw64);         // 8-pixel groups are 512 B apart
@@ -273,21 +313,23 @@ stem_block_kernel(const StemBlockArgs a, const StemGeom g, long long n_items, co
         const uint32_t d_stem = tmem_base + 4u * acc_cols;
         // The stem GEMM shares the tensor pipe with the conv: its four MMAs per 256-pixel step are issued HERE, between
         // the conv tiles and while waiting, so that a step never queues behind a whole item of conv MMAs (2,900 cycles).
-        uint32_t aph = 0;
+        uint32_t sgs = 0;                    // stem steps served so far
         auto service = [&]() -> bool {
-            const bool ready = __shfl_sync(0xffffffffu, mbar_try_wait(aready, aph) ? 1 : 0, 0) != 0;
+            const uint32_t ab = sgs & 1u;
+            const bool ready = __shfl_sync(0xffffffffu, mbar_try_wait(aready(ab), (sgs >> 1) & 1u) ? 1 : 0, 0) != 0;
             if (!ready) return false;
-            aph ^= 1u;
+            ++sgs;
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t lo_b = desc_lo(s_sb, 16u);
 #pragma unroll
                 for (uint32_t tl = 0; tl < 2; ++tl) {
-                    const uint32_t lo_a = desc_lo(s_sa + tl * 8192u, 16u);
-                    umma_bf16(d_stem + tl * 32u, desc64(lo_a, hi), desc64(lo_b, hi), kIdesc, 0u);
-                    umma_bf16_acc(d_stem + tl * 32u, desc64(lo_a + 2u, hi), desc64(lo_b + 2u, hi), kIdesc);
+                    const uint32_t lo_a = desc_lo(s_sa + ab * 16384u + tl * 8192u, 16u);
+                    const uint32_t dd = d_stem + ab * 64u + tl * 32u;
+                    umma_bf16(dd, desc64(lo_a, hi), desc64(lo_b, hi), kIdesc, 0u);
+                    umma_bf16_acc(dd, desc64(lo_a + 2u, hi), desc64(lo_b + 2u, hi), kIdesc);
                 }
-                umma_commit(smma);
+                umma_commit(smma(ab));
             }
             __syncwarp();
             return true;
@@ -313,7 +355,7 @@ stem_block_kernel(const StemBlockArgs a, const StemGeom g, long long n_items, co
             for (int t = 0; t < g.n_tiles; ++t, d += 32u, tile += 512u) {
                 // one stem step (of the item the stem warps are building) in front of every conv tile: the step's CUDA-core
                 // half then runs under the tile's 800 tensor cycles.  Bounded wait: there is no step left at the tail.
-                for (int tries = 0; tries < 6 && !service(); ++tries) {}
+                for (int tries = 0; tries < kStemTries && !service(); ++tries) {}
                 if (elect_one()) {
 #pragma unroll
                     for (int kh = 0; kh < 3; ++kh)
@@ -342,51 +384,63 @@ stem_block_kernel(const StemBlockArgs a, const StemGeom g, long long n_items, co
     } else if (warp < kStemWarps + 5) {
         // =========================== epilogue ===========================
         const int q = warp & 3;
+        const uint32_t band_px = (uint32_t)(g.R * g.Wp);                 // the staging buffers hold exactly the band
         uint32_t it = 0;
         for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t buf = it & 1u, ph = (it >> 1) & 1u;
-            mbar_wait(gfree, (it & 1u) ^ 1u);            // the stores of the previous item have read the staging buffers
             mbar_wait(afull(buf), ph);
             tc_fence_after();
             STEM_TS(di, 5);
-            for (int t = 0; t < g.n_tiles; ++t) {
-                const uint32_t p = (uint32_t)(t * 128 + q * 32 + lane);               // slab pixel == staging pixel
-                const uint32_t x = (p >> 1) & 3u;
+            // output by output (0: conv, BN + ReLU; 1: shortcut, BN), so that the store of the conv band runs under the
+            // shortcut's epilogue and the next item only has to wait for the store that is one full output pass old
 #pragma unroll
-                for (int o = 0; o < 2; ++o) {                                         // 0: conv (BN + ReLU), 1: shortcut (BN)
-                    const uint32_t taddr = tmem_base + buf * 2u * acc_cols + (uint32_t)o * acc_cols + (uint32_t)t * 32u + ((uint32_t)(q * 32) << 16);
-                    uint32_t r[32];
-                    {
-                        uint32_t (&r0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[0]);
-                        uint32_t (&r1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[16]);
-                        tmem_ld16(taddr, r0);
-                        tmem_ld16(taddr + 16, r1);
-                        tmem_ld_wait();
+            for (uint32_t o = 0; o < 2; ++o) {
+                mbar_wait(gfree(o), (it & 1u) ^ 1u);          // the previous item's store of this output has read the buffer
+                const uint32_t tbase = tmem_base + buf * 2u * acc_cols + o * acc_cols + ((uint32_t)(q * 32) << 16);
+                const uint32_t sbase = s_stg + o * g.stg_bytes;
+                for (int t0 = 0; t0 < g.n_tiles; t0 += 2) {       // two tiles per TMEM round trip
+                    const bool two = t0 + 1 < g.n_tiles;
+                    uint32_t r[2][32];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (u == 0 || two) {
+                            uint32_t (&r0)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[u][0]);
+                            uint32_t (&r1)[16] = *reinterpret_cast<uint32_t (*)[16]>(&r[u][16]);
+                            tmem_ld16(tbase + (uint32_t)(t0 + u) * 32u, r0);
+                            tmem_ld16(tbase + (uint32_t)(t0 + u) * 32u + 16, r1);
+                        }
                     }
-                    const uint32_t prow = s_stg + (uint32_t)o * g.stg_bytes + p * 64u;
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        float v[8];
+                    for (int u = 0; u < 2; ++u) {
+                        if (u == 1 && !two) break;
+                        const uint32_t p = (uint32_t)((t0 + u) * 128 + q * 32 + lane);        // slab pixel == staging pixel
+                        if (p >= band_px) continue;                                            // tile overhang
+                        const uint32_t x = (p >> 1) & 3u, prow = sbase + p * 64u;
 #pragma unroll
-                        for (int h = 0; h < 8; h += 4) {
-                            const uint4 s4 = lds16(s_ss + (uint32_t)(o * 256 + (e * 8 + h) * 4)), h4 = lds16(s_ss + (uint32_t)(o * 256 + 128 + (e * 8 + h) * 4));
-                            v[h] = fmaf(__uint_as_float(r[e * 8 + h]), __uint_as_float(s4.x), __uint_as_float(h4.x));
-                            v[h + 1] = fmaf(__uint_as_float(r[e * 8 + h + 1]), __uint_as_float(s4.y), __uint_as_float(h4.y));
-                            v[h + 2] = fmaf(__uint_as_float(r[e * 8 + h + 2]), __uint_as_float(s4.z), __uint_as_float(h4.z));
-                            v[h + 3] = fmaf(__uint_as_float(r[e * 8 + h + 3]), __uint_as_float(s4.w), __uint_as_float(h4.w));
+                        for (int e = 0; e < 4; ++e) {
+                            float v[8];
+#pragma unroll
+                            for (int h = 0; h < 8; h += 4) {
+                                const uint4 s4 = lds16(s_ss + (uint32_t)(o * 256 + (e * 8 + h) * 4)), h4 = lds16(s_ss + (uint32_t)(o * 256 + 128 + (e * 8 + h) * 4));
+                                v[h] = fmaf(__uint_as_float(r[u][e * 8 + h]), __uint_as_float(s4.x), __uint_as_float(h4.x));
+                                v[h + 1] = fmaf(__uint_as_float(r[u][e * 8 + h + 1]), __uint_as_float(s4.y), __uint_as_float(h4.y));
+                                v[h + 2] = fmaf(__uint_as_float(r[u][e * 8 + h + 2]), __uint_as_float(s4.z), __uint_as_float(h4.z));
+                                v[h + 3] = fmaf(__uint_as_float(r[u][e * 8 + h + 3]), __uint_as_float(s4.w), __uint_as_float(h4.w));
+                            }
+                            const uint4 out = o == 0 ? make_uint4(pack2_relu(v[0], v[1]), pack2_relu(v[2], v[3]), pack2_relu(v[4], v[5]), pack2_relu(v[6], v[7]))
+                                                     : make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+                            sts16(prow + (((uint32_t)e ^ x) << 4), out);
                         }
-                        if (o == 0) {
-#pragma unroll
-                            for (int h = 0; h < 8; ++h) v[h] = fmaxf(v[h], 0.f);
-                        }
-                        sts16(prow + (((uint32_t)e ^ x) << 4), make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7])));
                     }
                 }
+                if (o == 1) {
+                    tc_fence_before();
+                    mbar_arrive(aempty(buf));       // both accumulators of the buffer have been read
+                }
+                fence_proxy_async();            // staging writes (generic proxy) -> TMA store (async proxy)
+                mbar_arrive(gfull(o));
             }
-            tc_fence_before();
-            mbar_arrive(aempty(buf));
-            fence_proxy_async();            // staging writes (generic proxy) -> TMA store (async proxy)
-            mbar_arrive(gfull);
             STEM_TS(di, 6);
             ++di;
         }
@@ -397,12 +451,17 @@ stem_block_kernel(const StemBlockArgs a, const StemGeom g, long long n_items, co
             for (long long item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int b = (int)(item / g.n_bands);
                 const int band = (int)(item - (long long)b * g.n_bands);
-                mbar_wait(gfull, it & 1u);
+                // the conv band leaves while the epilogue works on the shortcut band
+                mbar_wait(gfull(0), it & 1u);
                 tmap_store_4d(&y1map, a.y1_choff, 0, band * g.R, b, s_stg);
+                bulk_commit();
+                mbar_wait(gfull(1), it & 1u);
                 tmap_store_4d(&y2map, a.y2_choff, 0, band * g.R, b, s_stg + g.stg_bytes);
                 bulk_commit();
-                bulk_wait_read0();          // both boxes have been read out of shared memory
-                mbar_arrive(gfree);
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");      // the first box has been read out
+                mbar_arrive(gfree(0));
+                bulk_wait_read0();
+                mbar_arrive(gfree(1));
                 STEM_TS(di, 7);
                 ++di;
             }
@@ -425,7 +484,7 @@ bool geometry(const StemBlockArgs &a, StemGeom &g) {
         g.px_e = (std::max(g.rows_e * g.Wp, g.n_tiles * 128 + g.Wp + 2) + 7) & ~7;
         g.px_o = (std::max(g.rows_o * g.Wp, g.n_tiles * 128 + 2) + 7) & ~7;
         g.slab_bytes = (64u * (uint32_t)(g.px_e + g.px_o) + 1023u) & ~1023u;
-        g.stg_bytes = (uint32_t)g.n_tiles * 128u * 64u;
+        g.stg_bytes = ((uint32_t)(R * g.Wp) * 64u + 1023u) & ~1023u;       // exactly the band (the epilogue masks the tile overhang)
         g.nbins = 2 * R + 3;
         g.Tp2 = a.T + 2;
         g.off_w1 = 0;
@@ -434,11 +493,11 @@ bool geometry(const StemBlockArgs &a, StemGeom &g) {
         g.off_ss = 11 * 2048;
         g.off_feat = g.off_ss + 512;
         g.off_sa = (g.off_feat + 2u * (uint32_t)(g.nbins * g.Tp2 * 4) + 1023u) & ~1023u;
-        g.off_stg = g.off_sa + 2u * 8192u;
+        g.off_stg = g.off_sa + 4u * 8192u;              // two A buffers of two 128-pixel tiles
         g.off_slab = g.off_stg + 2u * g.stg_bytes;
         g.off_bar = g.off_slab + 2u * g.slab_bytes;
-        g.smem_bytes = (int)g.off_bar + 128;
-        const int cols = g.n_tiles * 32 * 4 + 64;       // two accumulator sets, two buffers; two stem accumulators
+        g.smem_bytes = (int)g.off_bar + 176;
+        const int cols = g.n_tiles * 32 * 4 + 128;      // two accumulator sets, two buffers; 2 x 2 stem accumulators
         g.tmem_cols = cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
         if (cols <= 512 && g.smem_bytes <= 227 * 1024 && g.nbins * a.T <= kMaxLd * kStemThreads) {
             g.n_bands = (a.Ho + R - 1) / R;

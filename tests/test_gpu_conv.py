@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
+import torch.nn.functional as F_
 
 from b200spk import _lib
 from b200spk.program import Model, Program, conv_out
@@ -242,6 +243,46 @@ def test_reflect_padded_conv1d_im2col_plus_edge_fix(Cin, Cout, K, dil, T):
     ref = _bf16_round((torch.relu(ref) * ps.double() + pb.double()).float()).double()
     err = (y - ref).abs()
     assert bool((err <= 1e-4 * ref.abs().max() + 2.0 ** -7 * ref.abs()).all()), (err.max().item(), err.argmax().item())
+
+
+@pytest.mark.parametrize("T,F,B", [(148, 80, 5), (61, 80, 3), (254, 80, 2), (148, 24, 4)])
+def test_stem_block_fused_op(T, F, B):
+    """SPK_OP_STEM_BLOCK (conv_stem.cu): stem conv + BN + ReLU (never stored) -> 3x3 stride (2,1) conv + BN + ReLU and the
+    1x1 stride (2,1) shortcut + BN, vs torch in float64 with the kernel's roundings (stem and outputs stored as bf16,
+    bf16 conv weights).  The stem itself runs as a split-bf16 tensor-core GEMM: fp32-accurate, so a stem value may land on
+    the other side of a bf16 rounding boundary - hence rel-L2 and a few-ulp bound instead of an exact match."""
+    g = torch.Generator().manual_seed(11)
+    C = 32
+    feats = 3.0 * torch.randn(B, T, F, generator=g)
+    w0 = torch.randn(C, 3, 3, generator=g) / 3.0
+    w1 = torch.randn(C, 3, 3, C, generator=g) / math.sqrt(9 * C)
+    ws = torch.randn(C, 1, 1, C, generator=g) / math.sqrt(C)
+    bn = [(torch.rand(C, generator=g) + 0.5, 0.2 * torch.randn(C, generator=g)) for _ in range(3)]
+    model = Model(_lib.PREC_BF16, "cuda:0")
+    Ho = F // 2
+    prog = Program(T * F, Ho * T * 2 * C)
+    y1 = prog.buf("y1", Ho * T * C, _lib.DT_BF16)
+    y2 = prog.buf("y2", Ho * T * C, _lib.DT_BF16)
+    prog.op(_lib.OP_STEM_BLOCK, in_buf=0, out_buf=y1, out_ld=C, res_buf=y2, res_ld=C, H=F, W=T, Ho=Ho, Wo=T, Cin=1, Cout=C,
+            w=model.param(w0.reshape(-1)), epi_scale=model.param(bn[0][0]), epi_shift=model.param(bn[0][1]), act=_lib.ACT_RELU,
+            aux=[model.param(w1), model.param(bn[1][0]), model.param(bn[1][1]), model.param(ws)], iaux=[model.param(bn[2][0]), model.param(bn[2][1])])
+    eye = model.param(torch.eye(C).reshape(C, 1, 1, C))
+    for i, src in enumerate((y1, y2)):     # widen both outputs into the two halves of the f32 output pixel
+        prog.op(_lib.OP_CONV, in_buf=src, in_ld=C, out_buf=1, out_ld=2 * C, out_choff=i * C, H=Ho, W=T, Cin=C, Ho=Ho, Wo=T, Cout=C, w=eye)
+    model.set_program(1, prog)
+    out = model.forward(1, feats.reshape(B, -1).cuda().contiguous(), Ho * T * 2 * C, B).cpu().view(B, Ho, T, 2 * C).double()
+    model.close()
+    img = feats.permute(0, 2, 1).unsqueeze(1).double()                                        # [B, 1, F, T]
+    stem = F_.conv2d(img, w0.unsqueeze(1).double(), padding=1)
+    stem = _bf16_round(torch.relu(stem * bn[0][0].view(1, C, 1, 1) + bn[0][1].view(1, C, 1, 1)).float()).double()
+    r1 = F_.conv2d(stem, _bf16_round(w1).permute(0, 3, 1, 2).double(), stride=(2, 1), padding=1)
+    r1 = _bf16_round(torch.relu(r1 * bn[1][0].view(1, C, 1, 1) + bn[1][1].view(1, C, 1, 1)).float()).double().permute(0, 2, 3, 1)
+    r2 = F_.conv2d(stem, _bf16_round(ws).permute(0, 3, 1, 2).double(), stride=(2, 1))
+    r2 = _bf16_round((r2 * bn[2][0].view(1, C, 1, 1) + bn[2][1].view(1, C, 1, 1)).float()).double().permute(0, 2, 3, 1)
+    for name, got, ref in (("conv1", out[..., :C], r1), ("shortcut", out[..., C:], r2)):
+        rel = float((got - ref).norm() / ref.norm())
+        assert rel <= 3e-3, (name, rel)
+        assert float((got - ref).abs().max()) <= 2.0 ** -6 * float(ref.abs().max()), (name, float((got - ref).abs().max()))
 
 
 def test_slab4_channel_windows_are_clipped():

@@ -18,6 +18,7 @@ ncu --set full --clock-control none --import-source on -k regex:fbank_kernel -s 
 ncu --set full --clock-control none --import-source on -k regex:conv_gemm_kernel -s 60 -c 1 -f -o gpurun_out/r02_prof_gemm $FWD > gpurun_out/r02_ncu5.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:conv_slab3_kernel -s 14 -c 1 -f -o gpurun_out/r02_prof_slab3 $FWD > gpurun_out/r02_ncu6.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:cam_local_kernel -s 60 -c 1 -f -o gpurun_out/r02_prof_cam $FWD > gpurun_out/r02_ncu7.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:stem_block_kernel -s 4 -c 1 -f -o gpurun_out/r02_prof_stem $FWD > gpurun_out/r02_ncu10.log 2>&1
 # (4) ERes2NetV2 (3 s segments): launch list with DRAM bytes, full captures of the column-part slab kernel and of an im2col GEMM
 ER="python tools/run_forward.py --model eres --segments 163 --seconds 3.0 --iters 1"
 $ER > gpurun_out/r02_eres_plain.log 2>&1 && \

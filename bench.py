@@ -562,7 +562,7 @@ def leg_meeting(cx):
         wav, turns, wav_np = torch.empty(n, dtype=torch.int16).pin_memory(), None, None
     if cx.dist is not None:
         tmp = wav.to(cx.dev)
-        cx.dist.broadcast(tmp, src=0)
+        cx.dist.broadcast(tmp.view(torch.uint8), src=0)     # NCCL has no int16: ship the PCM as bytes
         wav.copy_(tmp)
         del tmp
     torch.manual_seed(1)                                   # default init, BN not randomised

@@ -11,7 +11,7 @@ import torch
 import b200spk
 from oracle import gen_golden, synth
 
-which = sys.argv[1:] or ["fbank", "campplus", "eres", "cluster"]
+which = sys.argv[1:] or ["fbank", "campplus", "eres", "ecapa", "cluster"]
 if "fbank" in which:
     x = torch.from_numpy(synth.white_noise(700, 24000, seed=1)).cuda()
     a = b200spk.fbank_batch(x, 80, True)                 # fused CMN path
@@ -38,6 +38,14 @@ if "eres" in which:
         e = m(feats)
     assert torch.isfinite(e).all()
     print("eres ok")
+if "ecapa" in which:
+    torch.manual_seed(8)
+    feats = torch.randn(3, 298, 80, device="cuda")
+    m = b200spk.ECAPA_TDNN(80, channels=[512, 512, 512, 512, 1536], precision="bf16").cuda().eval()
+    with torch.no_grad():
+        e = m(feats)
+    assert torch.isfinite(e).all()
+    print("ecapa ok")
 if "cluster" in which:
     X, _ = gen_golden.cluster_input(300, 64, 3, 22)
     np.random.seed(0)

@@ -8,6 +8,7 @@ from b200spk.program import Model, Program
 def main():
     B, W, K, N, reps = int(os.environ.get("B", "2048")), int(os.environ.get("W", "74")), int(os.environ.get("K", "512")), int(os.environ.get("N", "128")), int(os.environ.get("REPS", "8"))
     PRO, RES = int(os.environ.get("PRO", "1")), int(os.environ.get("RES", "0"))
+    LD = int(os.environ.get("LD", "0")) or K          # pixel pitch of the input buffer (>= K: a channel window of a wider buffer)
     g = torch.Generator().manual_seed(1)
     w = torch.randn(N, 1, 1, K, generator=g) / math.sqrt(K)
     ps, pb = torch.rand(K, generator=g) + 0.5, 0.1 * torch.randn(K, generator=g)
@@ -15,15 +16,15 @@ def main():
     res = {}
     for tag, k in (("base", 1), ("gemm", reps)):
         prog = Program(W * 32, W * N)
-        xin = prog.buf("x", W * K, _lib.DT_BF16)
+        xin = prog.buf("x", W * LD, _lib.DT_BF16)
         ybuf = prog.buf("y", W * N, _lib.DT_BF16)
         rbuf = prog.buf("r", W * N, _lib.DT_BF16)
         # widen the 32-channel input into a K-channel buffer (values do not matter for timing)
         wide = torch.zeros(K, 1, 1, 32)
         wide[torch.arange(K), 0, 0, torch.arange(K) % 32] = 1.0
-        prog.op(_lib.OP_CONV, in_buf=0, in_ld=32, out_buf=xin, out_ld=K, H=1, W=W, Cin=32, Ho=1, Wo=W, Cout=K, w=model.param(wide))
+        prog.op(_lib.OP_CONV, in_buf=0, in_ld=32, out_buf=xin, out_ld=LD, H=1, W=W, Cin=32, Ho=1, Wo=W, Cout=K, w=model.param(wide))
         for _ in range(k):
-            prog.op(_lib.OP_CONV, in_buf=xin, in_ld=K, out_buf=ybuf, out_ld=N, H=1, W=W, Cin=K, Ho=1, Wo=W, Cout=N,
+            prog.op(_lib.OP_CONV, in_buf=xin, in_ld=LD, out_buf=ybuf, out_ld=N, H=1, W=W, Cin=K, Ho=1, Wo=W, Cout=N,
                     w=model.param(w), act=_lib.ACT_RELU, **(dict(pro_scale=model.param(ps), pro_shift=model.param(pb), pro_relu=1) if PRO else {}),
                     **(dict(res_buf=rbuf, res_ld=N) if RES else {}))
         prog.op(_lib.OP_CONV, in_buf=ybuf, in_ld=N, out_buf=1, out_ld=N, H=1, W=W, Cin=N, Ho=1, Wo=W, Cout=N,

@@ -406,6 +406,8 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
         TOut *y = static_cast<TOut *>(a.y);
         const TRes *res = static_cast<const TRes *>(a.res);
         const bool wide_st = sizeof(TOut) == 2 && (reinterpret_cast<uintptr_t>(a.y) & 31) == 0 && a.out_ld % 16 == 0 && a.out_choff % 16 == 0;
+        const bool wide_f32 = sizeof(TOut) == 4 && (reinterpret_cast<uintptr_t>(a.y) & 31) == 0 && a.out_ld % 8 == 0 && a.out_choff % 8 == 0;
+        (void)wide_f32;
         const int grp = warp >= 10 ? 1 : 0;
         uint32_t it = 0, uses0 = 0, uses1 = 0;       // uses of staging buffer 0 / 1 so far (N = 256: by either group)
         (void)uses0; (void)uses1;
@@ -632,6 +634,11 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                                 *reinterpret_cast<uint4 *>(yq) = lo;
                                 *reinterpret_cast<uint4 *>(yq + 8) = hi;
                             }
+                        } else if (wide_f32) {      // full 32-byte sectors per lane (two per 16 columns) instead of four 16-byte stores
+#pragma unroll
+                            for (int e = 0; e < 16; e += 8)
+                                stg32(yq + e, make_uint4(__float_as_uint(vv[e]), __float_as_uint(vv[e + 1]), __float_as_uint(vv[e + 2]), __float_as_uint(vv[e + 3])),
+                                      make_uint4(__float_as_uint(vv[e + 4]), __float_as_uint(vv[e + 5]), __float_as_uint(vv[e + 6]), __float_as_uint(vv[e + 7])));
                         } else {
 #pragma unroll
                             for (int e = 0; e < 16; e += 4)

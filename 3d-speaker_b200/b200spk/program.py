@@ -102,6 +102,7 @@ class Model:
         if B <= self.graph_max_batch and not torch.cuda.is_current_stream_capturing():
             return self._forward_graph(T, feats, emb_dim, chunk, fine)
         ws = self.workspace(T, chunk, fine)
+        self._last_ws = ws
         self._launch(T, feats, emb, ws, chunk, fine)
         return emb
 
@@ -134,6 +135,7 @@ class Model:
         else:
             self._graphs.move_to_end(key)
         graph, sfeats, semb, ws, n_launch = ent
+        self._last_ws = ws              # read_buffer looks at the workspace the last forward really used
         sfeats.copy_(feats)
         graph.replay()
         _lib.lib().spk_add_launches(n_launch)       # the replay ran them; keep the library's launch counter truthful
@@ -147,7 +149,7 @@ class Model:
         bid = prog.names[name]
         n = prog.bufs[bid].elems * n_segments
         out = torch.empty(n, dtype=torch.float32, device=self.device)
-        ws = self.workspace(T, chunk, fine)
+        ws = self._last_ws
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().spk_model_read_buffer(self.handle, int(T), bid, chunk, fine, C.c_void_p(ws.data_ptr()),
                                                         C.c_void_p(out.data_ptr()), n, _lib.current_stream_ptr()))

@@ -132,6 +132,42 @@ def test_extractor_host_buffers_roundtrip():
     assert b.data_ptr() == a.data_ptr() and torch.equal(b, got)
 
 
+def test_graph_replay_is_bit_identical_to_eager_launches():
+    """Forwards of up to 128 segments are captured into a CUDA graph per shape and replayed (program.py): the replay,
+    a second shape, a return to the first shape and an eager run of the same batches must agree bit for bit, the
+    launch counter must keep counting replayed kernels, and read_buffer must see the replay's workspace."""
+    model = b200spk.CAMPPlus(embedding_size=192, precision="bf16").cuda().eval()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    fa, fb = torch.randn(16, 148, 80, device="cuda", generator=g), torch.randn(5, 148, 80, device="cuda", generator=g)
+    with torch.no_grad():
+        a1 = model(fa).clone()                         # eager warm-up + capture
+        n0 = b200spk.lib().spk_launch_count()
+        a2 = model(fa).clone()                         # replay
+        n1 = b200spk.lib().spk_launch_count()
+        b1 = model(fb).clone()                         # another shape: its own graph
+        a3 = model(fa + 0).clone()                     # back to the first shape, new input tensor
+        blk = model._engine.model.read_buffer(148, "block3", 16).clone()
+        eng = model._engine.model
+        assert len(eng._graphs) == 2 and n1 - n0 == len(eng.programs[148].ops)
+        eng.graph_max_batch = 0                        # eager launches from here on
+        e_a = model(fa)
+        blk_e = eng.read_buffer(148, "block3", 16).clone()
+        e_b = model(fb)
+    assert torch.equal(a1, a2) and torch.equal(a1, a3) and torch.equal(a1, e_a) and torch.equal(b1, e_b)
+    assert torch.equal(blk, blk_e)
+
+
+def test_extractor_batches_ramp_up_and_change_nothing():
+    """The extractor's schedule (head, then 4x larger batches up to batchsize) only changes how the work is cut."""
+    name, emb, batch, n_samples, wseed, bnrand = gen_golden.campplus_cases()[0]
+    model, sd = _model(emb, wseed, bnrand, precision="bf16")
+    wavs = torch.from_numpy(gen_golden.campplus_input(41, n_samples, seed=8)).pin_memory()
+    fb = b200spk.FBank(80, 16000, mean_nor=True)
+    ref = b200spk.EmbeddingExtractor(fb, model, batchsize=64, head=0)(wavs)          # one batch
+    got = b200spk.EmbeddingExtractor(fb, model, batchsize=32, head=2)(wavs)          # 2, 8, 31 windows
+    assert torch.equal(ref, got)
+
+
 def test_bf16_forward_takes_the_fused_kernels():
     """One kernel launch per op of the compiled program: the fused CAM layer, the TMA slab kernels and the TMA GEMM
     are the paths that run (a geometry or dispatch regression that silently drops to the unfused CAM layer or a

@@ -107,6 +107,9 @@ class CAMPPlus(EngineModule):
         return self._run(x, self.feat_dim, self.embedding_size)
 
 
+L2_HINTS = int(os.environ.get("SPK_L2_HINTS", "3"))       # bit 0: stream the concat reads, bit 1: keep the bottleneck output in L2
+
+
 class _Engine(EngineBase):
     def default_chunks(self, T):
         """(coarse, fine) sub-batch sizes.  Measured on B200 (tools/sweep_chunks.py): launch
@@ -211,9 +214,11 @@ class _Engine(EngineBase):
                 cin = ch + j * G
                 ps, pb = self._bn(p + ".nonlinear1.batchnorm")
                 es, eb = self._bn(p + ".nonlinear2.batchnorm")
+                # L2 hints: the concat buffer streams through (evict_first), the 128-channel bottleneck output is read back
+                # by the CAM layer right away and overwritten by the next layer's: it should never leave the L2
                 prog.op(_lib.OP_CONV, in_buf=xb, in_ld=ld, out_buf=hbuf, out_ld=BNC, H=1, W=T2, Cin=cin, Ho=1, Wo=T2,
                         Cout=BNC, w=self._w1d(p + ".linear1.weight"), pro_scale=ps, pro_shift=pb, pro_relu=1,
-                        epi_scale=es, epi_shift=eb, act=_lib.ACT_RELU)
+                        epi_scale=es, epi_shift=eb, act=_lib.ACT_RELU, reserved=L2_HINTS)
                 c = p + ".cam_layer"
                 # whole CAMLayer as one op: context gate + dilated local conv + gating, written in place
                 # into the block's concat buffer (fused kernel in bf16 mode, gate + gated conv otherwise)

@@ -198,6 +198,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
         if (lane == 0) {
             int stage = 0, sidx = 0;
             uint32_t phase = 0;
+            const uint64_t pol_first = l2_policy_evict_first();
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const long long mt = tile / n_tiles_n;
                 const int nt = (int)(tile - mt * n_tiles_n);
@@ -223,7 +224,8 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                         tma_load_2d(sa + C::kABytes, &wmap, (kh * a.KW + kw) * a.Cin + ch * BLOCK_K, nt * BLOCK_N, land_bar(stage));
                         if (++ch == chunks) { ch = 0; if (++kw == a.KW) { kw = 0; ++kh; } }
                     } else {
-                        tma_load_2d(sa, &amap, kc * BLOCK_K, (int)(mt * BLOCK_M), land_bar(stage));
+                        if (a.l2_flags & 1) tma_load_2d_hint(sa, &amap, kc * BLOCK_K, (int)(mt * BLOCK_M), land_bar(stage), pol_first);
+                        else tma_load_2d(sa, &amap, kc * BLOCK_K, (int)(mt * BLOCK_M), land_bar(stage));
                         tma_load_2d(sa + C::kABytes, &wmap, kc * BLOCK_K, nt * BLOCK_N, land_bar(stage));
                     }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
@@ -373,6 +375,7 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                 for (int j = 0; j < nblk; ++j)
                     tma_load_2d(s_stg + sb * C::kUnitBytes + (uint32_t)j * (BLOCK_M * 128u), &rmap, col0 + 64 * j, row0, rfull_bar(sb));
             };
+            const uint64_t pol_last = l2_policy_evict_last();
             Unit cur{(long long)blockIdx.x, 0u, 0}, pre[2];
             if (has_res)
                 for (uint32_t sb = 0; sb < 2; ++sb) {       // the residual of a buffer's next use is loaded as soon as the buffer is free
@@ -386,8 +389,10 @@ conv_gemm_kernel(const ConvArgs a, const bf16 *__restrict__ pro_scale_bf, const 
                 int row0, col0, nblk;
                 coords(cur, row0, col0, nblk);
                 mbar_wait(gfull_bar(sb), sph);
-                for (int j = 0; j < nblk; ++j)
-                    tma_store_2d(&ymap, col0 + 64 * j, row0, s_stg + sb * C::kUnitBytes + (uint32_t)j * (BLOCK_M * 128u));
+                for (int j = 0; j < nblk; ++j) {
+                    if (a.l2_flags & 2) tma_store_2d_hint(&ymap, col0 + 64 * j, row0, s_stg + sb * C::kUnitBytes + (uint32_t)j * (BLOCK_M * 128u), pol_last);
+                    else tma_store_2d(&ymap, col0 + 64 * j, row0, s_stg + sb * C::kUnitBytes + (uint32_t)j * (BLOCK_M * 128u));
+                }
                 bulk_commit();
                 bulk_wait_read0();          // the unit has been read out of shared memory
                 if (!has_res) mbar_arrive(sfree_bar(sb));

@@ -325,6 +325,7 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                     a.pro_relu = o.pro_relu; a.act = o.act;
                     a.K = o.KH * o.KW * o.Cin;
                     a.M = (long long)n * o.Ho * o.Wo;
+                    a.l2_flags = o.reserved;
                     if (m->precision == SPK_PREC_BF16 && o.pro_scale >= 0) {      // converted at set_program time
                         const __nv_bfloat16 *psb = nullptr, *phb = nullptr;
                         rc = param_bf16(m, o.pro_scale, &psb, s);

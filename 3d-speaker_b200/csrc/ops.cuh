@@ -23,6 +23,7 @@ struct ConvArgs {
     int pad_reflect;      // out-of-range columns mirror (F.pad mode='reflect') instead of reading zero; W axis only
     int gate_additive;    // gate[b, window, n] is ADDED before the activation (per-segment bias) instead of multiplied after
     const void *pro_scale_bf, *pro_shift_bf;   // bf16 copies of pro_scale/pro_shift owned by the model (tensor-core prologue)
+    int l2_flags;         // conv_gemm: bit 0 = load the input evict_first (a stream), bit 1 = store the output evict_last (keep in L2)
 };
 
 // fp32-accumulate CUDA-core implicit GEMM (exact-fp32 mode and odd shapes)

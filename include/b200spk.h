@@ -145,7 +145,8 @@ typedef struct {
     int32_t iaux[4];                       /* CAM_GATE: hidden, seg_len; STATS_POOL: unbiased */
     float   faux[2];                       /* STATS_POOL: eps inside sqrt                    */
     int32_t phase;                         /* 0: runs per fine sub-batch; 1: per coarse sub-batch */
-    int32_t reserved;
+    int32_t reserved;                      /* SPK_OP_CONV, stride-1 1x1 (TMA GEMM): L2 hints, bit 0 = the input is a stream (load
+                                              evict_first), bit 1 = keep the output in L2 for the next op (store evict_last) */
 } spk_op_t;
 
 int     spk_model_create(spk_model_t **out, int precision);

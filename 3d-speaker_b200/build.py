@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "b200spk", "libb200spk.so")
-SOURCES = ["api.cu", "fbank.cu", "conv_simt.cu", "conv_tc2.cu", "conv_gemm.cu", "conv_slab.cu", "conv_slab3.cu", "conv_slab4.cu", "conv_stem.cu", "cam_local.cu", "ecapa_ops.cu", "small_ops.cu", "model.cu", "cluster.cu"]
+SOURCES = ["api.cu", "fbank.cu", "conv_simt.cu", "conv_tc2.cu", "conv_gemm.cu", "conv_f32x3.cu", "conv_slab.cu", "conv_slab3.cu", "conv_slab4.cu", "conv_stem.cu", "cam_local.cu", "ecapa_ops.cu", "small_ops.cu", "model.cu", "cluster.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

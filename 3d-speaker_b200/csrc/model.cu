@@ -27,6 +27,7 @@ struct spk_model {
     std::vector<float *> params;
     std::vector<int64_t> param_n;
     std::vector<__nv_bfloat16 *> params_bf16;   // lazily created for tcgen05 convs
+    std::vector<float *> params_x3;             // fp32 mode: [2][n] TF32 heads / tails of the conv weights (conv_f32x3.cu)
     std::map<int64_t, spk_program> programs;
 };
 
@@ -74,6 +75,22 @@ int param_bf16(spk_model *m, int id, const __nv_bfloat16 **out, cudaStream_t s) 
         m->params_bf16[id] = d;
     }
     *out = m->params_bf16[id];
+    return SPK_OK;
+}
+
+int param_x3(spk_model *m, int id, const float **out, cudaStream_t s) {
+    if (id < 0 || id >= (int)m->params.size()) {
+        set_error("bad parameter id %d", id);
+        return SPK_ERR_INVALID;
+    }
+    if (m->params_x3[id] == nullptr) {
+        float *d = nullptr;
+        SPK_CUDA_OK(cudaMalloc(&d, (size_t)m->param_n[id] * 2 * sizeof(float)));
+        int rc = launch_split_tf32(m->params[id], d, d + m->param_n[id], m->param_n[id], s);
+        if (rc != SPK_OK) return rc;
+        m->params_x3[id] = d;
+    }
+    *out = m->params_x3[id];
     return SPK_OK;
 }
 
@@ -161,6 +178,8 @@ extern "C" int spk_model_destroy(spk_model_t *m) {
     for (float *p : m->params) cudaFree(p);
     for (__nv_bfloat16 *p : m->params_bf16)
         if (p) cudaFree(p);
+    for (float *p : m->params_x3)
+        if (p) cudaFree(p);
     delete m;
     return SPK_OK;
 }
@@ -178,6 +197,7 @@ extern "C" int64_t spk_model_add_param(spk_model_t *m, const float *host, int64_
     m->params.push_back(d);
     m->param_n.push_back(n);
     m->params_bf16.push_back(nullptr);
+    m->params_x3.push_back(nullptr);
     return (int64_t)m->params.size() - 1;
 }
 
@@ -209,6 +229,16 @@ extern "C" int spk_model_set_program(spk_model_t *m, int64_t T, const spk_buf_t 
             rc = param_bf16(m, o.w, &tmp, nullptr);
             if (rc == SPK_OK && o.pro_scale >= 0) rc = param_bf16(m, o.pro_scale, &tmp, nullptr);
             if (rc == SPK_OK && o.pro_shift >= 0) rc = param_bf16(m, o.pro_shift, &tmp, nullptr);
+            if (rc != SPK_OK) return rc;
+        }
+        SPK_CUDA_OK(cudaDeviceSynchronize());
+    }
+    if (m->precision == SPK_PREC_F32) {
+        // TF32 head / tail copies of the conv weights for the 3xTF32 tensor-core path, also finished here
+        const float *tmp = nullptr;
+        for (const spk_op_t &o : p.ops) {
+            if (o.kind != SPK_OP_CONV && o.kind != SPK_OP_CAM_LOCAL) continue;
+            rc = param_x3(m, o.w, &tmp, nullptr);
             if (rc != SPK_OK) return rc;
         }
         SPK_CUDA_OK(cudaDeviceSynchronize());
@@ -407,6 +437,14 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                             a.w = wb;
                             trace_dispatch("tc2_gather", a);
                             rc = launch_conv_tc(a, dt(o.out_buf), dt(o.res_buf), s);
+                        }
+                    } else if (m->precision == SPK_PREC_F32 && conv_f32x3_supported(a, dt(o.in_buf), dt(o.out_buf), dt(o.res_buf))) {
+                        const float *w3 = nullptr;
+                        rc = param_x3(m, o.w, &w3, s);
+                        if (rc == SPK_OK) {
+                            a.w = w3;
+                            trace_dispatch("f32x3", a);
+                            rc = launch_conv_f32x3(a, s);
                         }
                     } else {
                         a.w = param(m, o.w);

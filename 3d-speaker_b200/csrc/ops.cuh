@@ -35,6 +35,11 @@ int launch_conv_tc2(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_
 // TMA-fed GEMM for stride-1 1x1 convs with the BN-ReLU prologue applied in shared memory (conv_gemm.cu)
 bool conv_gemm_supported(const ConvArgs &a, int in_dtype);
 int launch_conv_gemm(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s);
+// fp32 precision mode on the tensor cores (conv_f32x3.cu): 3xTF32 split products, fp32 in / out / residual.
+// a.w = [2][Cout][K] fp32, the TF32 heads then tails of the packed weights (launch_split_tf32)
+bool conv_f32x3_supported(const ConvArgs &a, int in_dtype, int out_dtype, int res_dtype);
+int launch_conv_f32x3(const ConvArgs &a, cudaStream_t s);
+int launch_split_tf32(const float *src, float *hi, float *lo, long long n, cudaStream_t s);
 // slab kernel for the Cin=Cout=32 2-D convs of the CAM++ head (conv_slab.cu)
 bool conv_slab_supported(const ConvArgs &a, int in_dtype, int out_dtype, int res_dtype);
 int launch_conv_slab(const ConvArgs &a, cudaStream_t s);

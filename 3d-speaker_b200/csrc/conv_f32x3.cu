@@ -2,7 +2,7 @@
 // without leaving tcgen05.  The exact-fp32 mode used to run every conv on CUDA cores (conv_simt.cu, ~1.3 % of the bf16
 // rate); here the fp32 operands are split into a TF32 head and a TF32 tail,
 //
-//   x = x_hi + x_lo,  x_hi = rna_tf32(x),  x_lo = x - x_hi  (exact in fp32)
+//   x = x_hi + x_lo,  x_hi = x rounded to TF32,  x_lo = x - x_hi  (exact in fp32)
 //   D = A_lo * W_hi + A_hi * W_lo + A_hi * W_hi              (the A_lo * W_lo term, 2^-22 relative, is dropped)
 //
 // and the three products are accumulated in the fp32 TMEM accumulator by kind::tf32 MMAs.  The result carries ~21
@@ -12,10 +12,12 @@
 // Data path: activations stay fp32 [M, ld] channels-last in HBM.  The TMA producer lands a 128 x 32 fp32 tile of A
 // (plain 2-D tiles for stride-1 1x1 convs, TMA IM2COL loads of 32 channels x 128 pixels per filter tap otherwise, as
 // in conv_gemm.cu) together with the matching tiles of W_hi and W_lo (split once per model at spk_model_set_program).
-// Four transform warps apply the optional BN-ReLU prologue in fp32 and split the landed A tile in shared memory
-// (head in place, tail into a second tile of the stage); one thread then issues 12 MMAs (3 products x 4 K-steps of 8)
-// per 32-deep stage.  Epilogue as in conv_gemm.cu's register path (folded BN, residual, CAM gate, activation, ECAPA's
-// post-affine), two groups of four warps.
+// Transform warps (thread = tile row = TMEM lane) apply the optional BN-ReLU prologue in fp32, split the landed row and
+// store head and tail to TENSOR MEMORY (tcgen05.st); one thread then issues 12 MMAs (3 products x 4 K-steps of 8) per
+// 32-deep stage with A taken from TMEM.  Keeping the split tiles out of shared memory matters: with head and tail
+// written back to shared memory and re-read by every MMA the kernel moved 132 KB (N = 32) to 192 KB (N = 128) of
+// shared-memory traffic per stage - 1000-1500 cycles at 128 B/clk against 200-770 cycles of tensor-core work.
+// Epilogue as in conv_gemm.cu's register path (folded BN, residual, CAM gate, activation, ECAPA's post-affine).
 //
 // Reference ops served: every nn.Conv1d / nn.Conv2d of the fp32 eval forward of CAM++ (speakerlab/models/campplus/
 // layers.py, DTDNN.py), ERes2Net / ERes2NetV2 (speakerlab/models/eres2net/) and ECAPA-TDNN (speakerlab/models/
@@ -38,7 +40,8 @@ using namespace tc;
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;        // fp32 elements per stage = one 128-byte swizzled row
 constexpr int UMMA_K = 8;          // kind::tf32
-constexpr int kThreads = 448;      // 0 TMA, 1 MMA, 2-5 split/prologue, 6-9 and 10-13 epilogue groups
+// warps: 0 and 15 TMA (activation / weight tiles), 1 and 14 MMA issue (alternate chunks), 2-5 split/prologue, 6-9 drain/epilogue, 10-13 second drain group (N = 128: one column half each) or
+// second split group (N <= 64: alternate stages)
 constexpr int kXformThreads = 128;
 constexpr int kEpilogueThreads = 128;
 
@@ -49,6 +52,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// A (the split tile) from tensor memory: lane = row, one 32-bit column per K element
+__device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap *map, int c, int w, int h, int n, uint16_t off_w,
                                                    uint16_t off_h, uint32_t bar) {
     asm volatile(
@@ -61,30 +79,49 @@ constexpr uint32_t kSw128Hi = (1024u >> 4) | (1u << 14) | (2u << 29);
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
+// wait of a role with slack (drain, split): back off between polls so the spinning lanes leave the issue slots to the
+// warps that have work - the kernel is issue-bound (about 2000 warp instructions per 32-deep stage at N = 32)
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (ns) __nanosleep(ns);
+        if (++spins > kSpinLimit) __trap();
+    }
+}
 __device__ __forceinline__ float tf32_head(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
 
+// debug aid: per-stage role timestamps of CTA 0 (SPK_F32X3_DBG=1), read back by spk_debug_f32x3_timeline
+__device__ long long g_x3_ts[256 * 8];
+#define X3_TS(idx, slot) do { if (dbg && blockIdx.x == 0 && (idx) >= dbg_from && (idx) < dbg_from + 256 && (threadIdx.x & 31) == 0) g_x3_ts[((idx) - dbg_from) * 8 + (slot)] = clock64(); } while (0)
+
 template <int BLOCK_N> struct Cfg3 {
-    static constexpr int kABytes = BLOCK_M * BLOCK_K * 4;       // one of the two A tiles (head, tail)
-    static constexpr int kBBytes = BLOCK_N * BLOCK_K * 4;       // one of the two W tiles
-    static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-    static constexpr int kStagesFit = (227 * 1024 - 2048) / kStageBytes;
-    static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
-    static constexpr int kTxBytes = kABytes + 2 * kBBytes;      // what the TMA unit lands per stage
-    static constexpr int kAccBufs = 4;                          // TMEM accumulator ring: chunk partial sums waiting for their drain
-    static constexpr int kTmemCols = kAccBufs * BLOCK_N;
-    static_assert(kTmemCols <= 512 && kTmemCols >= 32, "accumulator ring does not fit tensor memory");
+    static constexpr int kABytes = BLOCK_M * BLOCK_K * 4;       // the landed fp32 A tile
+    static constexpr int kBBytes = BLOCK_N * BLOCK_K * 4;       // one of the two W tiles (heads, tails)
+    static constexpr int kStageBytes = kABytes + 2 * kBBytes;
+    static constexpr int kStagesFit = ((227 * 1024 - 2048) / kStageBytes) & ~1;      // even: see kXformGroups
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+    static constexpr int kXformGroups = BLOCK_N <= 64 ? 2 : 1;  // split groups on alternate stages (short MMA phases need both)
+    static constexpr int kDrainGroups = BLOCK_N <= 64 ? 1 : 2;  // drain threads keep <= 64 running sums each
+    static constexpr int kThreads = 512;                        // warp 14: second MMA issuer, warp 15: weight-tile producer
+    static constexpr int kSlots = 4;                            // TMEM ring of split A tiles: 32 head + 32 tail columns each
+    static constexpr int kSlotCols = 2 * BLOCK_K;
+    static constexpr int kAccBufs = BLOCK_N <= 64 ? 4 : 2;      // TMEM accumulator ring: chunk partial sums waiting for their drain
+    static constexpr int kAccCols = kAccBufs * BLOCK_N;
+    static constexpr int kTmemNeed = kAccCols + kSlots * kSlotCols;
+    static constexpr int kTmemCols = kTmemNeed <= 256 ? 256 : 512;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
-    static_assert(kStages >= 2, "stage ring too short");
+    static_assert(kStages >= 2 && kStages % 2 == 0 && kTmemNeed <= 512, "ring sizes");
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(Cfg3<BLOCK_N>::kThreads, 1)
 conv_f32x3_kernel(const ConvArgs a, int n_tiles_n, long long n_tiles, const __grid_constant__ CUtensorMap amap,
-                  const __grid_constant__ CUtensorMap whmap, const __grid_constant__ CUtensorMap wlmap, int im2col, int chunk_stages) {
+                  const __grid_constant__ CUtensorMap whmap, const __grid_constant__ CUtensorMap wlmap, int im2col, int chunk_stages, unsigned relax_ns, int dbg) {
+    const long long dbg_from = 512;          // skip the ramp
     using C = Cfg3<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -96,7 +133,8 @@ conv_f32x3_kernel(const ConvArgs a, int n_tiles_n, long long n_tiles, const __gr
     auto empty_bar = [&](int s) { return bar0 + 8u * (2 * C::kStages + s); };
     auto accf_bar = [&](int b) { return bar0 + 8u * (3 * C::kStages + b); };
     auto acce_bar = [&](int b) { return bar0 + 8u * (3 * C::kStages + C::kAccBufs + b); };
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + 3 * C::kStages + 2 * C::kAccBufs);
+    auto tfree_bar = [&](int t) { return bar0 + 8u * (3 * C::kStages + 2 * C::kAccBufs + t); };      // split slot t read by its MMAs
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + 3 * C::kStages + 2 * C::kAccBufs + C::kSlots);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -109,8 +147,9 @@ conv_f32x3_kernel(const ConvArgs a, int n_tiles_n, long long n_tiles, const __gr
         }
         for (int b = 0; b < C::kAccBufs; ++b) {
             mbar_init(accf_bar(b), 1);
-            mbar_init(acce_bar(b), 2 * kEpilogueThreads);      // both drain groups read every chunk
+            mbar_init(acce_bar(b), C::kDrainGroups * kEpilogueThreads);      // every drain group reads every chunk
         }
+        for (int t = 0; t < C::kSlots; ++t) mbar_init(tfree_bar(t), 1);
         fence_barrier_init();
         prefetch_tmap(&amap);
         prefetch_tmap(&whmap);
@@ -125,16 +164,21 @@ conv_f32x3_kernel(const ConvArgs a, int n_tiles_n, long long n_tiles, const __gr
     const int nk = im2col ? a.KH * a.KW * chunks : (a.K + BLOCK_K - 1) / BLOCK_K;
     pdl_wait();
 
-    if (warp == 0) {
-        // =========================== TMA producer ===========================
+    if (warp == 0 || warp == 15) {
+        // =========================== TMA producers ===========================
+        // Issuing a tensor load costs the issuing thread a few hundred cycles; with the activation tile and both weight
+        // tiles issued by one thread the producer loop (~780 cycles per stage) paced the whole kernel.  Warp 0 issues the
+        // activation tiles (and arms the stage barrier with the stage's full byte count), warp 15 the weight tiles.
         if (lane == 0) {
+            const bool act = warp == 0;
             int stage = 0;
+            long long sidx = 0;
             uint32_t phase = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const long long mt = tile / n_tiles_n;
                 const int nt = (int)(tile - mt * n_tiles_n);
                 int bw = 0, bh = 0, bn = 0, kh = 0, kw = 0, ch = 0;
-                if (im2col) {          // base position (filter tap 0, 0) of the tile's first output pixel
+                if (im2col && act) {          // base position (filter tap 0, 0) of the tile's first output pixel
                     const long long m0 = mt * BLOCK_M;
                     const int hw = a.Ho * a.Wo;
                     bn = (int)(m0 / hw);
@@ -143,93 +187,124 @@ conv_f32x3_kernel(const ConvArgs a, int n_tiles_n, long long n_tiles, const __gr
                     bh = p * a.sh - a.ph;
                     bw = (r - p * a.Wo) * a.sw - a.pw;
                 }
-                for (int kc = 0; kc < nk; ++kc) {
+                for (int kc = 0; kc < nk; ++kc, ++sidx) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
+                    X3_TS(sidx, act ? 1 : 2);
                     const uint32_t sa = base + stage * C::kStageBytes;
-                    const uint32_t sbh = sa + 2 * C::kABytes, sbl = sbh + C::kBBytes;
-                    mbar_arrive_expect_tx(land_bar(stage), C::kTxBytes);
-                    int kcol;
-                    if (im2col) {
-                        tma_load_im2col_4d(sa, &amap, a.in_choff + ch * BLOCK_K, bw, bh, bn, (uint16_t)(kw * a.dw), (uint16_t)(kh * a.dh),
-                                           land_bar(stage));
-                        kcol = (kh * a.KW + kw) * a.Cin + ch * BLOCK_K;
-                        if (++ch == chunks) { ch = 0; if (++kw == a.KW) { kw = 0; ++kh; } }
+                    if (act) {
+                        mbar_arrive_expect_tx(land_bar(stage), C::kStageBytes);
+                        if (im2col) {
+                            tma_load_im2col_4d(sa, &amap, a.in_choff + ch * BLOCK_K, bw, bh, bn, (uint16_t)(kw * a.dw), (uint16_t)(kh * a.dh),
+                                               land_bar(stage));
+                            if (++ch == chunks) { ch = 0; if (++kw == a.KW) { kw = 0; ++kh; } }
+                        } else {
+                            tma_load_2d(sa, &amap, kc * BLOCK_K, (int)(mt * BLOCK_M), land_bar(stage));
+                        }
                     } else {
-                        tma_load_2d(sa, &amap, kc * BLOCK_K, (int)(mt * BLOCK_M), land_bar(stage));
-                        kcol = kc * BLOCK_K;
+                        // weight column of this stage: tap-major packed K ((kh * KW + kw) * Cin + channel chunk)
+                        int kcol = kc * BLOCK_K;
+                        if (im2col) {
+                            kcol = (kh * a.KW + kw) * a.Cin + ch * BLOCK_K;
+                            if (++ch == chunks) { ch = 0; if (++kw == a.KW) { kw = 0; ++kh; } }
+                        }
+                        const uint32_t sbh = sa + C::kABytes, sbl = sbh + C::kBBytes;
+                        tma_load_2d(sbh, &whmap, kcol, nt * BLOCK_N, land_bar(stage));
+                        tma_load_2d(sbl, &wlmap, kcol, nt * BLOCK_N, land_bar(stage));
                     }
-                    tma_load_2d(sbh, &whmap, kcol, nt * BLOCK_N, land_bar(stage));
-                    tma_load_2d(sbl, &wlmap, kcol, nt * BLOCK_N, land_bar(stage));
                     if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
+    } else if (warp == 1 || warp == 14) {
+        // =========================== MMA issuers ===========================
+        // One issuing thread runs a serial chain of ~150 dependent instructions per stage (two barrier waits, fences, twelve
+        // descriptor builds + MMAs, three commits): ~1000 cycles measured, five times the tensor-core time of an N = 32
+        // stage.  Chunks accumulate in different TMEM buffers and are independent, so two warps issue alternate chunks.
         constexpr uint32_t idesc = make_idesc_tf32(BLOCK_N);
-        int stage = 0;
+        const uint32_t mine_parity = warp == 1 ? 0u : 1u;
+        int stage = 0, slot = 0, in_chunk = 0;
+        long long sidx = 0;
         uint32_t phase = 0, gc = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int kc = 0; kc < nk; ++kc) {
-                const int in_chunk = kc % chunk_stages;
-                const uint32_t buf = gc % C::kAccBufs, acc_phase = (gc / C::kAccBufs) & 1u;
-                if (in_chunk == 0) {               // a new chunk starts on the other TMEM buffer once it has been drained
-                    mbar_wait(acce_bar(buf), acc_phase ^ 1u);
-                    tc_fence_after();
-                }
-                const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
-                mbar_wait(ready_bar(stage), phase);
-                tc_fence_after();
+            for (int kc = 0; kc < nk; ++kc, ++sidx) {
                 const bool last = in_chunk == chunk_stages - 1 || kc == nk - 1;
-                if (elect_one()) {
-                    const uint32_t sa = base + stage * C::kStageBytes;
-                    const uint32_t ah = sw128_lo(sa), al = sw128_lo(sa + C::kABytes);
-                    const uint32_t bh = sw128_lo(sa + 2 * C::kABytes), bl = sw128_lo(sa + 2 * C::kABytes + C::kBBytes);
-                    // small terms first, then the head product
+                if ((gc & 1u) == mine_parity) {
+                    const uint32_t buf = gc % C::kAccBufs, acc_phase = (gc / C::kAccBufs) & 1u;
+                    X3_TS(sidx, 0);
+                    if (in_chunk == 0) {               // a new chunk starts on the next TMEM buffer once that has been drained
+                        mbar_wait(acce_bar(buf), acc_phase ^ 1u);
+                        X3_TS(sidx, 7);
+                        tc_fence_after();
+                    }
+                    const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+                    X3_TS(sidx, 4);
+                    mbar_wait(ready_bar(stage), phase);          // split tile in TMEM (and with it the stage's W tiles landed)
+                    tc_fence_after();
+                    X3_TS(sidx, 5);
+                    if (elect_one()) {
+                        const uint32_t sa = base + stage * C::kStageBytes;
+                        const uint32_t bh = sw128_lo(sa + C::kABytes), bl = sw128_lo(sa + C::kABytes + C::kBBytes);
+                        const uint32_t th = tmem_base + C::kAccCols + slot * C::kSlotCols, tl = th + BLOCK_K;
+                        // small terms first, then the head product
 #pragma unroll
-                    for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-                        umma_tf32(d_tmem, desc64(al + 2u * kk, kSw128Hi), desc64(bh + 2u * kk, kSw128Hi), idesc, (in_chunk | kk) != 0 ? 1u : 0u);
+                        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+                            umma_tf32_ta(d_tmem, tl + kk * UMMA_K, desc64(bh + 2u * kk, kSw128Hi), idesc, (in_chunk | kk) != 0 ? 1u : 0u);
 #pragma unroll
-                    for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-                        umma_tf32(d_tmem, desc64(ah + 2u * kk, kSw128Hi), desc64(bl + 2u * kk, kSw128Hi), idesc, 1u);
+                        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+                            umma_tf32_ta(d_tmem, th + kk * UMMA_K, desc64(bl + 2u * kk, kSw128Hi), idesc, 1u);
 #pragma unroll
-                    for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-                        umma_tf32(d_tmem, desc64(ah + 2u * kk, kSw128Hi), desc64(bh + 2u * kk, kSw128Hi), idesc, 1u);
-                    umma_commit(empty_bar(stage));
-                    if (last) umma_commit(accf_bar(buf));
+                        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+                            umma_tf32_ta(d_tmem, th + kk * UMMA_K, desc64(bh + 2u * kk, kSw128Hi), idesc, 1u);
+                        umma_commit(empty_bar(stage));
+                        umma_commit(tfree_bar(slot));
+                        if (last) umma_commit(accf_bar(buf));
+                    }
+                    __syncwarp();
+                    X3_TS(sidx, 6);
                 }
-                __syncwarp();
-                if (last) ++gc;
+                if (last) { ++gc; in_chunk = 0; } else ++in_chunk;
                 if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                if (++slot == C::kSlots) slot = 0;
             }
         }
-    } else if (warp < 6) {
-        // =========================== split (+ BN-ReLU prologue) ===========================
-        const int t = threadIdx.x - 64;            // 0..127
-        const int j = t & 7, r0 = t >> 3;          // 16-byte column j (4 channels), rows r0 + 16*i
-        const uint32_t sw_off = (uint32_t)((r0 >> 3) * 1024 + (r0 & 7) * 128 + ((j ^ (r0 & 7)) << 4));
+    } else if (warp < 6 || (warp >= 10 && C::kXformGroups == 2)) {
+        // =========================== split (+ BN-ReLU prologue) into tensor memory ===========================
+        // thread = tile row = TMEM lane: read the row's eight 16-byte chunks (128B-swizzled), apply the prologue, split,
+        // store 32 heads and 32 tails as columns of this lane in the stage's TMEM slot.  With two groups (N <= 64) the
+        // groups take alternate stage uses; rings are even, so a stage / slot always belongs to the same group.
+        const int q = warp & 3, r = q * 32 + lane;
+        const int grp = warp >= 10 ? 1 : 0;
+        const uint32_t row_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128), x7 = (uint32_t)(r & 7);
         const bool has_pro = a.pro_scale != nullptr, relu = a.pro_relu != 0;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int kc = 0; kc < nk; ++kc) {
-                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), h4 = s4;
-                if (has_pro) {                     // plain GEMM only: K = Cin, a multiple of 4
-                    const int c = kc * BLOCK_K + j * 4;
-                    if (c < a.K) {
-                        s4 = __ldg(reinterpret_cast<const float4 *>(a.pro_scale + c));
-                        h4 = __ldg(reinterpret_cast<const float4 *>(a.pro_shift + c));
-                    }
-                }
-                mbar_wait(land_bar(stage), phase);
-                const uint32_t sa = base + stage * C::kStageBytes + sw_off;
-                uint4 v[8];
+        const long long my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const long long n_uses = my_tiles * nk;
+        uint32_t coff[8];                              // the row's eight 16-byte chunks, swizzled
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = lds16(sa + i * 2048);
+        for (int j = 0; j < 8; ++j) coff[j] = row_off + (((uint32_t)j ^ x7) << 4);
+        // ring positions advance by the group count (no 64-bit divisions in the loop: this role is instruction-bound)
+        int stage = grp, slot = grp, kc = grp % nk;
+        uint32_t phase = 0, tphase = 0;
+        for (long long sidx = grp; sidx < n_uses; sidx += C::kXformGroups) {
+            mbar_wait_relaxed(tfree_bar(slot), tphase ^ 1u, relax_ns);          // the MMAs of the slot's previous tile are done
+            tc_fence_after();
+            mbar_wait_relaxed(land_bar(stage), phase, relax_ns);
+            const uint32_t sa = base + stage * C::kStageBytes;
+            const uint32_t taddr = tmem_base + C::kAccCols + slot * C::kSlotCols + ((uint32_t)(q * 32) << 16);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float x[4] = {__uint_as_float(v[i].x), __uint_as_float(v[i].y), __uint_as_float(v[i].z), __uint_as_float(v[i].w)};
-                    if (has_pro) {
+            for (int half = 0; half < 2; ++half) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = half * 4 + jj;
+                    const uint4 v = lds16(sa + coff[j]);
+                    float x[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
+                    if (has_pro) {                 // plain GEMM only: K = Cin, a multiple of 4; warp-uniform (broadcast) loads
+                        const int c = kc * BLOCK_K + j * 4;
+                        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), h4 = s4;
+                        if (c < a.K) {
+                            s4 = __ldg(reinterpret_cast<const float4 *>(a.pro_scale + c));
+                            h4 = __ldg(reinterpret_cast<const float4 *>(a.pro_shift + c));
+                        }
                         x[0] = fmaf(x[0], s4.x, h4.x); x[1] = fmaf(x[1], s4.y, h4.y);
                         x[2] = fmaf(x[2], s4.z, h4.z); x[3] = fmaf(x[3], s4.w, h4.w);
                         if (relu) {
@@ -237,29 +312,38 @@ conv_f32x3_kernel(const ConvArgs a, int n_tiles_n, long long n_tiles, const __gr
                             for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
                         }
                     }
-                    float hi[4], lo[4];
+                    // head = the value rounded to TF32 with integer ops (add half an ulp, mask: two instructions where
+                    // cvt.rna.tf32 compiles to four with its Inf/NaN guard - this role is instruction-bound; plain truncation,
+                    // one instruction, leaves a -2.3e-7 bias because the MMA then truncates a same-signed 13-bit tail)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        hi[e] = tf32_head(x[e]);
-                        lo[e] = x[e] - hi[e];
+                        const uint32_t h = (__float_as_uint(x[e]) + 0x1000u) & 0xFFFFE000u;
+                        hi[4 * jj + e] = h;
+                        lo[4 * jj + e] = __float_as_uint(x[e] - __uint_as_float(h));
                     }
-                    sts16(sa + i * 2048, make_uint4(__float_as_uint(hi[0]), __float_as_uint(hi[1]), __float_as_uint(hi[2]), __float_as_uint(hi[3])));
-                    sts16(sa + C::kABytes + i * 2048,
-                          make_uint4(__float_as_uint(lo[0]), __float_as_uint(lo[1]), __float_as_uint(lo[2]), __float_as_uint(lo[3])));
                 }
-                fence_proxy_async();
-                mbar_arrive(ready_bar(stage));
-                if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+                tmem_st16(taddr + 16 * half, hi);
+                tmem_st16(taddr + BLOCK_K + 16 * half, lo);
             }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(ready_bar(stage));
+            if (q == 2) X3_TS(sidx, 3);
+            stage += C::kXformGroups;
+            if (stage >= C::kStages) { stage -= C::kStages; phase ^= 1u; }
+            slot += C::kXformGroups;
+            if (slot >= C::kSlots) { slot -= C::kSlots; tphase ^= 1u; }
+            kc += C::kXformGroups;
+            while (kc >= nk) kc -= nk;
         }
     } else {
-        // =========================== drain + epilogue (two groups, one column half each) ===========================
+        // =========================== drain + epilogue ===========================
         // The tensor core's accumulator adds with truncation: a K-long sum kept in TMEM shrinks towards zero by ~K/8 x 3
         // x 2^-26 relative (measured: -5.9e-6 at K = 992), coherently from layer to layer.  So TMEM only ever holds the
         // partial sum of one chunk (`chunk_stages` stages of 32; small products issued first); these warps drain every
         // chunk into fp32 REGISTER sums with round-to-nearest adds while the MMAs of the next chunk fill the other
         // TMEM buffer (Ootomo & Yokota's remedy for tensor-core accumulation), and run the conv epilogue from registers.
-        constexpr int kCols = BLOCK_N / 2;            // columns per thread (group g: [g * kCols, (g + 1) * kCols))
+        constexpr int kCols = BLOCK_N / C::kDrainGroups;      // columns per thread (group g: [g * kCols, (g + 1) * kCols))
         constexpr int kPieces = kCols / 16;
         const int q = warp & 3;
         const int row = q * 32 + lane;
@@ -278,7 +362,7 @@ conv_f32x3_kernel(const ConvArgs a, int n_tiles_n, long long n_tiles, const __gr
             float acc[kCols];
             for (int c = 0; c < n_chunks; ++c, ++gc) {
                 const uint32_t buf = gc % C::kAccBufs, acc_phase = (gc / C::kAccBufs) & 1u;
-                mbar_wait(accf_bar(buf), acc_phase);
+                mbar_wait_relaxed(accf_bar(buf), acc_phase, relax_ns);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + buf * BLOCK_N + grp * kCols + ((uint32_t)(q * 32) << 16);
 #pragma unroll
@@ -291,6 +375,7 @@ conv_f32x3_kernel(const ConvArgs a, int n_tiles_n, long long n_tiles, const __gr
                 }
                 tc_fence_before();
                 mbar_arrive(acce_bar(buf));
+
             }
             if (m >= a.M) continue;
             const float *grow = nullptr;
@@ -467,7 +552,10 @@ int launch_one(const ConvArgs &a, cudaStream_t s) {
     const long long grid = std::min<long long>(tiles, sm_count());
     // stages (of 32 K elements) summed inside TMEM before a drain: 1 = fp32-class sums, larger = fewer drains
     static const int chunk_stages = [] { const char *e = getenv("SPK_F32X3_CHUNK"); return e && atoi(e) > 0 ? atoi(e) : 1; }();
-    const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), (size_t)C::kSmemBytes, s, a, ntn, tiles, amap, whmap, wlmap, im2col, chunk_stages);
+    static const int dbg_k = [] { const char *e = getenv("SPK_F32X3_DBG"); return e ? atoi(e) : 0; }();      // timeline of launches with this K
+    const int dbg = dbg_k != 0 && dbg_k == a.K;
+    static const unsigned relax_ns = [] { const char *e = getenv("SPK_F32X3_RELAX"); return e ? (unsigned)atoi(e) : 0u; }();
+    const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3(C::kThreads), (size_t)C::kSmemBytes, s, a, ntn, tiles, amap, whmap, wlmap, im2col, chunk_stages, relax_ns, dbg);
     if (le != cudaSuccess) {
         set_error("conv_f32x3_kernel launch failed: %s", cudaGetErrorString(le));
         return SPK_ERR_CUDA;
@@ -515,3 +603,8 @@ int launch_split_tf32(const float *src, float *hi, float *lo, long long n, cudaS
 }
 
 }  // namespace spk
+
+// debug aid (not part of the ABI)
+extern "C" int spk_debug_f32x3_timeline(long long *dst) {
+    return cudaMemcpyFromSymbol(dst, spk::g_x3_ts, sizeof(long long) * 256 * 8) == cudaSuccess ? 0 : -1;
+}

@@ -13,6 +13,8 @@ Extra blocks under ``"configs"`` (rank 0 prints everything on ONE JSON line):
   fbank_1024x3s            BASELINE config 2: the front end alone, HBM roofline
   eres2netv2_*_4096x3s     BASELINE config 3: both ERes2NetV2 variants, bf16, device-resident and end to end, CPU subsample
   campplus_batch64         the reference call sites' own batch size (infer_diarization.py:629-635)
+  campplus_fp32_mode       the same network in the fp32 precision mode (3xTF32 tensor-core convs, csrc/conv_f32x3.cu):
+                           embeddings/s and how far the bf16 embeddings are from it
   ecapa_bulk_100h          BASELINE config 5: 36,000 x 10 s chunks sharded over the ranks, per-recording mean,
                            1 M trial pairs scored
   diarization              BASELINE config 4: a synthetic 1-hour meeting end to end, stage breakdown, oracle check of
@@ -43,7 +45,7 @@ EMB = 512                         # CAM++ 7.2 M variant (BASELINE config 0)
 GFLOP_PER_SEG = 1.588             # minimal conv/linear FLOPs per 1.5 s segment
 FBANK_BYTES_PER_SEG = 4 * N_SAMPLES + 4 * T_FRAMES * 80
 WEIGHT_SEED = 7
-ALL_LEGS = ("fbank", "eres", "batch64", "ecapa", "meeting")
+ALL_LEGS = ("fbank", "eres", "batch64", "fp32", "ecapa", "meeting")
 METRIC = "CAM++ embeddings/sec (1.5 s windows)"
 
 
@@ -409,6 +411,45 @@ def leg_batch64(cx, model, fb):
     return out
 
 
+# ============================================================================= fp32 precision mode
+def leg_fp32(cx, model_bf16, fb):
+    """precision="fp32": every conv as a 3xTF32 split product on the tensor cores with fp32 register sums
+    (csrc/conv_f32x3.cu) - the mode whose embeddings match the reference's CPU fp32 forward to 1e-4 rel-L2 (tests/)."""
+    import b200spk
+    n, bs = 2048, 1024
+    m32 = b200spk.CAMPPlus(embedding_size=EMB, precision="fp32")
+    m32.load_state_dict(model_bf16.state_dict())
+    m32 = m32.to(cx.dev).eval()
+    wav = torch.from_numpy(make_windows(n, seed=4)).to(cx.dev)
+    with torch.no_grad():
+        feats = fb.batch(wav)
+
+        def run(m):
+            return torch.cat([m(feats[i:i + bs]) for i in range(0, n, bs)])
+        for _ in range(2):
+            e32 = run(m32)
+        torch.cuda.synchronize()
+        l0 = b200spk.lib().spk_launch_count()
+        t0, t1 = ev(), ev()
+        t0.record()
+        reps = 3
+        for _ in range(reps):
+            e32 = run(m32)
+        t1.record()
+        torch.cuda.synchronize()
+        dt = t0.elapsed_time(t1) / reps * 1e-3
+        launches = int((b200spk.lib().spk_launch_count() - l0) // reps)
+        e16 = run(model_bf16)
+    cos = torch.nn.functional.cosine_similarity(e16.float(), e32.float(), dim=1)
+    out = {"embeddings_per_s": n / dt, "ms_per_step": dt * 1e3, "gpu_launches": launches, "dtype": "f32 (3xTF32 products, fp32 sums)",
+           "tflops_fp32_equivalent": GFLOP_PER_SEG * n / dt / 1e3,
+           "bf16_vs_fp32_mode": {"cos_min": float(cos.min()), "rel_l2": float((e16 - e32).norm() / e32.norm())},
+           "workload": "CAM++ 512-d, %d x 1.5 s segments, feature matrices resident in HBM, forward calls of %d" % (n, bs)}
+    del m32
+    torch.cuda.empty_cache()
+    return out
+
+
 # ============================================================================= config 5: bulk ECAPA + scoring
 def leg_ecapa(cx):
     """100 h of synthetic audio = 4,000 recordings of 90 s -> 36,000 x 10 s chunks (infer_sv_batch.py:388-412),
@@ -737,6 +778,8 @@ def main():
             configs["fbank_1024x3s"] = leg_fbank(cx)
         if "batch64" in legs:
             configs["campplus_batch64"] = leg_batch64(cx, model, fb)
+        if "fp32" in legs and args.precision == "bf16":
+            configs["campplus_fp32_mode"] = leg_fp32(cx, model, fb)
     del wav_dev, emb_dev
     torch.cuda.empty_cache()
     if world == 1 and "eres" in legs:

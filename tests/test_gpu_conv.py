@@ -156,6 +156,51 @@ def test_conv_plain(case, precision):
     _check(y, ref, 2e-5)      # same rounded operands, fp32 accumulate
 
 
+@pytest.mark.parametrize("K", [128, 992, 4096])
+def test_fp32_mode_tensor_core_sum_error_does_not_grow_with_k(K):
+    """conv_f32x3.cu: 3xTF32 split products with the chunk partial sums drained into fp32 registers.  The error against
+    float64 is flat in K (1.4e-7 .. 2.5e-7 rel-L2 measured) and carries no shrink towards zero: sums left in the TMEM
+    accumulator, which truncates, measured -5.9e-6 mean signed relative error at K = 992 and -2.5e-5 at K = 4096."""
+    g = torch.Generator().manual_seed(K)
+    x = torch.randn(4, 1, 74, K, generator=g)
+    w = torch.randn(128, 1, 1, K, generator=g) / math.sqrt(K)
+    y, ref = run_conv(x, w, precision="fp32")
+    rel = ((y - ref).norm() / ref.norm()).item()
+    signed = (((y - ref) * ref.sign()).sum() / ref.abs().sum()).item()
+    assert rel <= 5e-7, rel
+    assert abs(signed) <= 2e-7, signed
+
+
+@pytest.mark.parametrize("Cin,Cout,B", [(352, 128, 40), (96, 32, 24), (1024, 128, 8), (64, 256, 12), (160, 48, 3)])
+def test_fp32_mode_gemm_prologue_many_tiles(Cin, Cout, B):
+    """The fp32-mode GEMM over many M tiles per CTA (ring and accumulator-ring wrap-around), fp32 BN-ReLU prologue on the
+    landed tile, partial last K stage, two N tiles (Cout = 256) and a Cout that is not a tile width."""
+    g = torch.Generator().manual_seed(Cin + Cout)
+    W = 74
+    x = torch.randn(B, 1, W, Cin, generator=g)
+    w = torch.randn(Cout, 1, 1, Cin, generator=g) / math.sqrt(Cin)
+    pro = (torch.rand(Cin, generator=g) + 0.5, 0.1 * torch.randn(Cin, generator=g))
+    epi = (torch.rand(Cout, generator=g) + 0.5, 0.1 * torch.randn(Cout, generator=g))
+    y, ref = run_conv(x, w, pro=pro, epi=epi, act=_lib.ACT_RELU, precision="fp32")
+    _check(y, ref, 2e-6)
+
+
+def test_fp32_mode_runs_on_the_tensor_cores():
+    """SPK_TRACE_DISPATCH=1 names the kernel family of every conv op: in the fp32 precision mode all convs of CAM++
+    except the per-segment dense layer go through conv_f32x3 (none through the CUDA-core implicit GEMM)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    env = dict(os.environ, SPK_TRACE_DISPATCH="1", SPK_GRAPH_MAX_BATCH="0")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "run_forward.py"), "--segments", "4", "--precision", "fp32", "--iters", "1"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    fams = [ln.split()[2] for ln in r.stderr.splitlines() if ln.startswith("[spk dispatch]")]
+    assert fams.count("f32x3") >= 100, (fams.count("f32x3"), sorted(set(fams)))
+    assert fams.count("simt") <= 2, fams.count("simt")          # the dense layer (routed to the split-K linear kernel)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_conv_prologue_epilogue_relu(precision):
     g = torch.Generator().manual_seed(1)

@@ -17,7 +17,8 @@ for r in rows:
         continue
     k = (cur, int(r[0]))
     a = agg.get(k, (0, 0))
-    agg[k] = (a[0] + int(r[ismp] or 0), a[1] + int(r[iex] or 0))
+    num = lambda v: int(v) if v.strip().isdigit() else 0
+    agg[k] = (a[0] + num(r[ismp]), a[1] + num(r[iex]))
 tot, totex = sum(v[0] for v in agg.values()), sum(v[1] for v in agg.values())
 src = open(src_path).read().split("\n")
 name = os.path.basename(src_path)

@@ -1,27 +1,37 @@
 // fp32-accurate convolution GEMM on the tensor cores (3xTF32): the "fp32" precision mode of the embedding networks
-// without leaving tcgen05.  The exact-fp32 mode used to run every conv on CUDA cores (conv_simt.cu, ~1.3 % of the bf16
-// rate); here the fp32 operands are split into a TF32 head and a TF32 tail,
+// without leaving tcgen05.  That mode used to run every conv on CUDA cores (conv_simt.cu); here the fp32 operands are
+// split into a TF32 head and a TF32 tail,
 //
 //   x = x_hi + x_lo,  x_hi = x rounded to TF32,  x_lo = x - x_hi  (exact in fp32)
 //   D = A_lo * W_hi + A_hi * W_lo + A_hi * W_hi              (the A_lo * W_lo term, 2^-22 relative, is dropped)
 //
-// and the three products are accumulated in the fp32 TMEM accumulator by kind::tf32 MMAs.  The result carries ~21
-// mantissa bits per product (the MMA reads the top 19 bits of the tails), i.e. fp32-class: the networks' embeddings
-// stay within 1e-5 rel-L2 of the CPU reference where the literal tolerance is 1e-4.
+// and the three products go through kind::tf32 MMAs.  The TMEM accumulator ADDS WITH TRUNCATION (measured: a K-long sum
+// left in TMEM comes out -5.9e-6 relative at K = 992, -2.5e-5 at K = 4096, always towards zero, coherent from layer to
+// layer), so TMEM only ever holds the partial sum of one 32-deep chunk: drain warps add every chunk into fp32 REGISTER
+// sums with round-to-nearest (Ootomo & Yokota's remedy) while the next chunks fill the other buffers of a TMEM ring.
+// Result: 1.4e-7 .. 2.5e-7 rel-L2 against float64 at any K - tighter than the CUDA-core fp32 sum (2e-7 .. 6e-7) - and
+// embeddings within 1.1e-6 rel-L2 of the CUDA-core path where the literal tolerance against the reference is 1e-4.
 //
-// Data path: activations stay fp32 [M, ld] channels-last in HBM.  The TMA producer lands a 128 x 32 fp32 tile of A
-// (plain 2-D tiles for stride-1 1x1 convs, TMA IM2COL loads of 32 channels x 128 pixels per filter tap otherwise, as
-// in conv_gemm.cu) together with the matching tiles of W_hi and W_lo (split once per model at spk_model_set_program).
-// Transform warps (thread = tile row = TMEM lane) apply the optional BN-ReLU prologue in fp32, split the landed row and
-// store head and tail to TENSOR MEMORY (tcgen05.st); one thread then issues 12 MMAs (3 products x 4 K-steps of 8) per
-// 32-deep stage with A taken from TMEM.  Keeping the split tiles out of shared memory matters: with head and tail
-// written back to shared memory and re-read by every MMA the kernel moved 132 KB (N = 32) to 192 KB (N = 128) of
-// shared-memory traffic per stage - 1000-1500 cycles at 128 B/clk against 200-770 cycles of tensor-core work.
-// Epilogue as in conv_gemm.cu's register path (folded BN, residual, CAM gate, activation, ECAPA's post-affine).
+// Data path: activations stay fp32 [M, ld] channels-last in HBM.  TMA lands a 128 x 32 fp32 tile of A (plain 2-D tiles
+// for stride-1 1x1 convs, TMA IM2COL loads of 32 channels x 128 pixels per filter tap otherwise, as in conv_gemm.cu)
+// and the matching tiles of W_hi and W_lo (split once per model at spk_model_set_program).  Split warps (thread = tile
+// row = TMEM lane) apply the optional BN-ReLU prologue in fp32, split the landed row and store head and tail to
+// TENSOR MEMORY (tcgen05.st); the MMAs take A from there.  (With head and tail written back to shared memory and
+// re-read by every MMA a stage moved 132 KB (N = 32) to 192 KB (N = 128) through shared memory: 1000-1500 cycles at
+// 128 B/clk against 200-770 cycles of tensor-core work.)  Epilogue from the register sums: folded BN, residual, CAM
+// gate, activation, ECAPA's post-affine.
+//
+// What bounds it (role timeline, SPK_F32X3_DBG + tools/x3_timeline.py): the single-thread roles.  One thread issuing
+// the 12 MMAs, three commits and two barrier waits of a stage runs a ~150-instruction dependent chain, ~1000 cycles
+// per stage; one thread issuing the three tensor loads of a stage ~780 cycles.  Hence two MMA-issuing warps (chunks
+// are independent accumulators: alternate chunks), two producer warps (activation / weight tiles), two split groups
+// on alternate stages for N <= 64, and a division-free split loop with integer TF32 rounding (cvt.rna.tf32 compiles
+// to four instructions).  First FCM conv of CAM++ (32 -> 32 channels, 3x3, 256 segments): 448 -> 313 us.
 //
 // Reference ops served: every nn.Conv1d / nn.Conv2d of the fp32 eval forward of CAM++ (speakerlab/models/campplus/
 // layers.py, DTDNN.py), ERes2Net / ERes2NetV2 (speakerlab/models/eres2net/) and ECAPA-TDNN (speakerlab/models/
-// ecapa_tdnn/ECAPA_TDNN.py) with zero padding; the per-segment dense layers stay on the split-K linear kernel.
+// ecapa_tdnn/ECAPA_TDNN.py); reflect-padded Conv1d's run zero-padded here and have their edge positions recomputed by
+// reflect_edge_fix_kernel (small_ops.cu); the per-segment dense layers stay on the split-K linear kernel.
 #include <cstdlib>
 #include <cuda.h>
 
@@ -45,13 +55,6 @@ constexpr int UMMA_K = 8;          // kind::tf32
 constexpr int kXformThreads = 128;
 constexpr int kEpilogueThreads = 128;
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
 // A (the split tile) from tensor memory: lane = row, one 32-bit column per K element
 __device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -78,15 +81,6 @@ constexpr uint32_t kSw128Hi = (1024u >> 4) | (1u << 14) | (2u << 29);
 // fp32 accumulate, TF32 x TF32 (format code 2), K-major both, M = 128
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-}
-// wait of a role with slack (drain, split): back off between polls so the spinning lanes leave the issue slots to the
-// warps that have work - the kernel is issue-bound (about 2000 warp instructions per 32-deep stage at N = 32)
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (ns) __nanosleep(ns);
-        if (++spins > kSpinLimit) __trap();
-    }
 }
 __device__ __forceinline__ float tf32_head(float x) {
     uint32_t r;
@@ -120,7 +114,7 @@ template <int BLOCK_N> struct Cfg3 {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(Cfg3<BLOCK_N>::kThreads, 1)
 conv_f32x3_kernel(const ConvArgs a, int n_tiles_n, long long n_tiles, const __grid_constant__ CUtensorMap amap,
-                  const __grid_constant__ CUtensorMap whmap, const __grid_constant__ CUtensorMap wlmap, int im2col, int chunk_stages, unsigned relax_ns, int dbg) {
+                  const __grid_constant__ CUtensorMap whmap, const __grid_constant__ CUtensorMap wlmap, int im2col, int chunk_stages, int dbg) {
     const long long dbg_from = 512;          // skip the ramp
     using C = Cfg3<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
@@ -285,9 +279,9 @@ conv_f32x3_kernel(const ConvArgs a, int n_tiles_n, long long n_tiles, const __gr
         int stage = grp, slot = grp, kc = grp % nk;
         uint32_t phase = 0, tphase = 0;
         for (long long sidx = grp; sidx < n_uses; sidx += C::kXformGroups) {
-            mbar_wait_relaxed(tfree_bar(slot), tphase ^ 1u, relax_ns);          // the MMAs of the slot's previous tile are done
+            mbar_wait(tfree_bar(slot), tphase ^ 1u);          // the MMAs of the slot's previous tile are done
             tc_fence_after();
-            mbar_wait_relaxed(land_bar(stage), phase, relax_ns);
+            mbar_wait(land_bar(stage), phase);
             const uint32_t sa = base + stage * C::kStageBytes;
             const uint32_t taddr = tmem_base + C::kAccCols + slot * C::kSlotCols + ((uint32_t)(q * 32) << 16);
 #pragma unroll
@@ -362,7 +356,7 @@ conv_f32x3_kernel(const ConvArgs a, int n_tiles_n, long long n_tiles, const __gr
             float acc[kCols];
             for (int c = 0; c < n_chunks; ++c, ++gc) {
                 const uint32_t buf = gc % C::kAccBufs, acc_phase = (gc / C::kAccBufs) & 1u;
-                mbar_wait_relaxed(accf_bar(buf), acc_phase, relax_ns);
+                mbar_wait(accf_bar(buf), acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + buf * BLOCK_N + grp * kCols + ((uint32_t)(q * 32) << 16);
 #pragma unroll
@@ -554,8 +548,7 @@ int launch_one(const ConvArgs &a, cudaStream_t s) {
     static const int chunk_stages = [] { const char *e = getenv("SPK_F32X3_CHUNK"); return e && atoi(e) > 0 ? atoi(e) : 1; }();
     static const int dbg_k = [] { const char *e = getenv("SPK_F32X3_DBG"); return e ? atoi(e) : 0; }();      // timeline of launches with this K
     const int dbg = dbg_k != 0 && dbg_k == a.K;
-    static const unsigned relax_ns = [] { const char *e = getenv("SPK_F32X3_RELAX"); return e ? (unsigned)atoi(e) : 0u; }();
-    const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3(C::kThreads), (size_t)C::kSmemBytes, s, a, ntn, tiles, amap, whmap, wlmap, im2col, chunk_stages, relax_ns, dbg);
+    const cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3(C::kThreads), (size_t)C::kSmemBytes, s, a, ntn, tiles, amap, whmap, wlmap, im2col, chunk_stages, dbg);
     if (le != cudaSuccess) {
         set_error("conv_f32x3_kernel launch failed: %s", cudaGetErrorString(le));
         return SPK_ERR_CUDA;
@@ -569,9 +562,10 @@ bool conv_f32x3_supported(const ConvArgs &a, int in_dtype, int out_dtype, int re
     static const bool off = [] { const char *e = getenv("SPK_NO_F32X3"); return e && e[0] == '1'; }();
     if (off) return false;
     if (in_dtype != SPK_DT_F32 || out_dtype != SPK_DT_F32 || (a.res != nullptr && res_dtype != SPK_DT_F32)) return false;
-    // per-segment dense layers (one output pixel per segment) and reflect padding stay on CUDA cores.  The rule must not
+    // per-segment dense layers (one output pixel per segment) stay on CUDA cores.  The rule must not
     // depend on the batch size: a segment's embedding may not change with the sub-batch it travels in
-    if (a.Ho * a.Wo < 8 || a.pad_reflect) return false;
+    if (a.Ho * a.Wo < 8) return false;
+    if (a.pad_reflect && !reflect_edge_fix_supported(a)) return false;      // zero-padded conv here, then the edge fix (model.cu)
     if (a.Cin % 4 != 0 || a.in_ld % 4 != 0 || a.in_choff % 4 != 0 || a.K % 4 != 0) return false;
     if (a.Cout % 16 != 0 || a.out_ld % 4 != 0 || a.out_choff % 4 != 0) return false;
     if (a.res != nullptr && (a.res_ld % 4 != 0 || a.res_choff % 4 != 0 || (reinterpret_cast<uintptr_t>(a.res) & 15) != 0)) return false;

@@ -869,7 +869,7 @@ int launch_conv_gemm_main(const ConvArgs &a, int out_dtype, int res_dtype, cudaS
 int launch_conv_gemm(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s) {
     const int rc = launch_conv_gemm_main(a, out_dtype, res_dtype, s);
     if (rc != SPK_OK || !a.pad_reflect || a.M == 0) return rc;
-    return launch_reflect_edge_fix(a, out_dtype, s);
+    return launch_reflect_edge_fix(a, SPK_DT_BF16, out_dtype, s);
 }
 
 int launch_conv_gemm_main(const ConvArgs &a, int out_dtype, int res_dtype, cudaStream_t s) {

@@ -445,6 +445,11 @@ extern "C" int spk_model_forward(spk_model_t *m, int64_t T, const float *feats, 
                             a.w = w3;
                             trace_dispatch("f32x3", a);
                             rc = launch_conv_f32x3(a, s);
+                            if (rc == SPK_OK && a.pad_reflect && a.M > 0) {      // mirrored taps at the segment ends, fp32 weights
+                                ConvArgs f = a;
+                                f.w = param(m, o.w);
+                                rc = launch_reflect_edge_fix(f, SPK_DT_F32, SPK_DT_F32, s);
+                            }
                         }
                     } else {
                         a.w = param(m, o.w);

@@ -130,7 +130,7 @@ int launch_asp_pool(const AspPoolArgs &a, int l_dtype, int x_dtype, cudaStream_t
 bool linear_supported(const ConvArgs &a, int in_dtype, int out_dtype);
 int launch_linear(const ConvArgs &a, int in_dtype, int out_dtype, cudaStream_t s);
 bool reflect_edge_fix_supported(const ConvArgs &a);           // 1-D 'same' conv with reflect padding: zero-padded conv + edge fix
-int launch_reflect_edge_fix(const ConvArgs &a, int out_dtype, cudaStream_t s);     // a.w: bf16 [Cout][KW][Cin]
+int launch_reflect_edge_fix(const ConvArgs &a, int in_dtype, int out_dtype, cudaStream_t s);     // a.w: [Cout][KW][Cin] in the activation dtype
 bool se_gate_cluster_supported(const CamGateArgs &a, int in_dtype);
 int launch_se_gate_cluster(const CamGateArgs &a, int in_dtype, cudaStream_t s);
 bool stats_pool_sliced_supported(const StatsPoolArgs &a);

@@ -339,20 +339,36 @@ asp_pool_online_kernel(const AspPoolArgs a) {
 // (every thread reads the same element: broadcast), each thread walks its own weight row once for all edge positions.
 constexpr int kFixMaxEdge = 8;
 
-template <typename TOut>
+__device__ __forceinline__ void load8_f32(const bf16 *p, float (&v)[8]) {
+    const uint4 raw = *reinterpret_cast<const uint4 *>(p);
+    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w4[q]);
+        v[2 * q] = __low2float(h);
+        v[2 * q + 1] = __high2float(h);
+    }
+}
+__device__ __forceinline__ void load8_f32(const float *p, float (&v)[8]) {
+    const float4 lo = *reinterpret_cast<const float4 *>(p), hi = *reinterpret_cast<const float4 *>(p + 4);
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+
+// TIn: type of the activations AND of the weights (bf16 mode / fp32 mode)
+template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 reflect_edge_fix_kernel(const ConvArgs a) {
     extern __shared__ float xs[];                       // [rows][Cin]
     const int b = blockIdx.x, right = blockIdx.y;
     const int E = a.pw, span = (a.KW - 1) * a.dw + 1;    // edge positions per end, input rows they touch
     const int row0 = right ? a.W - span : 0;
-    const bf16 *x = static_cast<const bf16 *>(a.x) + ((long long)b * a.W + row0) * a.in_ld + a.in_choff;
+    const TIn *x = static_cast<const TIn *>(a.x) + ((long long)b * a.W + row0) * a.in_ld + a.in_choff;
     for (int idx = threadIdx.x; idx < span * a.Cin; idx += blockDim.x) {
         const int r = idx / a.Cin, c = idx - r * a.Cin;
-        xs[idx] = __bfloat162float(x[(long long)r * a.in_ld + c]);
+        xs[idx] = to_f32(x[(long long)r * a.in_ld + c]);
     }
     __syncthreads();
-    const bf16 *w = static_cast<const bf16 *>(a.w);      // [Cout][KW][Cin]
+    const TIn *w = static_cast<const TIn *>(a.w);        // [Cout][KW][Cin]
     TOut *y = static_cast<TOut *>(a.y);
     for (int n = threadIdx.x; n < a.Cout; n += blockDim.x) {
         float acc[kFixMaxEdge];
@@ -367,21 +383,15 @@ reflect_edge_fix_kernel(const ConvArgs a) {
                 wi = wi < 0 ? -wi : (wi >= a.W ? 2 * (a.W - 1) - wi : wi);
                 rows[e] = (wi - row0) * a.Cin;
             }
-            const bf16 *wr = w + ((long long)n * a.KW + j) * a.Cin;
+            const TIn *wr = w + ((long long)n * a.KW + j) * a.Cin;
             for (int c = 0; c < a.Cin; c += 8) {
-                const uint4 raw = *reinterpret_cast<const uint4 *>(wr + c);
-                const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+                float wv[8];
+                load8_f32(wr + c, wv);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w4[q]);
-                    const float w0 = __low2float(h), w1 = __high2float(h);
+                for (int q = 0; q < 8; ++q) {
 #pragma unroll
-                    for (int e = 0; e < kFixMaxEdge; ++e) {
-                        if (e < E) {
-                            acc[e] = fmaf(w0, xs[rows[e] + c + 2 * q], acc[e]);
-                            acc[e] = fmaf(w1, xs[rows[e] + c + 2 * q + 1], acc[e]);
-                        }
-                    }
+                    for (int e = 0; e < kFixMaxEdge; ++e)
+                        if (e < E) acc[e] = fmaf(wv[q], xs[rows[e] + c + q], acc[e]);
                 }
             }
         }
@@ -452,12 +462,18 @@ bool reflect_edge_fix_supported(const ConvArgs &a) {
     return (size_t)((a.KW - 1) * a.dw + 1) * a.Cin * sizeof(float) <= 48 * 1024;
 }
 
-int launch_reflect_edge_fix(const ConvArgs &a, int out_dtype, cudaStream_t s) {
+int launch_reflect_edge_fix(const ConvArgs &a, int in_dtype, int out_dtype, cudaStream_t s) {
     if (a.B == 0) return SPK_OK;
     const size_t sh = (size_t)((a.KW - 1) * a.dw + 1) * a.Cin * sizeof(float);
     const dim3 grid((unsigned)a.B, 2);
-    if (out_dtype == SPK_DT_BF16) reflect_edge_fix_kernel<bf16><<<grid, 256, sh, s>>>(a);
-    else reflect_edge_fix_kernel<float><<<grid, 256, sh, s>>>(a);
+    if (in_dtype == SPK_DT_F32) {
+        if (out_dtype != SPK_DT_F32) {
+            set_error("reflect_edge_fix: fp32 activations take an fp32 output");
+            return SPK_ERR_UNSUPPORTED;
+        }
+        reflect_edge_fix_kernel<float, float><<<grid, 256, sh, s>>>(a);
+    } else if (out_dtype == SPK_DT_BF16) reflect_edge_fix_kernel<bf16, bf16><<<grid, 256, sh, s>>>(a);
+    else reflect_edge_fix_kernel<bf16, float><<<grid, 256, sh, s>>>(a);
     return check_launch("reflect_edge_fix_kernel");
 }
 

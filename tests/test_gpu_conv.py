@@ -260,19 +260,23 @@ def test_slab4_residual_c64_parts():
     _check(y, ref, 1e-4)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
 @pytest.mark.parametrize("Cin,Cout,K,dil,T", [(128, 128, 3, 3, 200), (128, 128, 3, 4, 998), (80, 256, 5, 1, 148), (128, 128, 3, 2, 131)])
-def test_reflect_padded_conv1d_im2col_plus_edge_fix(Cin, Cout, K, dil, T):
-    """ECAPA TDNNBlock (ECAPA_TDNN.py:49-77): Conv1d with reflect padding -> ReLU -> BN.  The tensor-core path runs the
-    zero-padded conv with TMA im2col loads and recomputes the positions next to the segment ends with mirrored taps."""
+def test_reflect_padded_conv1d_im2col_plus_edge_fix(Cin, Cout, K, dil, T, precision):
+    """ECAPA TDNNBlock (ECAPA_TDNN.py:49-77): Conv1d with reflect padding -> ReLU -> BN.  The tensor-core paths (bf16
+    conv_gemm, fp32-mode conv_f32x3) run the zero-padded conv with TMA im2col loads and recompute the positions next to
+    the segment ends with mirrored taps."""
     g = torch.Generator().manual_seed(9)
     B, pad = 5, dil * (K - 1) // 2
+    bf = precision == "bf16"
+    AD = _lib.DT_BF16 if bf else _lib.DT_F32
     x = torch.randn(B, 1, T, Cin, generator=g)
     w = torch.randn(Cout, 1, K, Cin, generator=g) / math.sqrt(K * Cin)
     ps, pb = torch.rand(Cout, generator=g) + 0.5, 0.1 * torch.randn(Cout, generator=g)
-    model = Model(_lib.PREC_BF16, "cuda:0")
+    model = Model(_lib.PREC_BF16 if bf else _lib.PREC_F32, "cuda:0")
     prog = Program(T * Cin, T * Cout)
-    xin = prog.buf("x", T * Cin, _lib.DT_BF16)
-    ybuf = prog.buf("y", T * Cout, _lib.DT_BF16)
+    xin = prog.buf("x", T * Cin, AD)
+    ybuf = prog.buf("y", T * Cout, AD)
     prog.op(_lib.OP_CONV, in_buf=0, in_ld=Cin, out_buf=xin, out_ld=Cin, H=1, W=T, Cin=Cin, Ho=1, Wo=T, Cout=Cin,
             w=model.param(torch.eye(Cin).reshape(Cin, 1, 1, Cin)))
     prog.op(_lib.OP_CONV, in_buf=xin, in_ld=Cin, out_buf=ybuf, out_ld=Cout, H=1, W=T, Cin=Cin, Ho=1, Wo=T, Cout=Cout, KH=1, KW=K,
@@ -282,12 +286,19 @@ def test_reflect_padded_conv1d_im2col_plus_edge_fix(Cin, Cout, K, dil, T):
     model.set_program(1, prog)
     y = model.forward(1, x.reshape(B, -1).cuda().contiguous(), T * Cout, B).cpu().view(B, T, Cout).double()
     model.close()
-    xr = _bf16_round(x)[:, 0].permute(0, 2, 1).double()                      # [B, Cin, T]
-    wr = _bf16_round(w)[:, 0].permute(0, 2, 1).double()                      # [Cout, Cin, K]
+    rnd = _bf16_round if bf else (lambda t: t)
+    xr = rnd(x)[:, 0].permute(0, 2, 1).double()                      # [B, Cin, T]
+    wr = rnd(w)[:, 0].permute(0, 2, 1).double()                      # [Cout, Cin, K]
     ref = F.conv1d(F.pad(xr, (pad, pad), mode="reflect"), wr, dilation=dil).permute(0, 2, 1)
-    ref = _bf16_round((torch.relu(ref) * ps.double() + pb.double()).float()).double()
-    err = (y - ref).abs()
-    assert bool((err <= 1e-4 * ref.abs().max() + 2.0 ** -7 * ref.abs()).all()), (err.max().item(), err.argmax().item())
+    ref = torch.relu(ref) * ps.double() + pb.double()
+    err = (y - ref if not bf else y - _bf16_round(ref.float()).double()).abs()
+    if bf:
+        ref = _bf16_round(ref.float()).double()
+        assert bool((err <= 1e-4 * ref.abs().max() + 2.0 ** -7 * ref.abs()).all()), (err.max().item(), err.argmax().item())
+    else:
+        assert bool((err <= 2e-6 * ref.abs().max()).all()), (err.max().item(), err.argmax().item())
+        edge = err[:, list(range(pad)) + list(range(T - pad, T))]
+        assert edge.max().item() <= 2e-6 * ref.abs().max().item()
 
 
 @pytest.mark.parametrize("T,F,B", [(148, 80, 5), (61, 80, 3), (254, 80, 2), (148, 24, 4)])

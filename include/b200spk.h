@@ -94,6 +94,11 @@ int spk_fbank_host_f32(const float *wav, int64_t B, int64_t n_samples, int64_t w
  */
 typedef struct spk_model spk_model_t;
 
+/* SPK_PREC_BF16: bf16 activations and weights, fp32 accumulation (tcgen05 kind::f16).
+ * SPK_PREC_F32:  fp32 activations and weights; convs run as 3xTF32 split products on the tensor cores
+ *                with fp32 register sums (csrc/conv_f32x3.cu): the result is fp32-accurate (about 2e-7 per
+ *                conv against float64), the mode whose embeddings match the reference's CPU forward to
+ *                1e-4 rel-L2.  SPK_NO_F32X3=1 in the environment moves them to CUDA cores. */
 enum { SPK_PREC_F32 = 0, SPK_PREC_BF16 = 1 };
 enum { SPK_DT_F32 = 0, SPK_DT_BF16 = 1 };
 

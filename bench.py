@@ -188,6 +188,9 @@ class Ctx:
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
+            # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout when the
+            # box sets NCCL_DEBUG) goes to stderr
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=self.dev)
             self.dist = dist
         self.pk = peaks()

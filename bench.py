@@ -39,6 +39,26 @@ for p in (ROOT, os.path.join(ROOT, "3d-speaker_b200")):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# stdout carries exactly ONE JSON line.  Native libraries write there too (NCCL prints "NCCL version ..." with printf
+# when the box sets NCCL_DEBUG): keep a private handle on the real stdout for the result line and point file descriptor
+# 1 at stderr for everything else.
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 N_SAMPLES = 24000                 # 1.5 s @ 16 kHz  (infer_diarization.py:285 chunk_dur)
 T_FRAMES = 148
 EMB = 512                         # CAM++ 7.2 M variant (BASELINE config 0)
@@ -188,9 +208,6 @@ class Ctx:
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
-            # stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ...", printed to stdout when the
-            # box sets NCCL_DEBUG) goes to stderr
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=self.dev)
             self.dist = dist
         self.pk = peaks()
@@ -280,7 +297,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "embeddings/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "embeddings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ============================================================================= config 2: fbank alone
@@ -664,6 +681,7 @@ def leg_meeting(cx):
 
 # ============================================================================= GPU arm
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -834,7 +852,7 @@ def main():
             line["diarization"] = meeting
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_campplus(args.cpu_seconds)
-        print(json.dumps(line))
+        emit(line)
     if cx.dist is not None:
         cx.dist.barrier()
         cx.dist.destroy_process_group()

@@ -168,3 +168,19 @@ def test_bulk_chunk_table_is_circle_pad_then_slice():
             assert np.array_equal(buf[idx], padded[q * cs:(q + 1) * cs])
             row += 1
     assert row == len(starts)
+
+
+def test_bench_stdout_carries_only_the_result_line():
+    """bench.py's contract is ONE JSON line on stdout.  Native libraries print there too (NCCL's version banner at
+    N > 1), so bench.main() points file descriptor 1 at stderr and keeps a private handle for the result."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench.claim_stdout(); "
+            "os.write(1, b'banner from a native library\\n'); print('python-level noise'); bench.emit({'value': 1})" % root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1000:]
+    assert r.stdout == json.dumps({"value": 1}) + "\n"
+    assert "banner from a native library" in r.stderr and "python-level noise" in r.stderr
